@@ -1,0 +1,554 @@
+// ftsgemm.cu -- host side of libftsgemm.so: the C ABI declared in include/ftsgemm.h.
+//
+// Owns: the kernel-variant table (reference: kernel/ft_sgemm/sgemm.cu:235-237 + code_gen/main.py:8-16), the id ->
+// launch dispatch (reference: sgemm.cu:110-199, 256-430), TMA tensor-map construction, the encode pre-pass launch,
+// the cuBLAS comparator rows (sgemm.cu:108,198,260), the non-fused ABFT baseline
+// (include/baseline_ft_sgemm.cuh:1-33) and the device-side comparator (utils/utils.cu:61-77).
+// There is NO CPU fallback: without an sm_100 device every compute entry point returns FTSGEMM_ERR_NO_DEVICE.
+#include <cublas_v2.h>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "../../include/ftsgemm.h"
+#include "ftsgemm_kernel.cuh"
+
+namespace {
+
+using namespace ftsgemm;
+
+// ------------------------------------------------------------------------------------------- variant table
+struct Variant {
+  ftsgemm_kernel_info info;
+  int bn;  // CTA tile N of the tcgen05 kernel (0 for library rows)
+};
+
+// Reference tiles from code_gen/main.py:8-16; sm_100a tiles: UMMA M is 128 (cta_group::1), so the reference's
+// "tall" (128x32) and "huge" (128x128) shapes are literal, the others map to the nearest UMMA-legal shape with
+// the same role (fewer/larger CTAs).  tile_k = K extent of one shared-memory stage (4 UMMA k-steps of 8).
+const Variant kVariants[] = {
+    {{0, "cublas", 0, 0, 0, 0, 0, 0, 0, 0}, 0},
+    {{1, "kernel_sgemm_small", 0, 1, 16, 16, 16, 128, 32, 32}, 32},
+    {{2, "kernel_sgemm_medium", 0, 1, 32, 32, 8, 128, 64, 32}, 64},
+    {{3, "kernel_sgemm_large", 0, 1, 64, 64, 8, 128, 128, 32}, 128},
+    {{4, "kernel_sgemm_tall", 0, 1, 128, 32, 8, 128, 32, 32}, 32},
+    {{5, "kernel_sgemm_wide", 0, 1, 32, 128, 8, 128, 256, 32}, 256},
+    {{6, "kernel_sgemm_huge", 0, 1, 128, 128, 8, 128, 128, 32}, 128},
+    {{7, "cublas_tf32", 0, 0, 0, 0, 0, 0, 0, 0}, 0},
+    {{10, "abft_baseline", 1, 2, 0, 0, 256, 0, 0, 256}, 0},
+    {{11, "abft_kernel_small", 1, 1, 16, 16, 16, 128, 32, 32}, 32},
+    {{12, "abft_kernel_medium", 1, 1, 32, 32, 8, 128, 64, 32}, 64},
+    {{13, "abft_kernel_large", 1, 1, 64, 64, 8, 128, 128, 32}, 128},
+    {{14, "abft_kernel_tall", 1, 1, 128, 32, 8, 128, 32, 32}, 32},
+    {{15, "abft_kernel_wide", 1, 1, 32, 128, 8, 128, 256, 32}, 256},
+    {{16, "abft_kernel_huge", 1, 1, 128, 128, 8, 128, 128, 32}, 128},
+    {{21, "kernel_sgemm_giant", 0, 1, 0, 0, 0, 128, 256, 32}, 256},
+    {{30, "abft_baseline_tf32", 1, 2, 0, 0, 256, 0, 0, 256}, 0},
+    {{31, "abft_kernel_giant", 1, 1, 0, 0, 0, 128, 256, 32}, 256},
+};
+constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+
+const Variant *find_variant(int id) {
+  if (id == 8 || id == 9) id = 0;  // reference: ids outside the table run plain cuBLAS (sgemm.cu:197-199)
+  for (int i = 0; i < kNumVariants; ++i)
+    if (kVariants[i].info.id == id) return &kVariants[i];
+  return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------- debug knobs
+std::mutex g_dbg_mu;
+std::map<std::string, long long> g_dbg;
+long long dbg(const char *key, long long dflt) {
+  std::lock_guard<std::mutex> lk(g_dbg_mu);
+  auto it = g_dbg.find(key);
+  return it == g_dbg.end() ? dflt : it->second;
+}
+
+// ------------------------------------------------------------------------------------------- handle
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct ftsgemm_handle_s {
+  int device = 0;
+  int num_sms = 0;
+  cublasHandle_t cublas = nullptr;
+  EncodeTiledFn encode_tiled = nullptr;
+  DeviceStats *d_stats = nullptr;
+  float *d_chk = nullptr;       // checksum panel [K][ntiles*32]
+  size_t chk_bytes = 0;
+  const float *chk_for_b = nullptr;  // B pointer / shape the panel was encoded from
+  int chk_n = 0, chk_k = 0, chk_bn = 0;
+  float *d_aux = nullptr;       // baseline vectors
+  size_t aux_floats = 0;
+  float *d_stage[3] = {nullptr, nullptr, nullptr};  // run_host staging A, B, C
+  size_t stage_bytes[3] = {0, 0, 0};
+  double *d_verify = nullptr;   // {first_bad (as long long), num, den}
+  cudaStream_t last_stream = nullptr;
+  int last_cuda_error = 0;
+};
+
+namespace {
+
+#define FT_CUDA(h, call)                                   \
+  do {                                                     \
+    cudaError_t e__ = (call);                              \
+    if (e__ != cudaSuccess) {                              \
+      if (h) (h)->last_cuda_error = static_cast<int>(e__); \
+      return FTSGEMM_ERR_CUDA;                             \
+    }                                                      \
+  } while (0)
+
+#define FT_CUBLAS(h, call)                                 \
+  do {                                                     \
+    cublasStatus_t s__ = (call);                           \
+    if (s__ != CUBLAS_STATUS_SUCCESS) {                    \
+      if (h) (h)->last_cuda_error = static_cast<int>(s__); \
+      return FTSGEMM_ERR_CUBLAS;                           \
+    }                                                      \
+  } while (0)
+
+int make_tmap_2d(ftsgemm_handle_t h, CUtensorMap *tm, const float *base, uint64_t inner, uint64_t outer,
+                 uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_elems * sizeof(float)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw =
+      static_cast<CUtensorMapSwizzle>(dbg("tma_swizzle", static_cast<long long>(CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)));
+  CUresult r = h->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    h->last_cuda_error = static_cast<int>(r);
+    return FTSGEMM_ERR_CUDA;
+  }
+  return FTSGEMM_OK;
+}
+
+template <int BN, bool FT>
+int launch_tc(ftsgemm_handle_t h, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
+              const KernelParams &p, cudaStream_t stream) {
+  using Cfg = TileCfg<BN, FT>;
+  auto kern = ftsgemm_tc_kernel<BN, FT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FT_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  int grid = static_cast<int>(dbg("grid", 0));
+  if (grid <= 0) grid = h->num_sms;
+  if (grid > num_tiles) grid = num_tiles;
+  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
+  FT_CUDA(h, cudaGetLastError());
+  return FTSGEMM_OK;
+}
+
+int ensure_chk(ftsgemm_handle_t h, size_t bytes, cudaStream_t stream) {
+  if (h->chk_bytes >= bytes) return FTSGEMM_OK;
+  if (h->d_chk) FT_CUDA(h, cudaFree(h->d_chk));
+  h->d_chk = nullptr;
+  h->chk_bytes = 0;
+  h->chk_for_b = nullptr;
+  FT_CUDA(h, cudaMalloc(&h->d_chk, bytes));  // fully overwritten by every encode pass (unused columns as zeros)
+  (void)stream;
+  h->chk_bytes = bytes;
+  return FTSGEMM_OK;
+}
+
+int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const float *dA, const float *dB, float *dC,
+           float alpha, float beta, const ftsgemm_opts &o, cudaStream_t stream) {
+  const int BN = v.bn;
+  const bool ft = v.info.fault_tolerant != 0;
+  if ((M % 4) || (N % 4)) return FTSGEMM_ERR_UNSUPPORTED;  // TMA global strides must be multiples of 16 bytes
+  if ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB) | reinterpret_cast<uintptr_t>(dC)) & 15)
+    return FTSGEMM_ERR_INVALID_ARG;
+
+  KernelParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.C = dC; p.ldc = M;
+  p.alpha = alpha; p.beta = beta;
+  p.tiles_m = (M + kBM - 1) / kBM;
+  p.tiles_n = (N + BN - 1) / BN;
+  long long g = dbg("group_n", 0);
+  p.group_n = g > 0 ? static_cast<int>(g) : (2048 / BN > 0 ? 2048 / BN : 1);
+  if (p.group_n > p.tiles_n) p.group_n = p.tiles_n;
+  // MN-major fp32 operands: 128B swizzle with 32B atoms.  One TMA box = 32 (M|N) x 32 (K) floats = 32 rows of
+  // 128 bytes, so successive M|N atoms are kBK*128 bytes apart (LBO), successive groups of 4 K-rows 512 bytes (SBO),
+  // and one UMMA k-step (8 K-rows) advances the start address by 1024 bytes.
+  p.lbo_bytes = static_cast<unsigned>(dbg("lbo", kBK * 128));
+  p.sbo_bytes = static_cast<unsigned>(dbg("sbo", 512));
+  p.layout_type = static_cast<unsigned>(dbg("layout_type", 1));
+  p.kstep_bytes = static_cast<unsigned>(dbg("kstep", 1024));
+  p.tau_abs = o.tau_abs > 0 ? o.tau_abs : 1e-3f;
+  p.tau_rel = o.tau_rel > 0 ? o.tau_rel : 2e-5f;
+  p.detect_only = o.detect_only;
+  p.inject_mode = ft ? o.inject_mode : 0;
+  p.selftest_value = o.selftest_value;
+  p.selftest_row = o.selftest_row & (kBM - 1);
+  p.selftest_col = o.selftest_col % BN;
+  p.n_faults = o.n_faults < 0 ? 0 : (o.n_faults > kMaxFaults ? kMaxFaults : o.n_faults);
+  for (int i = 0; i < p.n_faults; ++i) {
+    p.faults[i].row = o.faults[i].row;
+    p.faults[i].col = o.faults[i].col;
+    p.faults[i].mode = o.faults[i].mode;
+    p.faults[i].add_value = o.faults[i].add_value;
+    p.faults[i].xor_mask = o.faults[i].xor_mask;
+  }
+  p.stats = h->d_stats;
+
+  CUtensorMap tmA, tmB, tmC;
+  int rc = make_tmap_2d(h, &tmA, dA, M, K, M, kAtomMN, kBK);
+  if (rc) return rc;
+  rc = make_tmap_2d(h, &tmB, dB, N, K, N, kAtomMN, kBK);
+  if (rc) return rc;
+  tmC = tmB;
+  if (ft) {
+    const int chk_ld = p.tiles_n * kAtomMN;
+    rc = ensure_chk(h, static_cast<size_t>(K) * chk_ld * sizeof(float), stream);
+    if (rc) return rc;
+    const bool reuse = o.reuse_b_checksums && h->chk_for_b == dB && h->chk_n == N && h->chk_k == K && h->chk_bn == BN;
+    if (!reuse) {
+      dim3 grid(p.tiles_n, (K + kEncWarps * kEncKPerWarp - 1) / (kEncWarps * kEncKPerWarp));
+      encode_b_kernel<<<grid, kEncWarps * 32, 0, stream>>>(dB, N, K, N, BN, h->d_chk, chk_ld,
+                                                           static_cast<int>(dbg("enc_rounding", 0)));
+      FT_CUDA(h, cudaGetLastError());
+      h->chk_for_b = dB; h->chk_n = N; h->chk_k = K; h->chk_bn = BN;
+    }
+    rc = make_tmap_2d(h, &tmC, h->d_chk, chk_ld, K, chk_ld, kAtomMN, kBK);
+    if (rc) return rc;
+  }
+  h->last_stream = stream;
+  if (ft) {
+    switch (BN) {
+      case 32: return launch_tc<32, true>(h, tmA, tmB, tmC, p, stream);
+      case 64: return launch_tc<64, true>(h, tmA, tmB, tmC, p, stream);
+      case 128: return launch_tc<128, true>(h, tmA, tmB, tmC, p, stream);
+      case 256: return launch_tc<256, true>(h, tmA, tmB, tmC, p, stream);
+    }
+  } else {
+    switch (BN) {
+      case 32: return launch_tc<32, false>(h, tmA, tmB, tmC, p, stream);
+      case 64: return launch_tc<64, false>(h, tmA, tmB, tmC, p, stream);
+      case 128: return launch_tc<128, false>(h, tmA, tmB, tmC, p, stream);
+      case 256: return launch_tc<256, false>(h, tmA, tmB, tmC, p, stream);
+    }
+  }
+  return FTSGEMM_ERR_UNSUPPORTED;
+}
+
+int run_cublas(ftsgemm_handle_t h, bool tf32, int M, int N, int K, const float *dA, const float *dB, float *dC,
+               float alpha, float beta, cudaStream_t stream) {
+  FT_CUBLAS(h, cublasSetStream(h->cublas, stream));
+  FT_CUBLAS(h, cublasSetPointerMode(h->cublas, CUBLAS_POINTER_MODE_HOST));
+  FT_CUBLAS(h, cublasSetMathMode(h->cublas, tf32 ? CUBLAS_TF32_TENSOR_OP_MATH : CUBLAS_DEFAULT_MATH));
+  // NT on column-major buffers, as the reference's oracle call (sgemm.cu:108)
+  FT_CUBLAS(h, cublasSgemm(h->cublas, CUBLAS_OP_N, CUBLAS_OP_T, M, N, K, &alpha, dA, M, dB, N, &beta, dC, M));
+  h->last_stream = stream;
+  return FTSGEMM_OK;
+}
+
+__global__ void fill_kernel(float *p, float v, size_t n) {
+  size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// verify_matrix (utils/utils.cu:61-77) on the device: smallest failing index + Frobenius sums
+__global__ void verify_kernel(const float *ref, const float *x, size_t n, unsigned long long *first_bad, double *num,
+                              double *den) {
+  double ln = 0.0, ld = 0.0;
+  unsigned long long lb = ~0ull;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const double r = ref[i], d = fabs(r - static_cast<double>(x[i]));
+    if (((d / fabs(r)) > 0.01 && d > 0.01) || !(d == d)) lb = lb < i ? lb : i;
+    ln += d * d;
+    ld += r * r;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    ln += __shfl_xor_sync(0xffffffffu, ln, o);
+    ld += __shfl_xor_sync(0xffffffffu, ld, o);
+    unsigned long long ob = __shfl_xor_sync(0xffffffffu, lb, o);
+    lb = lb < ob ? lb : ob;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(num, ln);
+    atomicAdd(den, ld);
+    atomicMin(first_bad, lb);
+  }
+}
+
+}  // namespace
+
+// =============================================================================================== C ABI
+extern "C" {
+
+int ftsgemm_abi_version(void) { return FTSGEMM_ABI_VERSION; }
+
+const char *ftsgemm_error_string(int code) {
+  switch (code) {
+    case FTSGEMM_OK: return "ok";
+    case FTSGEMM_ERR_INVALID_ARG: return "invalid argument";
+    case FTSGEMM_ERR_UNSUPPORTED: return "unsupported shape or kernel id";
+    case FTSGEMM_ERR_CUDA: return "CUDA error (see ftsgemm_last_cuda_error)";
+    case FTSGEMM_ERR_NO_DEVICE: return "no sm_100 CUDA device available (libftsgemm has no CPU fallback)";
+    case FTSGEMM_ERR_CUBLAS: return "cuBLAS error";
+    case FTSGEMM_ERR_VERIFY: return "verification failed";
+  }
+  return "unknown error";
+}
+
+void ftsgemm_default_opts(ftsgemm_opts *o) {
+  if (!o) return;
+  memset(o, 0, sizeof(*o));
+  o->struct_size = sizeof(*o);
+  o->selftest_value = 10000.0f;  // ft_sgemm_huge.cuh:51
+  o->selftest_row = 17;          // ft_sgemm_huge.cuh:49 (tx_injec)
+  o->selftest_col = 0;
+  o->baseline_host_sync = 1;
+}
+
+int ftsgemm_kernel_table(ftsgemm_kernel_info *out, int cap) {
+  if (out)
+    for (int i = 0; i < kNumVariants && i < cap; ++i) out[i] = kVariants[i].info;
+  return kNumVariants;
+}
+
+int ftsgemm_kernel_lookup(int kernel_id, ftsgemm_kernel_info *out) {
+  const Variant *v = find_variant(kernel_id);
+  if (!v) return FTSGEMM_ERR_INVALID_ARG;
+  if (out) *out = v->info;
+  return FTSGEMM_OK;
+}
+
+int ftsgemm_debug_set(const char *key, long long value) {
+  if (!key) return FTSGEMM_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(g_dbg_mu);
+  if (value == -1) g_dbg.erase(key);
+  else g_dbg[key] = value;
+  return FTSGEMM_OK;
+}
+
+int ftsgemm_create(ftsgemm_handle_t *out) {
+  if (!out) return FTSGEMM_ERR_INVALID_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return FTSGEMM_ERR_NO_DEVICE;
+  ftsgemm_handle_t h = new ftsgemm_handle_s();
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&h->device) != cudaSuccess || cudaGetDeviceProperties(&prop, h->device) != cudaSuccess ||
+      prop.major != 10) {
+    delete h;
+    return FTSGEMM_ERR_NO_DEVICE;
+  }
+  h->num_sms = prop.multiProcessorCount;
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+    delete h;
+    return FTSGEMM_ERR_CUDA;
+  }
+  h->encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  if (cublasCreate(&h->cublas) != CUBLAS_STATUS_SUCCESS) {
+    delete h;
+    return FTSGEMM_ERR_CUBLAS;
+  }
+  if (cudaMalloc(&h->d_stats, sizeof(DeviceStats)) != cudaSuccess ||
+      cudaMemset(h->d_stats, 0, sizeof(DeviceStats)) != cudaSuccess ||
+      cudaMalloc(&h->d_verify, 4 * sizeof(double)) != cudaSuccess) {
+    ftsgemm_destroy(h);
+    return FTSGEMM_ERR_CUDA;
+  }
+  *out = h;
+  return FTSGEMM_OK;
+}
+
+int ftsgemm_destroy(ftsgemm_handle_t h) {
+  if (!h) return FTSGEMM_OK;
+  cudaDeviceSynchronize();
+  if (h->cublas) cublasDestroy(h->cublas);
+  cudaFree(h->d_stats);
+  cudaFree(h->d_chk);
+  cudaFree(h->d_aux);
+  cudaFree(h->d_verify);
+  for (int i = 0; i < 3; ++i) cudaFree(h->d_stage[i]);
+  delete h;
+  return FTSGEMM_OK;
+}
+
+int ftsgemm_last_cuda_error(ftsgemm_handle_t h) { return h ? h->last_cuda_error : 0; }
+
+int ftsgemm_run(ftsgemm_handle_t h, int kernel_id, int M, int N, int K, const float *dA, const float *dB, float *dC,
+                float alpha, float beta, const ftsgemm_opts *opts) {
+  if (!h) return FTSGEMM_ERR_NO_DEVICE;
+  if (!dA || !dB || !dC || M <= 0 || N <= 0 || K <= 0) return FTSGEMM_ERR_INVALID_ARG;
+  const Variant *v = find_variant(kernel_id);
+  if (!v) return FTSGEMM_ERR_INVALID_ARG;
+  ftsgemm_opts o;
+  ftsgemm_default_opts(&o);
+  if (opts) memcpy(&o, opts, opts->struct_size < sizeof(o) ? opts->struct_size : sizeof(o));
+  cudaStream_t stream = static_cast<cudaStream_t>(o.stream);
+  switch (v->info.engine) {
+    case 0: return run_cublas(h, v->info.id == 7, M, N, K, dA, dB, dC, alpha, beta, stream);
+    case 1: return run_tc(h, *v, M, N, K, dA, dB, dC, alpha, beta, o, stream);
+    case 2: return ftsgemm_baseline(h, M, N, K, dA, dB, dC, alpha, beta, v->info.id == 30 ? 1 : 0, &o, nullptr);
+  }
+  return FTSGEMM_ERR_UNSUPPORTED;
+}
+
+int ftsgemm_get_stats(ftsgemm_handle_t h, ftsgemm_stats *out) {
+  if (!h) return FTSGEMM_ERR_NO_DEVICE;
+  if (!out) return FTSGEMM_ERR_INVALID_ARG;
+  FT_CUDA(h, cudaStreamSynchronize(h->last_stream));
+  DeviceStats ds;
+  FT_CUDA(h, cudaMemcpy(&ds, h->d_stats, sizeof(ds), cudaMemcpyDeviceToHost));
+  FT_CUDA(h, cudaMemset(h->d_stats, 0, sizeof(DeviceStats)));
+  memset(out, 0, sizeof(*out));
+  out->tiles = ds.tiles;
+  out->rows_checked = ds.rows_checked;
+  out->detected = ds.detected;
+  out->corrected = ds.corrected;
+  out->uncorrectable = ds.uncorrectable;
+  out->checksum_faults = ds.checksum_faults;
+  memcpy(&out->max_abs_residual, &ds.max_abs_bits, 4);
+  memcpy(&out->max_rel_residual, &ds.max_rel_bits, 4);
+  out->n_events = ds.n_events < FTSGEMM_MAX_EVENTS ? ds.n_events : FTSGEMM_MAX_EVENTS;
+  for (int i = 0; i < out->n_events; ++i) {
+    out->events[i].row = ds.events[i].row;
+    out->events[i].col = ds.events[i].col;
+    out->events[i].residual = ds.events[i].residual;
+    out->events[i].corrected_value = ds.events[i].corrected_value;
+    out->events[i].status = ds.events[i].status;
+  }
+  return FTSGEMM_OK;
+}
+
+int ftsgemm_run_host(ftsgemm_handle_t h, int kernel_id, int M, int N, int K, const float *hA, const float *hB,
+                     float *hC, float alpha, float beta, const ftsgemm_opts *opts) {
+  if (!h) return FTSGEMM_ERR_NO_DEVICE;
+  if (!hA || !hB || !hC || M <= 0 || N <= 0 || K <= 0) return FTSGEMM_ERR_INVALID_ARG;
+  const size_t bytes[3] = {sizeof(float) * M * static_cast<size_t>(K), sizeof(float) * N * static_cast<size_t>(K),
+                           sizeof(float) * M * static_cast<size_t>(N)};
+  for (int i = 0; i < 3; ++i)
+    if (h->stage_bytes[i] < bytes[i]) {
+      if (h->d_stage[i]) FT_CUDA(h, cudaFree(h->d_stage[i]));
+      h->d_stage[i] = nullptr;
+      h->stage_bytes[i] = 0;
+      FT_CUDA(h, cudaMalloc(&h->d_stage[i], bytes[i]));
+      h->stage_bytes[i] = bytes[i];
+    }
+  cudaStream_t stream = opts ? static_cast<cudaStream_t>(opts->stream) : nullptr;
+  FT_CUDA(h, cudaMemcpyAsync(h->d_stage[0], hA, bytes[0], cudaMemcpyHostToDevice, stream));
+  FT_CUDA(h, cudaMemcpyAsync(h->d_stage[1], hB, bytes[1], cudaMemcpyHostToDevice, stream));
+  if (beta != 0.0f) FT_CUDA(h, cudaMemcpyAsync(h->d_stage[2], hC, bytes[2], cudaMemcpyHostToDevice, stream));
+  ftsgemm_opts o;
+  ftsgemm_default_opts(&o);
+  if (opts) memcpy(&o, opts, opts->struct_size < sizeof(o) ? opts->struct_size : sizeof(o));
+  o.reuse_b_checksums = 0;  // the staging buffer content changed
+  int rc = ftsgemm_run(h, kernel_id, M, N, K, h->d_stage[0], h->d_stage[1], h->d_stage[2], alpha, beta, &o);
+  if (rc) return rc;
+  FT_CUDA(h, cudaMemcpyAsync(hC, h->d_stage[2], bytes[2], cudaMemcpyDeviceToHost, stream));
+  FT_CUDA(h, cudaStreamSynchronize(stream));
+  return FTSGEMM_OK;
+}
+
+int ftsgemm_baseline(ftsgemm_handle_t h, int M, int N, int K, const float *dA, const float *dB, float *dC,
+                     float alpha, float beta, int math_mode, const ftsgemm_opts *opts, float *residual_out) {
+  if (!h) return FTSGEMM_ERR_NO_DEVICE;
+  if (!dA || !dB || !dC || M <= 0 || N <= 0 || K <= 0) return FTSGEMM_ERR_INVALID_ARG;
+  cudaStream_t stream = opts ? static_cast<cudaStream_t>(opts->stream) : nullptr;
+  const bool host_sync = opts ? opts->baseline_host_sync != 0 : true;
+  const int mx = M > N ? M : N;
+  // aux layout: ones[mx] | c_row[M] | c_col[N] | a_col[256] | b_row[256] | acol_x_b[N] | brow_x_a[M] | res[2] | consts[3]
+  const size_t need = static_cast<size_t>(mx) + M + N + 256 + 256 + N + M + 2 + 3;
+  if (h->aux_floats < need) {
+    if (h->d_aux) FT_CUDA(h, cudaFree(h->d_aux));
+    h->d_aux = nullptr;
+    h->aux_floats = 0;
+    FT_CUDA(h, cudaMalloc(&h->d_aux, need * sizeof(float)));
+    h->aux_floats = need;
+  }
+  float *ones = h->d_aux, *c_row = ones + mx, *c_col = c_row + M, *a_col = c_col + N, *b_row = a_col + 256,
+        *acol_x_b = b_row + 256, *brow_x_a = acol_x_b + N, *res = brow_x_a + M;
+  fill_kernel<<<(mx + 255) / 256, 256, 0, stream>>>(ones, 1.0f, mx);
+  FT_CUDA(h, cudaGetLastError());
+  FT_CUBLAS(h, cublasSetStream(h->cublas, stream));
+  FT_CUBLAS(h, cublasSetMathMode(h->cublas, math_mode ? CUBLAS_TF32_TENSOR_OP_MATH : CUBLAS_DEFAULT_MATH));
+  const float one = 1.0f, zero = 0.0f, neg1 = -1.0f;
+  for (int k0 = 0; k0 < K; k0 += 256) {
+    const int kc = (K - k0) < 256 ? (K - k0) : 256;
+    const float beta_eff = (k0 == 0) ? beta : 1.0f;
+    const float *Ac = dA + static_cast<size_t>(k0) * M;
+    const float *Bc = dB + static_cast<size_t>(k0) * N;
+    FT_CUBLAS(h, cublasSetPointerMode(h->cublas, CUBLAS_POINTER_MODE_HOST));
+    // product chunk (baseline_ft_sgemm.cuh:6)
+    FT_CUBLAS(h, cublasSgemm(h->cublas, CUBLAS_OP_N, CUBLAS_OP_T, M, N, kc, &alpha, Ac, M, Bc, N, &beta_eff, dC, M));
+    if (host_sync) FT_CUDA(h, cudaStreamSynchronize(stream));
+    // row / column sums of all of C (:9,:12) -- the re-read of C the fused kernel removes
+    FT_CUBLAS(h, cublasSgemv(h->cublas, CUBLAS_OP_N, M, N, &one, dC, M, ones, 1, &zero, c_row, 1));
+    FT_CUBLAS(h, cublasSgemv(h->cublas, CUBLAS_OP_T, M, N, &one, dC, M, ones, 1, &zero, c_col, 1));
+    // encode: e^T A_chunk (:15) and B_chunk^T e (:18)
+    FT_CUBLAS(h, cublasSgemv(h->cublas, CUBLAS_OP_T, M, kc, &one, Ac, M, ones, 1, &zero, a_col, 1));
+    FT_CUBLAS(h, cublasSgemv(h->cublas, CUBLAS_OP_T, N, kc, &one, Bc, N, ones, 1, &zero, b_row, 1));
+    if (host_sync) FT_CUDA(h, cudaStreamSynchronize(stream));
+    // checksum products (:21,:24); accumulated over chunks so that, for alpha = 1 and beta = 0, the residual of
+    // the last chunk is the residual of the whole product
+    const float *acc_beta = (k0 == 0) ? &zero : &one;
+    FT_CUBLAS(h, cublasSgemv(h->cublas, CUBLAS_OP_N, N, kc, &one, Bc, N, a_col, 1, acc_beta, acol_x_b, 1));
+    FT_CUBLAS(h, cublasSgemv(h->cublas, CUBLAS_OP_N, M, kc, &one, Ac, M, b_row, 1, acc_beta, brow_x_a, 1));
+    if (host_sync) FT_CUDA(h, cudaStreamSynchronize(stream));
+    // residual + reduce (:27-31); dot results land in device memory
+    FT_CUBLAS(h, cublasSaxpy(h->cublas, N, &neg1, acol_x_b, 1, c_col, 1));
+    FT_CUBLAS(h, cublasSetPointerMode(h->cublas, CUBLAS_POINTER_MODE_DEVICE));
+    FT_CUBLAS(h, cublasSdot(h->cublas, N, c_col, 1, ones, 1, res));
+    if (host_sync) FT_CUDA(h, cudaStreamSynchronize(stream));
+    FT_CUBLAS(h, cublasSetPointerMode(h->cublas, CUBLAS_POINTER_MODE_HOST));
+    FT_CUBLAS(h, cublasSaxpy(h->cublas, M, &neg1, brow_x_a, 1, c_row, 1));
+    FT_CUBLAS(h, cublasSetPointerMode(h->cublas, CUBLAS_POINTER_MODE_DEVICE));
+    FT_CUBLAS(h, cublasSdot(h->cublas, M, c_row, 1, ones, 1, res + 1));
+  }
+  FT_CUBLAS(h, cublasSetPointerMode(h->cublas, CUBLAS_POINTER_MODE_HOST));
+  if (residual_out)
+    FT_CUDA(h, cudaMemcpyAsync(residual_out, res, 2 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  h->last_stream = stream;
+  return FTSGEMM_OK;
+}
+
+int ftsgemm_verify(ftsgemm_handle_t h, const float *d_ref, const float *d_x, int M, int N, long long *first_bad,
+                   double *rel_fro, void *stream_v) {
+  if (!h) return FTSGEMM_ERR_NO_DEVICE;
+  if (!d_ref || !d_x || M <= 0 || N <= 0) return FTSGEMM_ERR_INVALID_ARG;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  unsigned long long init[4];
+  init[0] = ~0ull;
+  double z = 0.0;
+  memcpy(&init[1], &z, 8);
+  memcpy(&init[2], &z, 8);
+  init[3] = 0;
+  FT_CUDA(h, cudaMemcpyAsync(h->d_verify, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+  const size_t n = static_cast<size_t>(M) * N;
+  verify_kernel<<<h->num_sms * 8, 256, 0, stream>>>(d_ref, d_x, n, reinterpret_cast<unsigned long long *>(h->d_verify),
+                                                   h->d_verify + 1, h->d_verify + 2);
+  FT_CUDA(h, cudaGetLastError());
+  unsigned long long res[4];
+  FT_CUDA(h, cudaMemcpyAsync(res, h->d_verify, sizeof(res), cudaMemcpyDeviceToHost, stream));
+  FT_CUDA(h, cudaStreamSynchronize(stream));
+  double num, den;
+  memcpy(&num, &res[1], 8);
+  memcpy(&den, &res[2], 8);
+  if (first_bad) *first_bad = res[0] == ~0ull ? -1 : static_cast<long long>(res[0]);
+  if (rel_fro) *rel_fro = den > 0 ? sqrt(num / den) : sqrt(num);
+  return res[0] == ~0ull ? FTSGEMM_OK : FTSGEMM_ERR_VERIFY;
+}
+
+}  // extern "C"

@@ -1,0 +1,173 @@
+/*
+ * ftsgemm.h -- C ABI of libftsgemm.so: fused fault-tolerant (ABFT) SGEMM for NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the ONE hot path of
+ * shixun404/Fault-Tolerant-SGEMM-on-NVIDIA-GPUs.  The reference exposes no library API; its boundary is
+ *   (1) the process CLI   ft_sgemm START END GAP ST_KERNEL END_KERNEL   (kernel/ft_sgemm/sgemm.cu:13-19),
+ *   (2) the uniform kernel contract
+ *         void k(int M,int N,int K,float*A,float*B,float*C,float alpha,float beta)
+ *       (kernel/ft_sgemm/include_code_gen/ft_sgemm_huge.cuh:11) selected by a kernel id
+ *       (dispatch chains sgemm.cu:110-199 / :256-430, id+name tables sgemm.cu:235-237,
+ *        tile table code_gen/main.py:8-16),
+ *   (3) the non-fused baseline  baseline_ft_sgemm(...)  (kernel/ft_sgemm/include/baseline_ft_sgemm.cuh:1).
+ * Every entry point below names the reference interface it replaces.  Plain C types only: device/host
+ * pointers, ints, floats; no torch / C++ types.
+ *
+ * Data layout (identical to the reference kernels): A is M x K column-major (ld = M), B is N x K
+ * column-major (ld = N), C is M x N column-major (ld = M);  C = alpha * A * B^T + beta * C  in place.
+ * All functions return FTSGEMM_OK (0) or a negative FTSGEMM_ERR_* code; nothing calls exit().
+ */
+#ifndef FTSGEMM_H_
+#define FTSGEMM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FTSGEMM_ABI_VERSION 1
+
+enum {
+  FTSGEMM_OK = 0,
+  FTSGEMM_ERR_INVALID_ARG = -1,  /* bad pointer / size / id */
+  FTSGEMM_ERR_UNSUPPORTED = -2,  /* shape not supported by the selected variant */
+  FTSGEMM_ERR_CUDA = -3,         /* a CUDA runtime/driver call failed; see ftsgemm_last_cuda_error */
+  FTSGEMM_ERR_NO_DEVICE = -4,    /* no sm_100 device / driver (the product has NO CPU fallback) */
+  FTSGEMM_ERR_CUBLAS = -5,
+  FTSGEMM_ERR_VERIFY = -6        /* used by the driver helpers only */
+};
+
+/* Kernel ids: the reference's table (sgemm.cu:235-237) is kept verbatim for ids 0,1-6,10,11-16.
+ * ids 7-9 fall through to cuBLAS in the reference (sgemm.cu:197-199); here 7 = cuBLAS with TF32 tensor-op math
+ * (the "fault-free cuBLAS TF32" bar), 8-9 = cuBLAS FP32.  ids >= 20 are B200-only extras. */
+enum {
+  FTSGEMM_ID_CUBLAS = 0,
+  FTSGEMM_ID_SGEMM_SMALL = 1, FTSGEMM_ID_SGEMM_MEDIUM = 2, FTSGEMM_ID_SGEMM_LARGE = 3,
+  FTSGEMM_ID_SGEMM_TALL = 4, FTSGEMM_ID_SGEMM_WIDE = 5, FTSGEMM_ID_SGEMM_HUGE = 6,
+  FTSGEMM_ID_CUBLAS_TF32 = 7,
+  FTSGEMM_ID_ABFT_BASELINE = 10,
+  FTSGEMM_ID_ABFT_SMALL = 11, FTSGEMM_ID_ABFT_MEDIUM = 12, FTSGEMM_ID_ABFT_LARGE = 13,
+  FTSGEMM_ID_ABFT_TALL = 14, FTSGEMM_ID_ABFT_WIDE = 15, FTSGEMM_ID_ABFT_HUGE = 16,
+  FTSGEMM_ID_SGEMM_GIANT = 21,       /* 128 x 256 tile, plain  (B200 extra) */
+  FTSGEMM_ID_ABFT_BASELINE_TF32 = 30,/* non-fused baseline with TF32 tensor-op math */
+  FTSGEMM_ID_ABFT_GIANT = 31         /* 128 x 256 tile, fused ABFT (B200 extra) */
+};
+
+typedef struct ftsgemm_handle_s *ftsgemm_handle_t;
+
+/* One row of the kernel-variant table (replaces the id/name arrays at sgemm.cu:235-237 and the
+ * tile table at code_gen/main.py:8-16). */
+typedef struct ftsgemm_kernel_info {
+  int id;
+  char name[24];         /* reference row label, e.g. "abft_kernel_huge" */
+  int fault_tolerant;    /* 1 = online ABFT fused into the kernel */
+  int engine;            /* 0 = cuBLAS, 1 = tcgen05 fused kernel, 2 = cuBLAS call sequence (baseline) */
+  int ref_tile_m, ref_tile_n, ref_tile_k; /* the reference's CUDA-core CTA tile (0 for library rows) */
+  int tile_m, tile_n, tile_k;             /* this build's sm_100a CTA tile (UMMA M x N, K per smem stage) */
+} ftsgemm_kernel_info;
+
+/* Fault to inject into the FP32 accumulator tile in tensor memory, before the checksum test
+ * (generalises the reference's always-on injector, ft_sgemm_huge.cuh:49-51,324-327). */
+typedef struct ftsgemm_fault {
+  int row, col;          /* global element (m, n) of C */
+  int mode;              /* 0: acc += add_value      1: acc bits ^= xor_mask (single/multi bit flip) */
+  float add_value;
+  uint32_t xor_mask;
+} ftsgemm_fault;
+
+#define FTSGEMM_MAX_FAULTS 8
+#define FTSGEMM_MAX_EVENTS 16
+
+typedef struct ftsgemm_opts {
+  uint32_t struct_size;  /* sizeof(ftsgemm_opts), for ABI evolution */
+  void *stream;          /* cudaStream_t; NULL = default stream (the reference uses only the default stream) */
+  /* fault injection */
+  int inject_mode;       /* 0 none | 1 reference self-test: every CTA tile gets +selftest_value at
+                            (selftest_row, selftest_col) of the tile | 2 explicit list faults[0..n_faults) */
+  float selftest_value;  /* reference: 10000 */
+  int selftest_row, selftest_col;
+  int n_faults;
+  ftsgemm_fault faults[FTSGEMM_MAX_FAULTS];
+  /* detection threshold: a row is flagged when |expected - actual row checksum| > tau_abs + tau_rel * sum_n|acc|.
+   * <= 0 selects the calibrated defaults.  The reference uses the constant 9500
+   * (ft_sgemm_huge.cuh:50). */
+  float tau_abs, tau_rel;
+  int detect_only;       /* 1: count detections but do not correct */
+  int reuse_b_checksums; /* 1: B is unchanged since the previous FT call on this handle -> skip the encode pass */
+  int baseline_host_sync;/* id 10/30: 1 = host-synchronise between stages like the reference
+                            (baseline_ft_sgemm.cuh:7,19,26,30); 0 = stream-ordered */
+} ftsgemm_opts;
+
+typedef struct ftsgemm_event {
+  int row, col;          /* global element that was located (col = -1 if not locatable) */
+  float residual;        /* expected - actual row checksum */
+  float corrected_value; /* accumulator value after correction */
+  int status;            /* 1 corrected, 2 detected only (detect_only), 3 uncorrectable, 4 checksum-column fault */
+} ftsgemm_event;
+
+typedef struct ftsgemm_stats {
+  unsigned long long tiles;        /* CTA tiles processed */
+  unsigned long long rows_checked; /* row checksums tested */
+  unsigned long long detected;     /* rows whose residual exceeded the threshold */
+  unsigned long long corrected;    /* single-element corrections applied */
+  unsigned long long uncorrectable;/* detected but not locatable (multi-error row / ambiguous) */
+  unsigned long long checksum_faults; /* residual explained by a fault in the checksum column itself */
+  float max_abs_residual;          /* max |expected - actual| over all fault-free rows */
+  float max_rel_residual;          /* max |expected - actual| / sum_n|acc| over all fault-free rows */
+  int n_events;
+  ftsgemm_event events[FTSGEMM_MAX_EVENTS];
+} ftsgemm_stats;
+
+/* ---- lifetime ---------------------------------------------------------------------------------------- */
+int ftsgemm_create(ftsgemm_handle_t *out);   /* binds to the current CUDA device; owns cuBLAS handle + workspace */
+int ftsgemm_destroy(ftsgemm_handle_t h);
+int ftsgemm_abi_version(void);
+const char *ftsgemm_error_string(int code);
+int ftsgemm_last_cuda_error(ftsgemm_handle_t h); /* cudaError_t / CUresult of the last failure, 0 if none */
+void ftsgemm_default_opts(ftsgemm_opts *o);
+
+/* ---- kernel-variant table  (replaces sgemm.cu:235-237 + code_gen/main.py:8-16) --------------------------- */
+int ftsgemm_kernel_table(ftsgemm_kernel_info *out, int cap); /* returns number of rows (fills min(cap, rows)) */
+int ftsgemm_kernel_lookup(int kernel_id, ftsgemm_kernel_info *out);
+
+/* ---- the kernel contract  (replaces `kernel<<<grid,block>>>(M,N,K,dA,dB,dC,alpha,beta)` selected by id,
+ *      sgemm.cu:110-199, and cublasSgemm at sgemm.cu:108,198,260) ---------------------------------------------
+ * Device pointers, caller-owned, in place on C, asynchronous on opts->stream.  Preconditions as in the
+ * reference: 16-byte aligned pointers, M % 4 == 0 and N % 4 == 0 (16-byte rows for TMA); unlike the reference,
+ * M/N/K need not be multiples of the tile (TMA zero-fills the ragged edge).  K >= 1. */
+int ftsgemm_run(ftsgemm_handle_t h, int kernel_id, int M, int N, int K, const float *dA, const float *dB,
+                float *dC, float alpha, float beta, const ftsgemm_opts *opts);
+
+/* Counters of all FT launches since the previous call (synchronises the handle's last stream, then resets). */
+int ftsgemm_get_stats(ftsgemm_handle_t h, ftsgemm_stats *out);
+
+/* Same contract with HOST buffers: H2D of A, B (and C when beta != 0), the kernel, D2H of C, synchronous.
+ * This is the call the e2e benchmark times.  Device staging buffers are cached on the handle. */
+int ftsgemm_run_host(ftsgemm_handle_t h, int kernel_id, int M, int N, int K, const float *hA, const float *hB,
+                     float *hC, float alpha, float beta, const ftsgemm_opts *opts);
+
+/* ---- non-fused ABFT baseline  (replaces baseline_ft_sgemm(), include/baseline_ft_sgemm.cuh:1-33) -----------
+ * Same call sequence per 256-wide K chunk (1 Sgemm + 6 Sgemv + 2 x (Saxpy + Sdot)), detection only.
+ * Differences from the reference, by design: chunks after the first accumulate with beta = 1 so the result is
+ * a correct GEMM; Sdot results go to device memory in device-pointer mode; the last chunk may be < 256 wide.
+ * math_mode 0 = FP32 (reference), 1 = TF32 tensor-op.  residual_out (device, 2 floats, may be NULL) receives
+ * the last chunk's summed column / row residuals. */
+int ftsgemm_baseline(ftsgemm_handle_t h, int M, int N, int K, const float *dA, const float *dB, float *dC,
+                     float alpha, float beta, int math_mode, const ftsgemm_opts *opts, float *residual_out);
+
+/* ---- comparator (replaces verify_matrix, utils/utils.cu:61-77) on device buffers -------------------------
+ * Returns FTSGEMM_OK when every element passes the reference rule (fails iff rel > 1e-2 AND abs > 1e-2),
+ * FTSGEMM_ERR_VERIFY otherwise.  first_bad (may be NULL) receives the smallest failing linear index or -1;
+ * rel_fro (may be NULL) the Frobenius-norm relative error. */
+int ftsgemm_verify(ftsgemm_handle_t h, const float *d_ref, const float *d_x, int M, int N, long long *first_bad,
+                   double *rel_fro, void *stream);
+
+/* ---- internal / experiments (not part of the drop-in surface) ---------------------------------------------- */
+int ftsgemm_debug_set(const char *key, long long value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FTSGEMM_H_ */
