@@ -1,0 +1,233 @@
+// ft_sgemm_main.cu -- the `ft_sgemm START END GAP ST_KERNEL END_KERNEL` driver, a client of the C ABI.
+//
+// Mirrors the reference driver's contract (/root/reference/kernel/ft_sgemm/sgemm.cu:10-440):
+//   argv           sgemm.cu:13-19 (five atoi'd integers)
+//   inputs         srand(10); A, B, C drawn in that order at n = END, then C <- 0      sgemm.cu:12,52-56
+//   phase 1        for id in ST..END: cuBLAS NT reference, kernel id, verify_matrix      sgemm.cu:98-229
+//   phase 2        GFLOPS table, beta = -1.5, sizes START..END step GAP                  sgemm.cu:231-439
+//   stdout         identical strings / formats (sgemm.cu:100,214,223,227,231,239-243,248,435)
+// Deliberate differences: GAP <= 0 means "one size" (the reference loops forever);
+// CUDA errors return a non-zero exit code through the ABI's error codes instead of exit() inside helpers;
+// timing uses warm-up + back-to-back launches between two events unless FTSGEMM_TIMING=reference;
+// FT ids run with the reference's always-on +10000 self-test injection (FTSGEMM_INJECT=0 turns it off), and a
+// per-id fault summary goes to stderr; FTSGEMM_CPU_VERIFY=1 (default for END <= 1024) additionally checks every
+// result against a host sequential-k FP32 SGEMM (the role of the reference's unused cpu_gemm, utils/utils.cu:79-89).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../include/ftsgemm.h"
+
+namespace {
+
+#define CUDA_OR_DIE(call)                                                                    \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      printf("CUDA Error at line %d in file %s\n", __LINE__, __FILE__);                      \
+      printf("  Error message: %s\n", cudaGetErrorString(e__));                              \
+      printf("  In the function call %s\n", #call);                                          \
+      exit(1);                                                                               \
+    }                                                                                        \
+  } while (0)
+
+// Input distribution of utils/utils.cu:23-31: magnitude (rand()%10)*0.1 in double narrowed to float, second
+// rand() picks the sign.
+void random_matrix(float *dst, int n) {
+  for (long i = 0; i < static_cast<long>(n) * n; ++i) {
+    float mag = static_cast<float>(static_cast<double>(static_cast<float>(rand() % 10)) * 0.1);
+    dst[i] = (rand() % 2 == 0) ? mag : static_cast<float>(static_cast<double>(mag) * -1.0);
+  }
+}
+
+// Host check only (never produces a result the driver returns): C[m+n*M] = sum_k A[m+k*M]*B[n+k*N], ascending k, fp32.
+void host_sgemm_nt(int M, int N, int K, const float *A, const float *B, float *C) {
+  unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < nt; ++t)
+    pool.emplace_back([=]() {
+      for (int n = static_cast<int>(t); n < N; n += static_cast<int>(nt))
+        for (int m = 0; m < M; ++m) {
+          float acc = 0.0f;
+          for (int k = 0; k < K; ++k) acc = acc + A[m + static_cast<size_t>(k) * M] * B[n + static_cast<size_t>(k) * N];
+          C[m + static_cast<size_t>(n) * M] = acc;
+        }
+    });
+  for (auto &th : pool) th.join();
+}
+
+bool host_verify(const float *ref, const float *x, long count, double *rel_fro) {
+  bool ok = true;
+  double num = 0, den = 0;
+  for (long i = 0; i < count; ++i) {
+    double d = fabs(static_cast<double>(ref[i]) - static_cast<double>(x[i]));
+    if ((d / fabs(static_cast<double>(ref[i]))) > 0.01 && d > 0.01) ok = false;
+    num += d * d;
+    den += static_cast<double>(ref[i]) * ref[i];
+  }
+  *rel_fro = den > 0 ? sqrt(num / den) : sqrt(num);
+  return ok;
+}
+
+int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  if (argc < 6) {
+    fprintf(stderr, "usage: %s START END GAP ST_KERNEL END_KERNEL\n", argv[0]);
+    return 2;
+  }
+  srand(10);
+  const int start_size = atoi(argv[1]), end_size = atoi(argv[2]), gap_size = atoi(argv[3]);
+  const int st_kernel = atoi(argv[4]), end_kernel = atoi(argv[5]);
+  const int n = end_size;
+  if (n <= 0 || start_size <= 0) {
+    fprintf(stderr, "sizes must be positive\n");
+    return 2;
+  }
+  const bool inject = env_int("FTSGEMM_INJECT", 1) != 0;
+  const bool ref_timing = getenv("FTSGEMM_TIMING") && !strcmp(getenv("FTSGEMM_TIMING"), "reference");
+  const bool cpu_verify = env_int("FTSGEMM_CPU_VERIFY", n <= 1024 ? 1 : 0) != 0;
+
+  ftsgemm_handle_t h = nullptr;
+  int rc = ftsgemm_create(&h);
+  if (rc) {
+    fprintf(stderr, "ftsgemm_create: %s\n", ftsgemm_error_string(rc));
+    return 1;
+  }
+
+  const size_t count = static_cast<size_t>(n) * n;
+  std::vector<float> A(count), B(count), Cm(count), Cref(count), Chost;
+  random_matrix(A.data(), n);
+  random_matrix(B.data(), n);
+  random_matrix(Cm.data(), n);
+  std::fill(Cm.begin(), Cm.end(), 0.0f);
+
+  float *dA, *dB, *dC, *dCref;
+  CUDA_OR_DIE(cudaMalloc(&dA, count * sizeof(float)));
+  CUDA_OR_DIE(cudaMalloc(&dB, count * sizeof(float)));
+  CUDA_OR_DIE(cudaMalloc(&dC, count * sizeof(float)));
+  CUDA_OR_DIE(cudaMalloc(&dCref, count * sizeof(float)));
+  CUDA_OR_DIE(cudaMemcpy(dA, A.data(), count * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_OR_DIE(cudaMemcpy(dB, B.data(), count * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_OR_DIE(cudaMemcpy(dC, Cm.data(), count * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_OR_DIE(cudaMemcpy(dCref, Cm.data(), count * sizeof(float), cudaMemcpyHostToDevice));
+
+  ftsgemm_opts opts;
+  ftsgemm_default_opts(&opts);
+  if (inject) opts.inject_mode = 1;  // +10000 into one accumulator of every CTA tile (ft_sgemm_huge.cuh:324-327)
+
+  if (cpu_verify) {
+    Chost.resize(count);
+    host_sgemm_nt(n, n, n, A.data(), B.data(), Chost.data());
+  }
+
+  // ------------------------------------------------------------------ phase 1: verification (alpha = 1, beta = 0)
+  printf("Start verification!\n");
+  const int M = n, N = n, K = n;
+  for (int id = st_kernel; id <= end_kernel; ++id) {
+    ftsgemm_kernel_info info;
+    const int run_id = ftsgemm_kernel_lookup(id, &info) == FTSGEMM_OK ? id : 0;  // unknown ids run cuBLAS (sgemm.cu:197)
+    rc = ftsgemm_run(h, FTSGEMM_ID_CUBLAS, M, N, K, dA, dB, dCref, 1.0f, 0.0f, nullptr);
+    if (!rc) rc = ftsgemm_run(h, run_id, M, N, K, dA, dB, dC, 1.0f, 0.0f, &opts);
+    if (rc) {
+      fprintf(stderr, "[Kernel Launch Error] %s (status %d)\n", ftsgemm_error_string(rc), ftsgemm_last_cuda_error(h));
+      return EXIT_FAILURE;
+    }
+    cudaError_t se = cudaDeviceSynchronize();
+    if (se != cudaSuccess) {
+      fprintf(stderr, "[Kernel Execution Error] %s\n", cudaGetErrorString(se));
+      return EXIT_FAILURE;
+    }
+    printf("[Kernel Completed Successfully]\n");
+    long long first_bad = -1;
+    double rel = 0;
+    if (ftsgemm_verify(h, dCref, dC, M, N, &first_bad, &rel, nullptr) != FTSGEMM_OK)
+      printf("kernel %d failed to pass the correctness verification against NVIDIA cuBLAS. Exited.\n", id);
+    fflush(stdout);
+    printf("kernel %d finish verified!\n", id);
+    if (ftsgemm_kernel_lookup(run_id, &info) == FTSGEMM_OK && info.fault_tolerant && info.engine == 1) {
+      ftsgemm_stats st;
+      if (ftsgemm_get_stats(h, &st) == FTSGEMM_OK)
+        fprintf(stderr, "[abft] kernel %d: tiles %llu detected %llu corrected %llu uncorrectable %llu max_resid %.3e rel_fro_vs_cublas %.3e\n",
+                id, st.tiles, st.detected, st.corrected, st.uncorrectable, st.max_abs_residual, rel);
+    }
+    if (cpu_verify) {
+      CUDA_OR_DIE(cudaMemcpy(Cm.data(), dC, count * sizeof(float), cudaMemcpyDeviceToHost));
+      double rel_cpu = 0;
+      bool ok = host_verify(Chost.data(), Cm.data(), static_cast<long>(count), &rel_cpu);
+      fprintf(stderr, "[cpu-verify] kernel %d vs host sequential-k SGEMM (%u threads): %s, rel_fro %.3e\n", id,
+              std::max(1u, std::thread::hardware_concurrency()), ok ? "pass" : "FAIL", rel_cpu);
+    }
+  }
+
+  // ------------------------------------------------------------------ phase 2: performance (alpha = 1, beta = -1.5)
+  printf("################## Performance (GFLOPS) ########################\n");
+  const float alpha = 1.0f, beta = -1.5f;
+  const int list[] = {0, 1, 2, 3, 4, 5, 6, 7, 10, 11, 12, 13, 14, 15, 16, 21, 30, 31};
+  std::vector<int> sizes;
+  for (int s = start_size; s <= end_size; s += gap_size) {
+    sizes.push_back(s);
+    if (gap_size <= 0) break;
+  }
+  printf("Matrix Size         |");
+  for (int s : sizes) printf("%8d|", s);
+  printf("\n");
+  cudaEvent_t beg, end;
+  CUDA_OR_DIE(cudaEventCreate(&beg));
+  CUDA_OR_DIE(cudaEventCreate(&end));
+  opts.reuse_b_checksums = 0;
+  for (int id : list) {
+    if (id < st_kernel) continue;
+    if (id > end_kernel) break;
+    if ((id == 7 || id > 16) && end_kernel <= 16) continue;  // B200 extras only when asked for
+    ftsgemm_kernel_info info;
+    ftsgemm_kernel_lookup(id, &info);
+    printf("%-20s|", info.name);
+    for (int s : sizes) {
+      const int m = s, nn = s, k = s;
+      float ms = 0;
+      if (ref_timing) {  // sgemm.cu:419-429: events around 5 x {sync; launch; sync}
+        CUDA_OR_DIE(cudaEventRecord(beg));
+        for (int i = 0; i < 5; ++i) {
+          cudaDeviceSynchronize();
+          rc = ftsgemm_run(h, id, m, nn, k, dA, dB, dC, alpha, beta, &opts);
+          cudaDeviceSynchronize();
+        }
+        CUDA_OR_DIE(cudaEventRecord(end));
+        CUDA_OR_DIE(cudaEventSynchronize(end));
+        CUDA_OR_DIE(cudaEventElapsedTime(&ms, beg, end));
+        ms /= 5;
+      } else {
+        const int reps = info.engine == 2 ? 3 : 20;
+        for (int i = 0; i < 3 && !rc; ++i) rc = ftsgemm_run(h, id, m, nn, k, dA, dB, dC, alpha, beta, &opts);
+        cudaDeviceSynchronize();
+        CUDA_OR_DIE(cudaEventRecord(beg));
+        for (int i = 0; i < reps && !rc; ++i) rc = ftsgemm_run(h, id, m, nn, k, dA, dB, dC, alpha, beta, &opts);
+        CUDA_OR_DIE(cudaEventRecord(end));
+        CUDA_OR_DIE(cudaEventSynchronize(end));
+        CUDA_OR_DIE(cudaEventElapsedTime(&ms, beg, end));
+        ms /= reps;
+      }
+      if (rc) {
+        fprintf(stderr, "[Kernel Launch Error] %s\n", ftsgemm_error_string(rc));
+        return EXIT_FAILURE;
+      }
+      printf("%8.0f|", 2.0 * m * nn * k / 1e9 / (ms / 1e3));
+      fflush(stdout);
+    }
+    printf("\n");
+  }
+  ftsgemm_destroy(h);
+  return 0;
+}

@@ -252,7 +252,7 @@ int run_cublas(ftsgemm_handle_t h, bool tf32, int M, int N, int K, const float *
   FT_CUBLAS(h, cublasSetStream(h->cublas, stream));
   FT_CUBLAS(h, cublasSetPointerMode(h->cublas, CUBLAS_POINTER_MODE_HOST));
   FT_CUBLAS(h, cublasSetMathMode(h->cublas, tf32 ? CUBLAS_TF32_TENSOR_OP_MATH : CUBLAS_DEFAULT_MATH));
-  // NT on column-major buffers, as the reference's oracle call (sgemm.cu:108)
+  // NT on column-major buffers, as the reference's verification call (sgemm.cu:108)
   FT_CUBLAS(h, cublasSgemm(h->cublas, CUBLAS_OP_N, CUBLAS_OP_T, M, N, K, &alpha, dA, M, dB, N, &beta, dC, M));
   h->last_stream = stream;
   return FTSGEMM_OK;
