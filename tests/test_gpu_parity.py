@@ -1,0 +1,279 @@
+"""GPU parity tests proper (run on the B200 box with -m gpu): the CUDA path, called through the C ABI, against the
+CPU oracle on the same seeded inputs, against the committed golden fixtures, and -- at BASELINE.json's full sizes --
+through size-independent properties.
+
+Tolerances (stated once, used everywhere):
+  * TOL_NORM = 1e-3: Frobenius-norm relative error against the FP32 sequential-k oracle -- the north_star's
+    "within 1e-3 rel of the reference's CPU SGEMM".  The main contraction is single-pass TF32 (operands truncated to
+    10 mantissa bits by the tensor core, FP32 accumulate), measured 6.1e-4 .. 7.8e-4 on B200.
+  * TOL_MODEL = 5e-5: norm-wise against a float64 product of TF32-TRUNCATED operands (what the tensor core computes up
+    to FP32 accumulation order); measured 1.5e-7 (K=64) .. 2e-5 (K=8192).
+  * the reference comparator verify_matrix (utils/utils.cu:61-77; fail iff rel>1e-2 AND abs>1e-2) is applied too; with
+    single-pass TF32 a ~1e-5 fraction of near-zero elements of a K>=1024 product can exceed it (SURVEY.md section 7,
+    hard part 1), so the assertion is on the failing FRACTION (< 1e-4), and exactly zero against the TF32 model.
+"""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_NORM = 1e-3
+TOL_MODEL = 5e-5
+GOLD = json.loads((Path(__file__).parent / "golden" / "ref_cpu_gemm.json").read_text())
+
+
+def _fail_fraction(ref, x):
+    d = np.abs(ref.astype(np.float64) - x.astype(np.float64))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        bad = ((d / np.abs(ref.astype(np.float64))) > 0.01) & (d > 0.01)
+    return float(bad.mean())
+
+
+@pytest.fixture(scope="module")
+def dev(cuda, ft):
+    cuda.cuda.set_device(0)
+    h = ft.FtSgemm()
+    yield h
+    h.close()
+
+
+def _run(cuda, dev, kid, M, N, K, A, B, C0, alpha=1.0, beta=0.0, opts=None):
+    dA, dB = cuda.from_numpy(A).cuda(), cuda.from_numpy(B).cuda()
+    dC = cuda.from_numpy(C0.copy()).cuda()
+    dev.run(kid, M, N, K, dA, dB, dC, alpha, beta, opts)
+    cuda.cuda.synchronize()
+    return dC.cpu().numpy()
+
+
+def _rand(rng, count):
+    return (rng.integers(0, 10, count) * 0.1 * rng.choice([-1.0, 1.0], count)).astype(np.float32)
+
+
+# ------------------------------------------------------------------ golden fixtures (reference inputs, END = n)
+@pytest.mark.parametrize("n", [256, 512, 1024])
+@pytest.mark.parametrize("name", ["small", "medium", "large", "tall", "wide", "huge"])
+def test_reference_inputs_vs_golden_and_oracle(cuda, ft, dev, oracle, n, name):
+    import hashlib
+    A, B, C0 = oracle.make_inputs(n)
+    want = oracle.sgemm_nt(n, n, n, 1.0, A, B, 0.0, C0.copy())
+    assert hashlib.sha256(want.tobytes()).hexdigest() == GOLD[str(n)]["sha256"]["C"]  # oracle == reference cpu_gemm
+    model = oracle.sgemm_nt_tf32_model(n, n, n, 1.0, A, B, 0.0, C0, "trunc")
+    for kid in (ft.SGEMM_IDS[name], ft.ABFT_IDS[name]):
+        got = _run(cuda, dev, kid, n, n, n, A, B, C0)
+        em = oracle.error_metrics(want, got)
+        assert em["rel_fro"] < TOL_NORM, (kid, em)
+        assert oracle.error_metrics(model, got)["rel_fro"] < TOL_MODEL
+        assert _fail_fraction(want, got) < 1e-4
+        assert oracle.verify_matrix(model, got, n, n) == -1
+        # golden scalars: C[0], C[1], C[n], C[n*n-1] and the sum, to the TF32 norm-wise tolerance
+        scale = float(np.sqrt(np.mean(want.astype(np.float64) ** 2)))
+        for idx, v in GOLD[str(n)]["C_sel"].items():
+            assert abs(float(got[int(idx)]) - v) < 5e-3 * scale
+    if name == "huge":  # fault-free FT run must not flag anything
+        st = dev.stats()
+        assert st["detected"] == 0 and st["rows_checked"] > 0
+
+
+def test_ft_equals_plain_bitwise_when_fault_free(cuda, ft, dev):
+    rng = np.random.default_rng(3)
+    M, N, K = 512, 768, 640
+    A, B = _rand(rng, M * K), _rand(rng, N * K)
+    C0 = np.zeros(M * N, np.float32)
+    for name in ("medium", "huge", "wide"):
+        a = _run(cuda, dev, ft.SGEMM_IDS[name], M, N, K, A, B, C0)
+        b = _run(cuda, dev, ft.ABFT_IDS[name], M, N, K, A, B, C0)
+        assert np.array_equal(a, b), name
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 8), (128, 32, 40), (200, 136, 100), (260, 388, 72), (1024, 256, 2048),
+                                   (4, 4, 1), (132, 36, 33)])
+def test_ragged_shapes_alpha_beta(cuda, ft, dev, oracle, shape):
+    M, N, K = shape
+    rng = np.random.default_rng(M * 7 + N)
+    A, B = rng.standard_normal(M * K).astype(np.float32), rng.standard_normal(N * K).astype(np.float32)
+    C0 = rng.standard_normal(M * N).astype(np.float32)
+    want = oracle.sgemm_nt(M, N, K, 0.75, A, B, -1.5, C0.copy())
+    model = oracle.sgemm_nt_tf32_model(M, N, K, 0.75, A, B, -1.5, C0, "trunc")
+    for kid in (1, 2, 6, 5, 11, 12, 16, 15):
+        got = _run(cuda, dev, kid, M, N, K, A, B, C0, 0.75, -1.5)
+        assert oracle.error_metrics(model, got)["rel_fro"] < TOL_MODEL, kid
+        assert oracle.error_metrics(want, got)["rel_fro"] < 2 * TOL_NORM, kid  # beta*C term dilutes; K tiny
+    assert dev.stats()["detected"] == 0
+
+
+def test_unsupported_and_invalid_args(cuda, ft, dev):
+    t = cuda.zeros(64 * 64, device="cuda")
+    with pytest.raises(ft.FtsgemmError) as e:
+        dev.run(16, 62, 64, 64, t, t, t)  # M % 4 != 0 -> TMA stride not 16B
+    assert e.value.code == -2
+    with pytest.raises(ft.FtsgemmError) as e:
+        dev.run(99, 64, 64, 64, t, t, t)
+    assert e.value.code == -1
+    with pytest.raises(ft.FtsgemmError) as e:
+        dev.run(16, 64, 64, 0, t, t, t)
+    assert e.value.code == -1
+
+
+# ------------------------------------------------------------------ cuBLAS rows and the non-fused baseline
+def test_cublas_rows_and_baseline(cuda, ft, dev, oracle):
+    n = 512
+    A, B, C0 = oracle.make_inputs(n)
+    want = oracle.sgemm_nt(n, n, n, 1.0, A, B, 0.0, C0.copy())
+    got = _run(cuda, dev, ft.ID_CUBLAS, n, n, n, A, B, C0)
+    assert oracle.error_metrics(want, got)["rel_fro"] < 1e-6 and oracle.verify_matrix(want, got, n, n) == -1
+    got = _run(cuda, dev, ft.ID_CUBLAS_TF32, n, n, n, A, B, C0)
+    assert oracle.error_metrics(want, got)["rel_fro"] < TOL_NORM
+    for kid, tol in ((ft.ID_ABFT_BASELINE, 1e-6), (ft.ID_ABFT_BASELINE_TF32, TOL_NORM)):
+        got = _run(cuda, dev, kid, n, n, n, A, B, C0)
+        assert oracle.error_metrics(want, got)["rel_fro"] < tol
+    # residual of the baseline's separate checksum pass (detection only, like the reference)
+    dA, dB = cuda.from_numpy(A).cuda(), cuda.from_numpy(B).cuda()
+    dC, res = cuda.zeros(n * n, device="cuda"), cuda.zeros(2, device="cuda")
+    dev.baseline(n, n, n, dA, dB, dC, 1.0, 0.0, False, None, res)
+    cuda.cuda.synchronize()
+    assert float(res.abs().max()) < 0.5  # sum of 512 row/col residuals of an FP32 product
+
+
+# ------------------------------------------------------------------ fault injection: detect + correct
+def test_reference_selftest_every_tile_corrected(cuda, ft, dev, oracle):
+    """The reference's always-on injector (+10000 into one accumulator of every CTA tile, ft_sgemm_huge.cuh:324-327):
+    'FT kernel passes verify_matrix' <=> 'detect + correct worked'."""
+    n = 1024
+    A, B, C0 = oracle.make_inputs(n)
+    want = oracle.sgemm_nt(n, n, n, 1.0, A, B, 0.0, C0.copy())
+    for name in ("small", "medium", "tall", "huge", "wide"):
+        clean = _run(cuda, dev, ft.ABFT_IDS[name], n, n, n, A, B, C0)
+        dev.stats()
+        got = _run(cuda, dev, ft.ABFT_IDS[name], n, n, n, A, B, C0, opts=ft.make_opts(selftest=(10000.0, 17, 5)))
+        st = dev.stats()
+        tiles = st["tiles"]
+        assert tiles == (n // 128) * -(-n // [k for k in ft.kernel_table() if k["id"] == ft.ABFT_IDS[name]][0]["tile"][1])
+        assert st["detected"] == tiles and st["corrected"] == tiles and st["uncorrectable"] == 0
+        diff = np.flatnonzero(got != clean)
+        assert len(diff) <= tiles  # only injected elements may differ (most are restored bit-exactly)
+        assert np.abs(got - clean).max() < 5e-3  # corrected from the FP32 checksum: ~ulp(1e4)
+        assert oracle.error_metrics(want, got)["rel_fro"] < TOL_NORM
+        # without correction the same fault is fatal for the reference comparator
+        bad = _run(cuda, dev, ft.ABFT_IDS[name], n, n, n, A, B, C0,
+                   opts=ft.make_opts(selftest=(10000.0, 17, 5), detect_only=True))
+        st = dev.stats()
+        assert st["detected"] == tiles and st["corrected"] == 0
+        assert oracle.verify_matrix(clean, bad, n, n) != -1
+
+
+@pytest.mark.parametrize("bit", [31, 30, 27, 23, 22, 21, 20])
+def test_single_bit_flips_detected_and_corrected(cuda, ft, dev, bit):
+    """Config 4 of BASELINE.json in miniature: flip one bit of one FP32 accumulator in tensor memory.  Elements with
+    |value| in [8, 64) are chosen so that every listed bit moves the value by >= 1 (bit 20 of an element in [8,16));
+    the per-bit detection/correction RATES over random elements are measured by scripts/fault_campaign.py."""
+    rng = np.random.default_rng(bit)
+    M = N = 512
+    K = 2048
+    A, B = _rand(rng, M * K), _rand(rng, N * K)
+    C0 = np.zeros(M * N, np.float32)
+    clean = _run(cuda, dev, 16, M, N, K, A, B, C0)
+    cand = np.flatnonzero((np.abs(clean) >= 8) & (np.abs(clean) < 64))
+    faults, seen = [], set()
+    for idx in rng.permutation(cand):
+        r, c = int(idx % M), int(idx // M)
+        if (r, c // 128) in seen:
+            continue
+        seen.add((r, c // 128))  # one fault per (row, tile)
+        faults.append({"row": r, "col": c, "xor": 1 << bit})
+        if len(faults) == 6:
+            break
+    dev.stats()
+    got = _run(cuda, dev, 16, M, N, K, A, B, C0, opts=ft.make_opts(faults=faults))
+    st = dev.stats()
+    assert st["detected"] == len(faults) == st["corrected"], st
+    located = {(e["row"], e["col"]) for e in st["events"]}
+    assert located == {(f["row"], f["col"]) for f in faults}
+    assert np.abs(got - clean).max() < 2e-2
+    for f in faults:  # everything except the faulty elements is bit-identical to the fault-free run
+        idx = f["row"] + f["col"] * M
+        got[idx] = clean[idx]
+    assert np.array_equal(got, clean)
+
+
+def test_low_order_flip_below_threshold_is_harmless(cuda, ft, dev):
+    rng = np.random.default_rng(9)
+    M = N = 256
+    K = 1024
+    A, B = _rand(rng, M * K), _rand(rng, N * K)
+    C0 = np.zeros(M * N, np.float32)
+    clean = _run(cuda, dev, 16, M, N, K, A, B, C0)
+    got = _run(cuda, dev, 16, M, N, K, A, B, C0, opts=ft.make_opts(faults=[{"row": 3, "col": 9, "xor": 1 << 2}]))
+    assert np.abs(got - clean).max() < 1e-4  # an undetected flip is below the rounding floor by construction
+
+
+def test_two_faults_in_one_row_reported_uncorrectable(cuda, ft, dev):
+    rng = np.random.default_rng(11)
+    M = N = 256
+    K = 512
+    A, B = _rand(rng, M * K), _rand(rng, N * K)
+    C0 = np.zeros(M * N, np.float32)
+    _run(cuda, dev, 16, M, N, K, A, B, C0,
+         opts=ft.make_opts(faults=[{"row": 40, "col": 10, "add": 100.0}, {"row": 40, "col": 90, "add": -37.0}]))
+    st = dev.stats()
+    assert st["detected"] == 1 and st["corrected"] == 0 and st["uncorrectable"] == 1
+
+
+# ------------------------------------------------------------------ host-buffer (e2e) entry point
+def test_run_host_matches_device_path(cuda, ft, dev, oracle):
+    n = 384
+    A, B, C0 = oracle.make_inputs(n)
+    C0 = np.random.default_rng(0).standard_normal(n * n).astype(np.float32)
+    want = _run(cuda, dev, 16, n, n, n, A, B, C0, 1.0, -1.5)
+    hC = C0.copy()
+    dev.run_host(16, n, n, n, A, B, hC, 1.0, -1.5, None)
+    assert np.array_equal(hC, want)
+
+
+# ------------------------------------------------------------------ BASELINE.json full sizes: properties
+@pytest.mark.parametrize("n,kid", [(4096, 16), (4096, 15), (8192, 16)])
+def test_full_size_properties(cuda, ft, dev, oracle, n, kid):
+    """Size-independent checks at the metric's sizes: (1) sampled rows against the CPU oracle, (2) the checksum of
+    checksums e^T C e = (e^T A)(B^T e) in float64, (3) linearity in alpha, (4) injected faults are repaired in place."""
+    torch = cuda
+    g = torch.Generator(device="cuda").manual_seed(n)
+    dA = (torch.randint(0, 10, (n * n,), generator=g, device="cuda").float() * 0.1) * \
+        (torch.randint(0, 2, (n * n,), generator=g, device="cuda").float() * 2 - 1)
+    dB = (torch.randint(0, 10, (n * n,), generator=g, device="cuda").float() * 0.1) * \
+        (torch.randint(0, 2, (n * n,), generator=g, device="cuda").float() * 2 - 1)
+    dC = torch.zeros(n * n, device="cuda")
+    dev.stats()
+    dev.run(kid, n, n, n, dA, dB, dC, 1.0, 0.0, None)
+    torch.cuda.synchronize()
+    st = dev.stats()
+    assert st["detected"] == 0 and st["rows_checked"] >= n * (n // 256)
+    # (1) 16 sampled rows x all columns on the host cores
+    rows = np.random.default_rng(n).choice(n, 16, replace=False)
+    A, B = dA.cpu().numpy(), dB.cpu().numpy()
+    want = oracle.sgemm_nt_rows(n, n, n, 1.0, A, B, 0.0, None, rows)
+    got = dC.view(n, n).t()[torch.from_numpy(rows).cuda()].cpu().numpy()  # C is column-major
+    assert np.linalg.norm(want - got) / np.linalg.norm(want) < TOL_NORM
+    # (2) checksum of checksums (TF32-truncated operands, float64 reference)
+    At = (dA.view(torch.int32) & -8192).view(torch.float32).double().view(n, n)  # [k][m]
+    Bt = (dB.view(torch.int32) & -8192).view(torch.float32).double().view(n, n)  # [k][n]
+    ref_total = float((At.sum(1) * Bt.sum(1)).sum())
+    got_total = float(dC.double().sum())
+    denom = float((At.abs().sum(1) * Bt.abs().sum(1)).sum())
+    assert abs(ref_total - got_total) / denom < 1e-6
+    # (3) linearity: alpha = 2 gives exactly twice the result (power-of-two scaling is exact in FP32)
+    dC2 = torch.zeros(n * n, device="cuda")
+    dev.run(kid, n, n, n, dA, dB, dC2, 2.0, 0.0, None)
+    torch.cuda.synchronize()
+    assert torch.equal(dC2, dC * 2)
+    # (4) faults in distinct tiles are repaired; all other elements stay bit-identical
+    faults = [{"row": 1234, "col": 4000, "xor": 1 << 30}, {"row": 17, "col": 5, "add": 10000.0},
+              {"row": n - 1, "col": n - 1, "xor": 1 << 31}]
+    dC3 = torch.zeros(n * n, device="cuda")
+    dev.run(kid, n, n, n, dA, dB, dC3, 1.0, 0.0, ft.make_opts(faults=faults))
+    torch.cuda.synchronize()
+    st = dev.stats()
+    assert st["detected"] == 3 and st["corrected"] == 3
+    delta = (dC3 - dC).abs()
+    assert int((delta > 0).sum()) <= 3 and float(delta.max()) < 2e-2
