@@ -26,8 +26,8 @@ MAX_EVENTS = 16
 
 # kernel ids (include/ftsgemm.h; reference sgemm.cu:235-237)
 ID_CUBLAS, ID_CUBLAS_TF32, ID_ABFT_BASELINE, ID_ABFT_BASELINE_TF32 = 0, 7, 10, 30
-SGEMM_IDS = {"small": 1, "medium": 2, "large": 3, "tall": 4, "wide": 5, "huge": 6, "giant": 21}
-ABFT_IDS = {"small": 11, "medium": 12, "large": 13, "tall": 14, "wide": 15, "huge": 16, "giant": 31}
+SGEMM_IDS = {"small": 1, "medium": 2, "large": 3, "tall": 4, "wide": 5, "huge": 6, "giant": 21, "pair128": 22}
+ABFT_IDS = {"small": 11, "medium": 12, "large": 13, "tall": 14, "wide": 15, "huge": 16, "giant": 31, "pair128": 32}
 
 
 class FtsgemmError(RuntimeError):

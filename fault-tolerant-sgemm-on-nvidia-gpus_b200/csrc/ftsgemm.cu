@@ -26,31 +26,35 @@ using namespace ftsgemm;
 // ------------------------------------------------------------------------------------------- variant table
 struct Variant {
   ftsgemm_kernel_info info;
-  int bn;  // CTA tile N of the tcgen05 kernel (0 for library rows)
+  int bn;  // CTA(-pair) tile N of the tcgen05 kernel (0 for library rows)
+  int cg;  // 1 = one CTA per tile (UMMA M = 128), 2 = CTA pair per tile (cta_group::2, UMMA M = 256)
 };
 
-// Reference tiles from code_gen/main.py:8-16; sm_100a tiles: UMMA M is 128 (cta_group::1), so the reference's
-// "tall" (128x32) and "huge" (128x128) shapes are literal, the others map to the nearest UMMA-legal shape with
-// the same role (fewer/larger CTAs).  tile_k = K extent of one shared-memory stage (4 UMMA k-steps of 8).
+// Reference tiles from code_gen/main.py:8-16; sm_100a tiles: UMMA M is 128 per CTA, so the reference's "tall"
+// (128x32) and "huge" (128x128) shapes are literal, the others map to the nearest UMMA-legal shape with the same
+// role (fewer/larger CTAs).  "giant" (ids 21/31) is the B200-only CTA-pair tile 256x256.  tile_k = K extent of one
+// shared-memory stage (4 UMMA k-steps of 8).
 const Variant kVariants[] = {
-    {{0, "cublas", 0, 0, 0, 0, 0, 0, 0, 0}, 0},
-    {{1, "kernel_sgemm_small", 0, 1, 16, 16, 16, 128, 32, 32}, 32},
-    {{2, "kernel_sgemm_medium", 0, 1, 32, 32, 8, 128, 64, 32}, 64},
-    {{3, "kernel_sgemm_large", 0, 1, 64, 64, 8, 128, 128, 32}, 128},
-    {{4, "kernel_sgemm_tall", 0, 1, 128, 32, 8, 128, 32, 32}, 32},
-    {{5, "kernel_sgemm_wide", 0, 1, 32, 128, 8, 128, 256, 32}, 256},
-    {{6, "kernel_sgemm_huge", 0, 1, 128, 128, 8, 128, 128, 32}, 128},
-    {{7, "cublas_tf32", 0, 0, 0, 0, 0, 0, 0, 0}, 0},
-    {{10, "abft_baseline", 1, 2, 0, 0, 256, 0, 0, 256}, 0},
-    {{11, "abft_kernel_small", 1, 1, 16, 16, 16, 128, 32, 32}, 32},
-    {{12, "abft_kernel_medium", 1, 1, 32, 32, 8, 128, 64, 32}, 64},
-    {{13, "abft_kernel_large", 1, 1, 64, 64, 8, 128, 128, 32}, 128},
-    {{14, "abft_kernel_tall", 1, 1, 128, 32, 8, 128, 32, 32}, 32},
-    {{15, "abft_kernel_wide", 1, 1, 32, 128, 8, 128, 256, 32}, 256},
-    {{16, "abft_kernel_huge", 1, 1, 128, 128, 8, 128, 128, 32}, 128},
-    {{21, "kernel_sgemm_giant", 0, 1, 0, 0, 0, 128, 256, 32}, 256},
-    {{30, "abft_baseline_tf32", 1, 2, 0, 0, 256, 0, 0, 256}, 0},
-    {{31, "abft_kernel_giant", 1, 1, 0, 0, 0, 128, 256, 32}, 256},
+    {{0, "cublas", 0, 0, 0, 0, 0, 0, 0, 0}, 0, 0},
+    {{1, "kernel_sgemm_small", 0, 1, 16, 16, 16, 128, 32, 32}, 32, 1},
+    {{2, "kernel_sgemm_medium", 0, 1, 32, 32, 8, 128, 64, 32}, 64, 1},
+    {{3, "kernel_sgemm_large", 0, 1, 64, 64, 8, 128, 128, 32}, 128, 1},
+    {{4, "kernel_sgemm_tall", 0, 1, 128, 32, 8, 128, 32, 32}, 32, 1},
+    {{5, "kernel_sgemm_wide", 0, 1, 32, 128, 8, 128, 256, 32}, 256, 1},
+    {{6, "kernel_sgemm_huge", 0, 1, 128, 128, 8, 128, 128, 32}, 128, 1},
+    {{7, "cublas_tf32", 0, 0, 0, 0, 0, 0, 0, 0}, 0, 0},
+    {{10, "abft_baseline", 1, 2, 0, 0, 256, 0, 0, 256}, 0, 0},
+    {{11, "abft_kernel_small", 1, 1, 16, 16, 16, 128, 32, 32}, 32, 1},
+    {{12, "abft_kernel_medium", 1, 1, 32, 32, 8, 128, 64, 32}, 64, 1},
+    {{13, "abft_kernel_large", 1, 1, 64, 64, 8, 128, 128, 32}, 128, 1},
+    {{14, "abft_kernel_tall", 1, 1, 128, 32, 8, 128, 32, 32}, 32, 1},
+    {{15, "abft_kernel_wide", 1, 1, 32, 128, 8, 128, 256, 32}, 256, 1},
+    {{16, "abft_kernel_huge", 1, 1, 128, 128, 8, 128, 128, 32}, 128, 1},
+    {{21, "kernel_sgemm_giant", 0, 1, 0, 0, 0, 256, 256, 32}, 256, 2},
+    {{22, "kernel_sgemm_pair128", 0, 1, 0, 0, 0, 256, 128, 32}, 128, 2},
+    {{30, "abft_baseline_tf32", 1, 2, 0, 0, 256, 0, 0, 256}, 0, 0},
+    {{31, "abft_kernel_giant", 1, 1, 0, 0, 0, 256, 256, 32}, 256, 2},
+    {{32, "abft_kernel_pair128", 1, 1, 0, 0, 0, 256, 128, 32}, 128, 2},
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
@@ -83,8 +87,10 @@ struct ftsgemm_handle_s {
   cublasHandle_t cublas = nullptr;
   EncodeTiledFn encode_tiled = nullptr;
   DeviceStats *d_stats = nullptr;
-  float *d_chk = nullptr;       // checksum panel [K][ntiles*32]
+  float *d_chk = nullptr;       // encoded checksum vectors [K][tiles_n*8]  (extra "rows" of B)
   size_t chk_bytes = 0;
+  float *d_chk_out = nullptr;   // expected checksums M x (tiles_n*8), column-major, + slab flags behind it
+  size_t chk_out_bytes = 0;
   const float *chk_for_b = nullptr;  // B pointer / shape the panel was encoded from
   int chk_n = 0, chk_k = 0, chk_bn = 0;
   float *d_aux = nullptr;       // baseline vectors
@@ -134,40 +140,50 @@ int make_tmap_2d(ftsgemm_handle_t h, CUtensorMap *tm, const float *base, uint64_
   return FTSGEMM_OK;
 }
 
-template <int BN, bool FT>
+template <int BN, bool FT, int CG>
 int launch_tc(ftsgemm_handle_t h, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
               const KernelParams &p, cudaStream_t stream) {
-  using Cfg = TileCfg<BN, FT>;
-  auto kern = ftsgemm_tc_kernel<BN, FT>;
+  using Cfg = TileCfg<BN, FT, CG>;
+  auto kern = ftsgemm_tc_kernel<BN, FT, CG>;
   static bool attr_set = false;
   if (!attr_set) {
     FT_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int num_tiles = p.tiles_m * p.tiles_n;
-  int grid = static_cast<int>(dbg("grid", 0));
-  if (grid <= 0) grid = h->num_sms;
-  if (grid > num_tiles) grid = num_tiles;
-  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
-  FT_CUDA(h, cudaGetLastError());
+  const int num_tiles = p.tiles_m * (p.tiles_n + p.tiles_c);
+  int units = static_cast<int>(dbg("grid", 0));
+  if (units <= 0) units = h->num_sms / CG;
+  if (units > num_tiles) units = num_tiles;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(units * CG);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (CG > 1) ? 1 : 0;
+  FT_CUDA(h, cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p));
   return FTSGEMM_OK;
 }
 
-int ensure_chk(ftsgemm_handle_t h, size_t bytes, cudaStream_t stream) {
-  if (h->chk_bytes >= bytes) return FTSGEMM_OK;
-  if (h->d_chk) FT_CUDA(h, cudaFree(h->d_chk));
-  h->d_chk = nullptr;
-  h->chk_bytes = 0;
-  h->chk_for_b = nullptr;
-  FT_CUDA(h, cudaMalloc(&h->d_chk, bytes));  // fully overwritten by every encode pass (unused columns as zeros)
-  (void)stream;
-  h->chk_bytes = bytes;
+int ensure_buf(ftsgemm_handle_t h, float **buf, size_t *have, size_t bytes) {
+  if (*have >= bytes) return FTSGEMM_OK;
+  if (*buf) FT_CUDA(h, cudaFree(*buf));
+  *buf = nullptr;
+  *have = 0;
+  FT_CUDA(h, cudaMalloc(buf, bytes));
+  *have = bytes;
   return FTSGEMM_OK;
 }
 
 int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const float *dA, const float *dB, float *dC,
            float alpha, float beta, const ftsgemm_opts &o, cudaStream_t stream) {
-  const int BN = v.bn;
+  const int BN = v.bn, CG = v.cg;
   const bool ft = v.info.fault_tolerant != 0;
   if ((M % 4) || (N % 4)) return FTSGEMM_ERR_UNSUPPORTED;  // TMA global strides must be multiples of 16 bytes
   if ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB) | reinterpret_cast<uintptr_t>(dC)) & 15)
@@ -178,7 +194,7 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
   p.M = M; p.N = N; p.K = K;
   p.C = dC; p.ldc = M;
   p.alpha = alpha; p.beta = beta;
-  p.tiles_m = (M + kBM - 1) / kBM;
+  p.tiles_m = (M + kBM * CG - 1) / (kBM * CG);
   p.tiles_n = (N + BN - 1) / BN;
   long long g = dbg("group_n", 0);
   p.group_n = g > 0 ? static_cast<int>(g) : (2048 / BN > 0 ? 2048 / BN : 1);
@@ -214,36 +230,43 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
   if (rc) return rc;
   tmC = tmB;
   if (ft) {
-    const int chk_ld = p.tiles_n * kAtomMN;
-    rc = ensure_chk(h, static_cast<size_t>(K) * chk_ld * sizeof(float), stream);
+    // checksum vectors of B: 8 columns per N-tile, appended to B as extra tile-columns of the same GEMM
+    p.n_chk_cols = p.tiles_n * kChkPerTile;
+    p.tiles_c = (p.n_chk_cols + BN - 1) / BN;
+    const int n_slabs = p.tiles_m * CG * (kBM / 32);
+    const float *chk_before = h->d_chk;
+    rc = ensure_buf(h, &h->d_chk, &h->chk_bytes, static_cast<size_t>(K) * p.n_chk_cols * sizeof(float));
     if (rc) return rc;
+    if (h->d_chk != chk_before) h->chk_for_b = nullptr;  // reallocated: the cached encode is gone
+    const size_t out_floats = static_cast<size_t>(M) * p.n_chk_cols;
+    rc = ensure_buf(h, &h->d_chk_out, &h->chk_out_bytes, (out_floats + n_slabs) * sizeof(float));
+    if (rc) return rc;
+    p.chk_out = h->d_chk_out;
+    p.chk_flags = reinterpret_cast<int *>(h->d_chk_out + out_floats);
+    FT_CUDA(h, cudaMemsetAsync(p.chk_flags, 0, n_slabs * sizeof(int), stream));
     const bool reuse = o.reuse_b_checksums && h->chk_for_b == dB && h->chk_n == N && h->chk_k == K && h->chk_bn == BN;
     if (!reuse) {
       dim3 grid(p.tiles_n, (K + kEncWarps * kEncKPerWarp - 1) / (kEncWarps * kEncKPerWarp));
-      encode_b_kernel<<<grid, kEncWarps * 32, 0, stream>>>(dB, N, K, N, BN, h->d_chk, chk_ld,
+      encode_b_kernel<<<grid, kEncWarps * 32, 0, stream>>>(dB, N, K, N, BN, h->d_chk, p.n_chk_cols,
                                                            static_cast<int>(dbg("enc_rounding", 0)));
       FT_CUDA(h, cudaGetLastError());
       h->chk_for_b = dB; h->chk_n = N; h->chk_k = K; h->chk_bn = BN;
     }
-    rc = make_tmap_2d(h, &tmC, h->d_chk, chk_ld, K, chk_ld, kAtomMN, kBK);
+    rc = make_tmap_2d(h, &tmC, h->d_chk, p.n_chk_cols, K, p.n_chk_cols, kAtomMN, kBK);
     if (rc) return rc;
   }
   h->last_stream = stream;
-  if (ft) {
-    switch (BN) {
-      case 32: return launch_tc<32, true>(h, tmA, tmB, tmC, p, stream);
-      case 64: return launch_tc<64, true>(h, tmA, tmB, tmC, p, stream);
-      case 128: return launch_tc<128, true>(h, tmA, tmB, tmC, p, stream);
-      case 256: return launch_tc<256, true>(h, tmA, tmB, tmC, p, stream);
-    }
-  } else {
-    switch (BN) {
-      case 32: return launch_tc<32, false>(h, tmA, tmB, tmC, p, stream);
-      case 64: return launch_tc<64, false>(h, tmA, tmB, tmC, p, stream);
-      case 128: return launch_tc<128, false>(h, tmA, tmB, tmC, p, stream);
-      case 256: return launch_tc<256, false>(h, tmA, tmB, tmC, p, stream);
-    }
-  }
+#define FT_DISPATCH(bn, cg)                                                          \
+  if (BN == bn && CG == cg)                                                          \
+    return ft ? launch_tc<bn, true, cg>(h, tmA, tmB, tmC, p, stream)                 \
+              : launch_tc<bn, false, cg>(h, tmA, tmB, tmC, p, stream);
+  FT_DISPATCH(32, 1)
+  FT_DISPATCH(64, 1)
+  FT_DISPATCH(128, 1)
+  FT_DISPATCH(256, 1)
+  FT_DISPATCH(128, 2)
+  FT_DISPATCH(256, 2)
+#undef FT_DISPATCH
   return FTSGEMM_ERR_UNSUPPORTED;
 }
 
@@ -379,6 +402,7 @@ int ftsgemm_destroy(ftsgemm_handle_t h) {
   if (h->cublas) cublasDestroy(h->cublas);
   cudaFree(h->d_stats);
   cudaFree(h->d_chk);
+  cudaFree(h->d_chk_out);
   cudaFree(h->d_aux);
   cudaFree(h->d_verify);
   for (int i = 0; i < 3; ++i) cudaFree(h->d_stage[i]);

@@ -3,31 +3,34 @@
 // Replaces the reference's code-generated CUDA-core kernels
 //   sgemm_{small..huge}    (/root/reference/kernel/ft_sgemm/include_code_gen/sgemm_*.cuh:11)     [FT = false]
 //   ft_sgemm_{small..huge} (/root/reference/kernel/ft_sgemm/include_code_gen/ft_sgemm_*.cuh:11)  [FT = true]
-// with ONE warp-specialised, persistent tcgen05 kernel template:
+// with ONE warp-specialised, persistent tcgen05 kernel template <BN, FT, CG>:
 //
-//   warp 0   TMA producer   : cp.async.bulk.tensor 32(M|N) x 32(K) fp32 boxes, 128B swizzle with 32B atoms,
-//                             into a STAGES-deep shared-memory ring (full/empty mbarriers)
-//   warp 1   MMA issuer     : one thread issues tcgen05.mma.kind::tf32 (UMMA 128 x BN x 8, FP32 accumulate in TMEM);
-//                             when FT, a second UMMA 128 x 16 x 8 per k-step multiplies the same A tile by the
-//                             *checksum columns* of the B tile, so the expected row checksums accumulate in 16 extra
-//                             TMEM columns next to the data ("checksum GEMM rides the same TMEM tile")
+//   CG = 1 : one CTA per tile, UMMA 128 x BN x 8 (cta_group::1)
+//   CG = 2 : a CTA PAIR (cluster of 2 on one TPC) per 256 x BN tile, UMMA 256 x BN x 8 (cta_group::2): each CTA stages
+//            its own 128 rows of A and its own HALF of the B tile, so per-SM shared-memory traffic per flop halves --
+//            the limiter measured on B200 (profiles/r01_ncu_*_v1.txt: TMA writes + UMMA reads share ~128 B/clk/SM)
+//
+//   warp 0   TMA producer   : cp.async.bulk.tensor 32(M|N) x 32(K) fp32 boxes, 128B swizzle with 32B atoms, into a
+//                             STAGES-deep shared-memory ring (full/empty mbarriers)
+//   warp 1   MMA issuer     : one thread (of the pair's leader CTA) issues tcgen05.mma.kind::tf32, FP32 accumulate in
+//                             TMEM, two accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1
 //   warp 2   TMEM allocator
-//   warps 4-7 epilogue      : tcgen05.ld the accumulator (lane = row), per-row detect / locate / correct against the
-//                             checksum columns, then C = alpha*acc + beta*C with coalesced column-major stores
+//   warps 4-7 epilogue      : tcgen05.ld (lane = row), per-row ABFT detect / locate / correct, C = alpha*acc + beta*C
 //
-// ABFT scheme.  For a CTA tile with rows I (128) and columns J (BN), with b~ the TF32 value
-// the tensor core actually consumes:
-//   encode    (pre-pass, encode.cuh; reference ft_sgemm_huge.cuh:150-168)
-//             e[k] = sum_{n in J} b~[n,k]         w[k] = sum_{n in J} (n-n0+1) b~[n,k]      (3-way TF32 split each)
-//   checksum GEMM (tensor core; reference :171-213)
-//             r1[m] = sum_k a~[m,k] e[k]          r2[m] = sum_k a~[m,k] w[k]
-//   detect    (epilogue; reference :328-421)
-//             d1[m] = r1[m] - sum_n acc[m,n]      d2[m] = r2[m] - sum_n (n-n0+1) acc[m,n]
+// ABFT scheme.  With b~ = the TF32 value the tensor core actually consumes and J_t the columns
+// of N-tile t:
+//   encode    (pre-pass encode_b_kernel; reference ENCODE ft_sgemm_huge.cuh:150-168)
+//             e_t[k] = sum_{n in J_t} b~[n,k]      w_t[k] = sum_{n in J_t} (n-n0+1) b~[n,k]     (3-way TF32 split each)
+//   checksum GEMM (reference CHECKSUM-GEMV :171-213): the 8 checksum vectors of every N-tile are appended to B as extra
+//             "rows", i.e. the SAME kernel computes extra tile-columns  R = A * [e_t, w_t]^T  first (FP32 accumulate in
+//             TMEM, identical operand rounding), writes them to a small workspace and publishes a per-32-row flag.
+//             Cost: 8 columns per BN data columns (3 % at BN = 256) instead of a second pass over A.
+//   detect    (epilogue; reference :328-421)  d1[m] = r1[m] - sum_n acc[m,n],  d2[m] = r2[m] - sum_n (n-n0+1) acc[m,n],
 //             flagged iff |d1| > tau_abs + tau_rel * sum_n |acc[m,n]|
 //   locate    column j = round(d2/d1) - 1   (weighted checksum; the reference intersects a row and a column residual)
-//   correct   acc[m,j] = r1[m] - sum_{n != j} acc[m,n]  (recomputed, so it also repairs Inf/NaN/huge upsets;
+//   correct   acc[m,j] = r1[m] - sum_{n != j} acc[m,n]   (recomputed, so Inf/NaN/huge upsets are repaired too;
 //             reference :422-485 adds the row residual)
-// One error per (row, tile) is correctable, i.e. up to 128 per tile (the reference: one per tile per check).
+// One error per (row, tile) is correctable, i.e. up to 128 per CTA tile (the reference: one per tile per check).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -37,11 +40,10 @@
 
 namespace ftsgemm {
 
-constexpr int kBM = 128;          // UMMA M (cta_group::1)
+constexpr int kBM = 128;          // rows per CTA (UMMA M = 128 * CG)
 constexpr int kBK = 32;           // K extent of one shared-memory stage (4 UMMA k-steps of 8)
 constexpr int kAtomMN = 32;       // floats per 128-byte swizzle row
-constexpr int kChkCols = 16;      // UMMA N of the checksum GEMM (6 columns used)
-constexpr int kChkUsed = 6;
+constexpr int kChkPerTile = 8;    // checksum columns per N-tile (6 used: e hi/mid/lo, w hi/mid/lo)
 constexpr int kThreads = 256;
 constexpr int kMaxFaults = 8;
 constexpr int kMaxEvents = 16;
@@ -68,11 +70,15 @@ struct KernelParams {
   float *C;
   int ldc;
   float alpha, beta;
-  // tile schedule
+  // tile schedule (tiles_m counts CG*128-row blocks)
   int tiles_m, tiles_n, group_n;
   // UMMA shared-memory descriptor parameters (runtime so the bring-up probe can sweep them)
   unsigned int lbo_bytes, sbo_bytes, layout_type, kstep_bytes;
-  // fault tolerance
+  // fault tolerance: checksum tile-columns
+  int tiles_c;          // number of BN-wide checksum tile-columns (0 when FT is off)
+  int n_chk_cols;       // tiles_n * kChkPerTile
+  float *chk_out;       // M x n_chk_cols, column-major (ld = M): expected checksums r1/r2 (3-way split)
+  int *chk_flags;       // one counter per 32-row slab; == tiles_c once that slab's checksums are published
   float tau_abs, tau_rel;
   int detect_only;
   int inject_mode;
@@ -83,15 +89,16 @@ struct KernelParams {
   DeviceStats *stats;
 };
 
-template <int BN, bool FT>
+template <int BN, bool FT, int CG>
 struct TileCfg {
+  static_assert(CG == 1 || CG == 2, "cta_group");
+  static_assert(BN % (32 * CG) == 0 && BN >= 32 && BN <= 256, "tile N");
+  static constexpr int kBNLocal = BN / CG;                  // B rows staged by this CTA
   static constexpr int kABytes = kBM * kBK * 4;
-  static constexpr int kBBytes = BN * kBK * 4;
-  static constexpr int kCBytes = FT ? kAtomMN * kBK * 4 : 0;
-  static constexpr int kStageBytes = kABytes + kBBytes + kCBytes;
-  static constexpr int kAccStride = FT ? BN + 32 : BN;            // TMEM columns per accumulator stage
-  static constexpr int kAccStages = (2 * kAccStride <= 512) ? 2 : 1;
-  static constexpr int kTmemNeeded = kAccStages * kAccStride;
+  static constexpr int kBBytes = kBNLocal * kBK * 4;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kAccStages = (2 * BN <= 512) ? 2 : 1;
+  static constexpr int kTmemNeeded = kAccStages * BN;
   static constexpr int kTmemCols = kTmemNeeded <= 32 ? 32 : kTmemNeeded <= 64 ? 64 : kTmemNeeded <= 128 ? 128
                                    : kTmemNeeded <= 256 ? 256 : 512;
   static constexpr int kMaxSmem = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*barriers*/;
@@ -103,26 +110,273 @@ struct TileCfg {
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
 __device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
 
-__device__ __forceinline__ void decode_tile(const KernelParams &p, int t, int &m_blk, int &n_blk) {
+struct TileCoord {
+  int m_blk, n_blk;  // n_blk indexes checksum tile-columns when is_chk
+  bool is_chk;
+};
+
+// Tile order: all checksum tile-columns first (so their results are published long before the data tiles that need
+// them reach their epilogue), then the data tiles in groups of group_n tile-columns, M fastest inside a group, so
+// that one wave of CTAs shares few A row-panels and few B row-panels in L2.
+__device__ __forceinline__ TileCoord decode_tile(const KernelParams &p, int t) {
+  TileCoord tc;
+  const int n_chk_tiles = p.tiles_c * p.tiles_m;
+  if (t < n_chk_tiles) {
+    tc.is_chk = true;
+    tc.m_blk = t % p.tiles_m;
+    tc.n_blk = t / p.tiles_m;
+    return tc;
+  }
+  t -= n_chk_tiles;
+  tc.is_chk = false;
   const int per_group = p.group_n * p.tiles_m;
   const int g = t / per_group;
   const int first_n = g * p.group_n;
   const int gsz = min(p.group_n, p.tiles_n - first_n);
   const int local = t - g * per_group;
-  n_blk = first_n + local % gsz;
-  m_blk = local / gsz;
+  tc.n_blk = first_n + local % gsz;
+  tc.m_blk = local / gsz;
+  return tc;
 }
 
-template <int BN, bool FT>
+__device__ __forceinline__ int ld_acquire(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Epilogue store pass: out = alpha*acc + beta*out, column-major, lane = consecutive rows -> 128-byte coalesced.
+// ------------------------------------------------------------------------------------------------------------
+template <int BN>
+__device__ __forceinline__ void store_tile(uint32_t taddr, float *crow, bool row_ok, int n0, int n_limit, int ldc,
+                                           float alpha, float beta, int fix_col, float fix_val) {
+  const bool full_n = (n0 + BN <= n_limit);
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t v[32];
+    ptx::tmem_ld_x32(taddr + c * 32, v);
+    ptx::tmem_wait_ld();
+    if (fix_col >= 0 && (fix_col >> 5) == c) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i == (fix_col & 31)) v[i] = f2u(fix_val);
+    }
+    const int nb = n0 + c * 32;
+    if (!row_ok) continue;
+    if (full_n) {
+      if (beta == 0.0f) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) crow[static_cast<size_t>(nb + i) * ldc] = alpha * u2f(v[i]);
+      } else {
+        float old[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) old[i] = crow[static_cast<size_t>(nb + i) * ldc];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) crow[static_cast<size_t>(nb + i) * ldc] = alpha * u2f(v[i]) + beta * old[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (nb + i < n_limit) {
+          float *dst = crow + static_cast<size_t>(nb + i) * ldc;
+          const float o = (beta == 0.0f) ? 0.0f : beta * (*dst);
+          *dst = alpha * u2f(v[i]) + o;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// ABFT check of one accumulator tile (executed by the 4 epilogue warps, lane = row).  Returns the column to replace
+// (or -1) and its corrected value.  q = TMEM lane quadrant of this warp, m = global row of this lane.
+// ------------------------------------------------------------------------------------------------------------
+template <int BN>
+__device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr, int q, int lane, int m, int m0_cta,
+                                           int n0, int n_blk, int &fix_col, float &fix_val) {
+  // ---- fault injection into the TMEM accumulator (reference: ft_sgemm_huge.cuh:324-327) ----
+  if (p.inject_mode == 1) {
+    if ((p.selftest_row >> 5) == q && p.selftest_col < BN) {
+      uint32_t x = ptx::tmem_ld_x1(taddr + p.selftest_col);
+      ptx::tmem_wait_ld();
+      if (lane == (p.selftest_row & 31)) x = f2u(u2f(x) + p.selftest_value);
+      ptx::tmem_st_x1(taddr + p.selftest_col, x);
+      ptx::tmem_wait_st();
+    }
+  } else if (p.inject_mode == 2) {
+    for (int f = 0; f < p.n_faults; ++f) {
+      const int tr = p.faults[f].row - m0_cta, tc = p.faults[f].col - n0;
+      if (tr >= 0 && tr < kBM && tc >= 0 && tc < BN && (tr >> 5) == q) {  // warp-uniform
+        uint32_t x = ptx::tmem_ld_x1(taddr + tc);
+        ptx::tmem_wait_ld();
+        if (lane == (tr & 31))
+          x = p.faults[f].mode == 0 ? f2u(u2f(x) + p.faults[f].add_value) : (x ^ p.faults[f].xor_mask);
+        ptx::tmem_st_x1(taddr + tc, x);
+        ptx::tmem_wait_st();
+      }
+    }
+  }
+  // ---- pass 1: actual row checksums (thread-local: lane == row) ----
+  float s1 = 0.0f, s2 = 0.0f, sabs = 0.0f;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t v[32];
+    ptx::tmem_ld_x32(taddr + c * 32, v);
+    ptx::tmem_wait_ld();
+    const float wbase = static_cast<float>(c * 32 + 1);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float f = u2f(v[i]);
+      s1 += f;
+      s2 = fmaf(f, wbase + static_cast<float>(i), s2);
+      sabs += fabsf(f);
+    }
+  }
+  // ---- expected checksums published by the checksum tile-columns (wait for this 32-row slab's flag) ----
+  {
+    const int *flag = p.chk_flags + (m0_cta >> 5) + q;
+    if (lane == 0) {
+      unsigned spins = 0;
+      while (ld_acquire(flag) < p.tiles_c) {
+        __nanosleep(64);
+        if (++spins > (1u << 24)) __trap();
+      }
+    }
+    __syncwarp();
+  }
+  float r1 = 0.0f, r2 = 0.0f;
+  if (m < p.M) {
+    const float *cp = p.chk_out + static_cast<size_t>(n_blk) * kChkPerTile * p.M + m;
+    const float e0 = __ldcg(cp), e1 = __ldcg(cp + p.M), e2 = __ldcg(cp + 2 * static_cast<size_t>(p.M));
+    const float w0 = __ldcg(cp + 3 * static_cast<size_t>(p.M)), w1 = __ldcg(cp + 4 * static_cast<size_t>(p.M)),
+                w2 = __ldcg(cp + 5 * static_cast<size_t>(p.M));
+    r1 = e0 + (e1 + e2);
+    r2 = w0 + (w1 + w2);
+  }
+  const float d1 = r1 - s1, d2 = r2 - s2;
+  const float thr = p.tau_abs + p.tau_rel * sabs;
+  const bool flagged = !(fabsf(d1) <= thr);  // also true for NaN
+  const unsigned flag_mask = __ballot_sync(0xffffffffu, flagged);
+
+  // fault-free residual statistics (threshold calibration)
+  {
+    float ra = flagged ? 0.0f : fabsf(d1);
+    float rr = flagged ? 0.0f : fabsf(d1) / fmaxf(sabs, 1e-30f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ra = fmaxf(ra, __shfl_xor_sync(0xffffffffu, ra, o));
+      rr = fmaxf(rr, __shfl_xor_sync(0xffffffffu, rr, o));
+    }
+    if (lane == 0 && p.stats) {
+      atomicMax(&p.stats->max_abs_bits, f2u(ra));
+      atomicMax(&p.stats->max_rel_bits, f2u(rr));
+      atomicAdd(&p.stats->rows_checked, 32ull);
+      if (q == 0) atomicAdd(&p.stats->tiles, 1ull);
+    }
+  }
+  if (flag_mask == 0u) return;
+
+  // ---- rare slow path (warp-uniform): locate, recompute, verify ----
+  int j = -1;
+  bool use_argmax = false;
+  if (flagged) {
+    if (isfinite(d1) && isfinite(d2) && d1 != 0.0f) {
+      const float jf = d2 / d1;
+      const float jr = rintf(jf);
+      if (fabsf(jf) < 0.5f) j = -2;  // d2 ~ 0: the expected checksum itself was hit, data are intact
+      else if (jr >= 1.0f && jr <= static_cast<float>(BN) && fabsf(jf - jr) <= 0.3f) j = static_cast<int>(jr) - 1;
+      else j = -1;
+    } else {
+      use_argmax = true;  // Inf/NaN in the row: the culprit is the non-finite / largest element
+    }
+  }
+  if (__ballot_sync(0xffffffffu, use_argmax) != 0u) {
+    float best = -1.0f;
+    int bj = 0;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      ptx::tmem_ld_x32(taddr + c * 32, v);
+      ptx::tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float a = fabsf(u2f(v[i]));
+        if (!(a <= best)) {  // NaN wins
+          best = (a == a) ? a : CUDART_INF_F;
+          bj = c * 32 + i;
+        }
+      }
+    }
+    if (use_argmax) j = bj;
+  }
+  float x1 = 0.0f, x2 = 0.0f, xabs = 0.0f;  // row checksums without column j
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t v[32];
+    ptx::tmem_ld_x32(taddr + c * 32, v);
+    ptx::tmem_wait_ld();
+    const float wbase = static_cast<float>(c * 32 + 1);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float f = (c * 32 + i == j) ? 0.0f : u2f(v[i]);
+      x1 += f;
+      x2 = fmaf(f, wbase + static_cast<float>(i), x2);
+      xabs += fabsf(f);
+    }
+  }
+  if (!flagged) return;
+  int status;
+  float vc = 0.0f;
+  if (j == -2) {
+    status = 4;
+  } else if (j < 0) {
+    status = 3;
+  } else {
+    vc = r1 - x1;
+    const float wj = static_cast<float>(j + 1);
+    const float e2 = (r2 - x2) - wj * vc;  // the second checksum must agree with a single error at column j
+    const float tol = static_cast<float>(BN) * (p.tau_abs + p.tau_rel * (xabs + fabsf(vc)));
+    status = (fabsf(e2) <= tol) ? 1 : 3;
+  }
+  if (status == 1 && p.detect_only) status = 2;
+  if (status == 1) {
+    fix_col = j;
+    fix_val = vc;
+  }
+  if (p.stats) {
+    atomicAdd(&p.stats->detected, 1ull);
+    if (status == 1) atomicAdd(&p.stats->corrected, 1ull);
+    if (status == 3) atomicAdd(&p.stats->uncorrectable, 1ull);
+    if (status == 4) atomicAdd(&p.stats->checksum_faults, 1ull);
+    const int slot = atomicAdd(&p.stats->n_events, 1);
+    if (slot < kMaxEvents) {
+      DeviceEvent ev;
+      ev.row = m;
+      ev.col = j >= 0 ? n0 + j : -1;
+      ev.residual = d1;
+      ev.corrected_value = vc;
+      ev.status = status;
+      p.stats->events[slot] = ev;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// The kernel.
+// ------------------------------------------------------------------------------------------------------------
+template <int BN, bool FT, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmChk, const KernelParams p) {
-  using Cfg = TileCfg<BN, FT>;
+  using Cfg = TileCfg<BN, FT, CG>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kAccStages = Cfg::kAccStages;
 
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B-swizzle atoms need 1024B alignment
+  // 128B-swizzle atoms need 1024B alignment.  (Both CTAs of a pair see the same dynamic-smem base offset, which
+  // cta_group::2 requires: the pair's MMA applies one descriptor to both CTAs' shared memory.)
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -134,7 +388,11 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+  const int unit = blockIdx.x / CG;        // persistent work unit = CTA (CG=1) or CTA pair (CG=2)
+  const int num_units = gridDim.x / CG;
+  const int num_tiles = p.tiles_m * (p.tiles_n + p.tiles_c);
   const int num_kb = (p.K + kBK - 1) / kBK;
 
   if (warp == 0 && lane == 0) {
@@ -144,88 +402,104 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
-      ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), 1);
+      ptx::mbar_init(full_bar(s), CG);   // leader's own arrive.expect_tx (+ the peer's remote arrive)
+      ptx::mbar_init(empty_bar(s), 1);   // one tcgen05.commit (multicast to both CTAs when CG = 2)
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
-      ptx::mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+      ptx::mbar_init(tempty_bar(a), 4 * CG);  // one arrive per epilogue warp of every CTA in the group
     }
     ptx::fence_mbar_init();
   }
+  if (CG == 2) ptx::cluster_sync_all();  // peer barriers must be initialised before any remote arrive / 2-CTA alloc
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    ptx::tmem_relinquish();
+    if (CG == 2) {
+      ptx::tmem_alloc_cg2(tmem_slot, Cfg::kTmemCols);
+      ptx::tmem_relinquish_cg2();
+    } else {
+      ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync_all();
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0 && lane == 0) {
-    // ===================================================================== TMA producer
+    // ===================================================================== TMA producer (every CTA)
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      int m_blk, n_blk;
-      decode_tile(p, t, m_blk, n_blk);
-      const int m0 = m_blk * kBM, n0 = n_blk * BN;
+    for (int t = unit; t < num_tiles; t += num_units) {
+      const TileCoord tc = decode_tile(p, t);
+      const int m0 = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;        // this CTA's 128 rows of A
+      const int nb0 = tc.n_blk * BN + static_cast<int>(cta_rank) * Cfg::kBNLocal;  // this CTA's share of B rows
+      const CUtensorMap *tmb = (FT && tc.is_chk) ? &tmChk : &tmB;
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-        ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
         const uint32_t sA = smem_base + stage * Cfg::kStageBytes;
         const uint32_t sB = sA + Cfg::kABytes;
         const int k0 = kb * kBK;
+        if (CG == 2) {
+          const uint32_t lbar = ptx::mapa(full_bar(stage), 0);  // the leader's barrier collects both CTAs' bytes
+          if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+          else ptx::mbar_arrive_cluster(lbar);
 #pragma unroll
-        for (int i = 0; i < kBM / kAtomMN; ++i)
-          ptx::tma_load_2d(sA + i * (kBK * 128), &tmA, full_bar(stage), m0 + i * kAtomMN, k0);
+          for (int i = 0; i < kBM / kAtomMN; ++i)
+            ptx::tma_load_2d_cg2(sA + i * (kBK * 128), &tmA, lbar, m0 + i * kAtomMN, k0);
 #pragma unroll
-        for (int i = 0; i < BN / kAtomMN; ++i)
-          ptx::tma_load_2d(sB + i * (kBK * 128), &tmB, full_bar(stage), n0 + i * kAtomMN, k0);
-        if (FT) ptx::tma_load_2d(sB + Cfg::kBBytes, &tmChk, full_bar(stage), n_blk * kAtomMN, k0);
+          for (int i = 0; i < Cfg::kBNLocal / kAtomMN; ++i)
+            ptx::tma_load_2d_cg2(sB + i * (kBK * 128), tmb, lbar, nb0 + i * kAtomMN, k0);
+        } else {
+          ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+#pragma unroll
+          for (int i = 0; i < kBM / kAtomMN; ++i)
+            ptx::tma_load_2d(sA + i * (kBK * 128), &tmA, full_bar(stage), m0 + i * kAtomMN, k0);
+#pragma unroll
+          for (int i = 0; i < Cfg::kBNLocal / kAtomMN; ++i)
+            ptx::tma_load_2d(sB + i * (kBK * 128), tmb, full_bar(stage), nb0 + i * kAtomMN, k0);
+        }
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1u;
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================================================================== MMA issuer
-    const uint32_t idesc_main = ptx::make_idesc_tf32(kBM, BN, 1, 1);
-    const uint32_t idesc_chk = ptx::make_idesc_tf32(kBM, kChkCols, 1, 1);
+  } else if (warp == 1 && lane == 0 && is_leader) {
+    // ===================================================================== MMA issuer (leader CTA only)
+    const uint32_t idesc = ptx::make_idesc_tf32(kBM * CG, BN, 1, 1);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = unit; t < num_tiles; t += num_units) {
       ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       ptx::tc_fence_after();
-      const uint32_t d_main = tmem_base + acc * Cfg::kAccStride;
-      const uint32_t d_chk = d_main + BN;
+      const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait(full_bar(stage), phase);
         ptx::tc_fence_after();
         const uint32_t sA = smem_base + stage * Cfg::kStageBytes;
         const uint32_t sB = sA + Cfg::kABytes;
-        const uint32_t sC = sB + Cfg::kBBytes;
 #pragma unroll
         for (int j = 0; j < kBK / 8; ++j) {
           const uint64_t da = ptx::make_smem_desc(sA + j * p.kstep_bytes, p.lbo_bytes, p.sbo_bytes, p.layout_type);
           const uint64_t db = ptx::make_smem_desc(sB + j * p.kstep_bytes, p.lbo_bytes, p.sbo_bytes, p.layout_type);
           const uint32_t accum = (kb | j) != 0 ? 1u : 0u;
-          ptx::mma_tf32(d_main, da, db, idesc_main, accum);
-          if (FT) {
-            const uint64_t dc = ptx::make_smem_desc(sC + j * p.kstep_bytes, p.lbo_bytes, p.sbo_bytes, p.layout_type);
-            ptx::mma_tf32(d_chk, da, dc, idesc_chk, accum);
-          }
+          if (CG == 2) ptx::mma_tf32_cg2(d_tmem, da, db, idesc, accum);
+          else ptx::mma_tf32(d_tmem, da, db, idesc, accum);
         }
-        ptx::mma_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
+        // frees the smem slot (in both CTAs) once these MMAs have read it
+        if (CG == 2) ptx::mma_commit_cg2(empty_bar(stage), 0x3);
+        else ptx::mma_commit(empty_bar(stage));
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      ptx::mma_commit(tfull_bar(acc));  // accumulator (data + checksum columns) complete
+      if (CG == 2) ptx::mma_commit_cg2(tfull_bar(acc), 0x3);  // accumulator complete (both CTAs' epilogues)
+      else ptx::mma_commit(tfull_bar(acc));
       if (kAccStages == 2) {
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
@@ -234,223 +508,40 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp >= 4) {
-    // ===================================================================== epilogue (4 warps, lane = row)
+    // ===================================================================== epilogue (4 warps per CTA, lane = row)
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;
+    const uint32_t tempty_leader = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      int m_blk, n_blk;
-      decode_tile(p, t, m_blk, n_blk);
-      const int m0 = m_blk * kBM, n0 = n_blk * BN;
-      const int m = m0 + row;
+    for (int t = unit; t < num_tiles; t += num_units) {
+      const TileCoord tc = decode_tile(p, t);
+      const int m0_cta = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;
+      const int n0 = tc.n_blk * BN;
+      const int m = m0_cta + row;
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::kAccStride;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
-      int fix_col = -1;       // tile-local column whose value is replaced in the store pass
-      float fix_val = 0.0f;
-
-      if (FT) {
-        // ---- fault injection into the TMEM accumulator (reference: ft_sgemm_huge.cuh:324-327) ----
-        if (p.inject_mode == 1) {
-          if ((p.selftest_row >> 5) == q && p.selftest_col < BN) {
-            uint32_t x = ptx::tmem_ld_x1(taddr + p.selftest_col);
-            ptx::tmem_wait_ld();
-            if (lane == (p.selftest_row & 31)) x = f2u(u2f(x) + p.selftest_value);
-            ptx::tmem_st_x1(taddr + p.selftest_col, x);
-            ptx::tmem_wait_st();
-          }
-        } else if (p.inject_mode == 2) {
-          for (int f = 0; f < p.n_faults; ++f) {
-            const int tr = p.faults[f].row - m0, tc = p.faults[f].col - n0;
-            if (tr >= 0 && tr < kBM && tc >= 0 && tc < BN && (tr >> 5) == q) {  // warp-uniform
-              uint32_t x = ptx::tmem_ld_x1(taddr + tc);
-              ptx::tmem_wait_ld();
-              if (lane == (tr & 31))
-                x = p.faults[f].mode == 0 ? f2u(u2f(x) + p.faults[f].add_value) : (x ^ p.faults[f].xor_mask);
-              ptx::tmem_st_x1(taddr + tc, x);
-              ptx::tmem_wait_st();
-            }
-          }
-        }
-        // ---- pass 1: actual row checksums (thread-local: lane == row) ----
-        float s1 = 0.0f, s2 = 0.0f, sabs = 0.0f;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t v[32];
-          ptx::tmem_ld_x32(taddr + c * 32, v);
-          ptx::tmem_wait_ld();
-          const float wbase = static_cast<float>(c * 32 + 1);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float f = u2f(v[i]);
-            s1 += f;
-            s2 = fmaf(f, wbase + static_cast<float>(i), s2);
-            sabs += fabsf(f);
-          }
-        }
-        uint32_t e[8];
-        ptx::tmem_ld_x8(taddr + BN, e);
-        ptx::tmem_wait_ld();
-        const float r1 = u2f(e[0]) + (u2f(e[1]) + u2f(e[2]));
-        const float r2 = u2f(e[3]) + (u2f(e[4]) + u2f(e[5]));
-        const float d1 = r1 - s1, d2 = r2 - s2;
-        const float thr = p.tau_abs + p.tau_rel * sabs;
-        const bool flagged = !(fabsf(d1) <= thr);  // also true for NaN
-        const unsigned flag_mask = __ballot_sync(0xffffffffu, flagged);
-
-        // fault-free residual statistics (threshold calibration)
-        {
-          float ra = flagged ? 0.0f : fabsf(d1);
-          float rr = flagged ? 0.0f : fabsf(d1) / fmaxf(sabs, 1e-30f);
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            ra = fmaxf(ra, __shfl_xor_sync(0xffffffffu, ra, o));
-            rr = fmaxf(rr, __shfl_xor_sync(0xffffffffu, rr, o));
-          }
-          if (lane == 0 && p.stats) {
-            atomicMax(&p.stats->max_abs_bits, f2u(ra));
-            atomicMax(&p.stats->max_rel_bits, f2u(rr));
-            atomicAdd(&p.stats->rows_checked, 32ull);
-            if (q == 0) atomicAdd(&p.stats->tiles, 1ull);
-          }
-        }
-
-        if (flag_mask != 0u) {  // rare slow path, warp-uniform
-          // candidate column from the weighted checksum; Inf/NaN rows fall back to the largest-magnitude element
-          int j = -1;
-          bool use_argmax = false;
-          if (flagged) {
-            if (isfinite(d1) && isfinite(d2) && d1 != 0.0f) {
-              const float jf = d2 / d1;
-              const float jr = rintf(jf);
-              if (fabsf(jf) < 0.5f) j = -2;  // d2 ~ 0: the checksum column itself was hit, data are intact
-              else if (jr >= 1.0f && jr <= static_cast<float>(BN) && fabsf(jf - jr) <= 0.3f) j = static_cast<int>(jr) - 1;
-              else j = -1;
-            } else {
-              use_argmax = true;
-            }
-          }
-          const unsigned argmax_mask = __ballot_sync(0xffffffffu, use_argmax);
-          if (argmax_mask != 0u) {
-            float best = -1.0f;
-            int bj = 0;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-              uint32_t v[32];
-              ptx::tmem_ld_x32(taddr + c * 32, v);
-              ptx::tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float a = fabsf(u2f(v[i]));
-                const bool better = !(a <= best);  // NaN wins
-                if (better) {
-                  best = (a == a) ? a : CUDART_INF_F;
-                  bj = c * 32 + i;
-                }
-              }
-            }
-            if (use_argmax) j = bj;
-          }
-          // recompute the row checksums without column j
-          float x1 = 0.0f, x2 = 0.0f;
-#pragma unroll 1
-          for (int c = 0; c < BN / 32; ++c) {
-            uint32_t v[32];
-            ptx::tmem_ld_x32(taddr + c * 32, v);
-            ptx::tmem_wait_ld();
-            const float wbase = static_cast<float>(c * 32 + 1);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float f = (c * 32 + i == j) ? 0.0f : u2f(v[i]);
-              x1 += f;
-              x2 = fmaf(f, wbase + static_cast<float>(i), x2);
-            }
-          }
-          if (flagged) {
-            int status;
-            float vc = 0.0f;
-            if (j == -2) {
-              status = 4;
-            } else if (j < 0) {
-              status = 3;
-            } else {
-              vc = r1 - x1;
-              const float wj = static_cast<float>(j + 1);
-              const float e2 = (r2 - x2) - wj * vc;  // second checksum must agree with a single error at j
-              const float tol = static_cast<float>(BN) * (p.tau_abs + p.tau_rel * (sabs == sabs && isfinite(sabs) ? sabs : fabsf(x1) + fabsf(vc)));
-              status = (fabsf(e2) <= tol) ? 1 : 3;
-            }
-            if (status == 1 && p.detect_only) status = 2;
-            if (status == 1) {
-              fix_col = j;
-              fix_val = vc;
-            }
-            if (p.stats) {
-              atomicAdd(&p.stats->detected, 1ull);
-              if (status == 1) atomicAdd(&p.stats->corrected, 1ull);
-              if (status == 3) atomicAdd(&p.stats->uncorrectable, 1ull);
-              if (status == 4) atomicAdd(&p.stats->checksum_faults, 1ull);
-              const int slot = atomicAdd(&p.stats->n_events, 1);
-              if (slot < kMaxEvents) {
-                DeviceEvent ev;
-                ev.row = m;
-                ev.col = j >= 0 ? n0 + j : -1;
-                ev.residual = d1;
-                ev.corrected_value = vc;
-                ev.status = status;
-                p.stats->events[slot] = ev;
-              }
-            }
-          }
-        }
+      if (FT && tc.is_chk) {
+        // checksum tile-column: publish R = A * [e, w]^T for these 128 rows, then raise the slab flag
+        store_tile<BN>(taddr, p.chk_out + m, m < p.M, n0, p.n_chk_cols, p.M, 1.0f, 0.0f, -1, 0.0f);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(p.chk_flags + (m0_cta >> 5) + q, 1);
+      } else {
+        int fix_col = -1;
+        float fix_val = 0.0f;
+        if (FT) abft_check<BN>(p, taddr, q, lane, m, m0_cta, n0, tc.n_blk, fix_col, fix_val);
+        store_tile<BN>(taddr, p.C + m, m < p.M, n0, p.N, p.ldc, p.alpha, p.beta, fix_col, fix_val);
       }
-
-      // ---- store pass: C = alpha*acc + beta*C, column-major (lane = consecutive m -> 128B coalesced) ----
-      const bool row_ok = m < p.M;
-      float *crow = p.C + m;
-      const bool full_n = (n0 + BN <= p.N);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_x32(taddr + c * 32, v);
-        ptx::tmem_wait_ld();
-        if (FT && (fix_col >> 5) == c && fix_col >= 0) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i == (fix_col & 31)) v[i] = f2u(fix_val);
-        }
-        const int nb = n0 + c * 32;
-        if (row_ok) {
-          if (full_n) {
-            if (p.beta == 0.0f) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) crow[static_cast<size_t>(nb + i) * p.ldc] = p.alpha * u2f(v[i]);
-            } else {
-              float old[32];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) old[i] = crow[static_cast<size_t>(nb + i) * p.ldc];
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                crow[static_cast<size_t>(nb + i) * p.ldc] = p.alpha * u2f(v[i]) + p.beta * old[i];
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (nb + i < p.N) {
-                float *dst = crow + static_cast<size_t>(nb + i) * p.ldc;
-                const float o = (p.beta == 0.0f) ? 0.0f : p.beta * (*dst);
-                *dst = p.alpha * u2f(v[i]) + o;
-              }
-            }
-          }
-        }
-      }
-      // release this accumulator stage back to the MMA warp
+      // release this accumulator stage back to the MMA warp (of the leader CTA)
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CG == 2) ptx::mbar_arrive_cluster(tempty_leader + 8u * acc);
+        else ptx::mbar_arrive(tempty_bar(acc));
+      }
       if (kAccStages == 2) {
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
@@ -460,11 +551,14 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   }
 
+  __syncwarp();  // reconverge the single-lane roles before the .aligned barriers below
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync_all();  // no CTA may exit while its peer can still signal its barriers
+  else __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CG == 2) ptx::tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -472,8 +566,9 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // Encode pre-pass (reference: ft_sgemm_huge.cuh:150-168 ENCODE of B, done there per CTA and per k-step with
 // shuffles; here once per GEMM and per BN-wide column block, because a CUDA-core re-read of every shared-memory
 // stage does not fit next to a tensor-core main loop -- DESIGN.md section 3).
-//   chk[k][t*32 + 0..2] = 3-way TF32 split of  e = sum_{n in block t} tf32(B[n,k])
-//   chk[k][t*32 + 3..5] = 3-way TF32 split of  w = sum_{n in block t} (n - n0 + 1) * tf32(B[n,k])
+//   chk[k][t*8 + 0..2] = 3-way TF32 split of  e = sum_{n in block t} tf32(B[n,k])
+//   chk[k][t*8 + 3..5] = 3-way TF32 split of  w = sum_{n in block t} (n - n0 + 1) * tf32(B[n,k])
+//   chk[k][t*8 + 6..7] = 0
 // Sums are accumulated in FP64, so the three TF32 terms carry the checksum to ~2^-33 relative.
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float tf32_bits(float x, int rounding) {
@@ -525,13 +620,13 @@ encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, floa
       w[u] += __shfl_xor_sync(0xffffffffu, w[u], o);
     }
     const int k = kbase + u;
-    if (k < K) {  // every lane holds the totals; lane i writes column i of the 32-float block (6 used, rest zero)
+    if (k < K && lane < kChkPerTile) {  // every lane holds the totals; lane i writes column i of the 8-float block
       float eh, em, el, wh, wm, wl;
       split3_tf32(e[u], eh, em, el);
       split3_tf32(w[u], wh, wm, wl);
       const float val = lane == 0 ? eh : lane == 1 ? em : lane == 2 ? el : lane == 3 ? wh : lane == 4 ? wm
                         : lane == 5 ? wl : 0.0f;
-      chk[static_cast<size_t>(k) * chk_ld + t * kAtomMN + lane] = val;
+      chk[static_cast<size_t>(k) * chk_ld + t * kChkPerTile + lane] = val;
     }
   }
 }

@@ -46,11 +46,11 @@ def test_kernel_table_matches_reference_ids(ft):
         assert tab[ft.SGEMM_IDS[nm]]["tile"] == tab[ft.ABFT_IDS[nm]]["tile"]  # FT and non-FT share the tiling
     # config 2 of BASELINE.json: the huge tile is literally 128 x 128 with UMMA K = 8 steps
     assert tab[16]["tile"][:2] == (128, 128) and tab[14]["tile"][:2] == (128, 32)
-    # UMMA legality of every tcgen05 tile: M = 128, N % 16 == 0, 16 <= N <= 256
+    # UMMA legality of every tcgen05 tile: M = 128 (cta_group::1) or 256 (cta_group::2), N % 16 == 0, 16 <= N <= 256
     for k in tab.values():
         if k["engine"] == 1:
             m, n, kk = k["tile"]
-            assert m == 128 and n % 16 == 0 and 16 <= n <= 256 and kk % 8 == 0
+            assert m in (128, 256) and n % 16 == 0 and 16 <= n <= 256 and kk % 8 == 0
 
 
 def test_opts_struct_layout(ft):
