@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- the driver-facing benchmark of the fused ABFT-SGEMM hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size n] [--id KERNEL_ID] [--sweep]
+
+One "step" = one pass of the hot path over one batch of synthetic input: one fused fault-tolerant SGEMM
+C = alpha*A*B^T + beta*C (encode pre-pass + tcgen05 kernel with checksum tile-columns, per-tile detect/correct) at
+BASELINE.json configs[1]: M=N=K=4096, alpha=1, beta=-1.5 (the reference's timing phase, sgemm.cu:22,234), reference
+input distribution (utils/utils.cu:23-31).  Inputs are resident in HBM for `value`; `e2e` runs the same step through
+the host-buffer C-ABI call (ftsgemm_run_host) with H2D/D2H inside the timed region.  At N>1 every rank (one process per
+GPU, torchrun) owns one C block of a 2-D block-sharded product (A row-panel x B row-panel -> no operand traffic) and the
+ranks all-reduce their checksum/fault counters over NCCL every step: weak scaling, value = aggregate GFLOPS over the
+max-over-ranks time.
+
+--impl reference times the reference's own CPU SGEMM (cpu_gemm, utils/utils.cu:79-89, compiled unmodified into
+oracle/_ref/libref_utils.so; falls back to the OpenMP oracle port) on the host cores; rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "fused ABFT SGEMM GFLOPS (2*M*N*K/t) and ABFT overhead % vs cuBLAS-TF32, M=N=K=4096"
+README_ABFT_HUGE_4096 = 4005.0  # BASELINE.md section 1 (README.md:53), hardware unspecified
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"bf16_tflops": float(d["bf16_tflops"]), "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                "hbm_gbs": float(d["hbm_gbs"]), "src": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            if t0 <= ts <= t1 + 0.1:
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than the sampling period: use the nearest samples
+            for ts, line in self.lines[-3:]:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                except Exception:
+                    pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def _cpu_port_baseline(n, seconds_target=12.0):
+    """OpenMP oracle (port of cpu_gemm's arithmetic) on all host cores, bounded row sample of the n^3 workload."""
+    import numpy as np
+    from oracle import oracle as O
+    A, B, _ = O.make_inputs(min(n, 1024))
+    if n > 1024:  # tile the 1024-sized reference-distribution block; content does not affect CPU time
+        rng = np.random.default_rng(0)
+        A = (rng.integers(-9, 10, n * n) * 0.1).astype(np.float32)
+        B = (rng.integers(-9, 10, n * n) * 0.1).astype(np.float32)
+    nn = n if n > 1024 else min(n, 1024)
+    rows = np.arange(4, dtype=np.int32)
+    t0 = time.time()
+    O.sgemm_nt_rows(nn, nn, nn, 1.0, A, B, 0.0, None, rows)
+    t_probe = max(time.time() - t0, 1e-4)
+    nrows = int(max(4, min(nn, 4 * seconds_target / t_probe)))
+    rows = np.linspace(0, nn - 1, nrows).astype(np.int32)
+    t0 = time.time()
+    O.sgemm_nt_rows(nn, nn, nn, 1.0, A, B, 0.0, None, rows)
+    dt = time.time() - t0
+    gf = 2.0 * nrows * nn * nn / dt / 1e9
+    return {"value": round(gf, 3), "unit": "GFLOPS", "cores": O.num_threads(), "kind": "port",
+            "sample": f"{nrows} of {nn} rows x {nn} cols x K={nn} (sequential-k fp32, OpenMP over columns), {dt:.1f} s"}
+
+
+def run_reference_arm(args):
+    """The reference's own CPU SGEMM on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import oracle as O
+    n_ref = 1024  # bounded sample of the 4096^3 workload: cpu_gemm is square, single-threaded, ~4.5 s at n=1024
+    r = O.ref_utils()
+    A, B, C = O.make_inputs(n_ref)
+    X = np.ascontiguousarray(B.reshape(n_ref, n_ref).T).reshape(-1)
+    steps, warm = max(1, min(args.steps, 6)), min(args.warmup, 1)
+    times = []
+    if r is not None:
+        kind, cores = "reference", 1
+        sample = f"cpu_gemm (utils/utils.cu:79-89, unmodified) n={n_ref} per step = 1/64 of the 4096^3 flops"
+        for i in range(warm + steps):
+            Z = np.zeros(n_ref * n_ref, np.float32)
+            t0 = time.time()
+            r.ref_cpu_gemm(1.0, -1.5, O._p(X), O._p(A), n_ref, O._p(Z))
+            if i >= warm:
+                times.append(time.time() - t0)
+    else:
+        kind, cores = "port", O.num_threads()
+        sample = f"oracle_sgemm_nt (OpenMP port of cpu_gemm) n={n_ref} per step"
+        for i in range(warm + steps):
+            Z = np.zeros(n_ref * n_ref, np.float32)
+            t0 = time.time()
+            O.sgemm_nt(n_ref, n_ref, n_ref, 1.0, A, B, -1.5, Z)
+            if i >= warm:
+                times.append(time.time() - t0)
+    dt = sum(times) / len(times)
+    gf = 2.0 * n_ref ** 3 / dt / 1e9
+    out = {"impl": "reference", "metric": METRIC, "value": round(gf, 4), "unit": "GFLOPS", "n_gpus": args.gpus,
+           "steps": len(times), "warmup": warm, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"reference CPU SGEMM, bounded sample of M=N=K=4096: {sample}", "alpha": 1.0, "beta": -1.5},
+           "cpu_baseline": {"value": round(gf, 4), "unit": "GFLOPS", "cores": cores, "kind": kind, "sample": sample},
+           "e2e": {"value": round(gf, 4), "unit": "GFLOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--size", type=int, default=4096)
+    ap.add_argument("--id", type=int, default=31, help="fused ABFT kernel id (31 = 256x256 CTA-pair tile, 16 = literal huge 128x128)")
+    ap.add_argument("--sweep", action="store_true", help="also print the README-style table 1024..16384 to stderr")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.size
+    M = N = K = n
+    alpha, beta = 1.0, -1.5
+    W = max(args.warmup, 3)
+    steps = args.steps
+    # 2-D block sharding of a (P*n) x (Q*n) product over the ranks: rank (p,q) owns A row-panel p, B row-panel q, C block
+    P = 1
+    while P * P * 2 <= world and world % (P * 2) == 0:
+        P *= 2
+    Q = world // P
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+
+    def ref_dist(count):
+        return (torch.randint(0, 10, (count,), generator=g, device="cuda").float() * 0.1) * \
+               (torch.randint(0, 2, (count,), generator=g, device="cuda").float() * 2 - 1)
+
+    dA, dB = ref_dist(M * K), ref_dist(N * K)
+    dC = torch.zeros(M * N, device="cuda")
+    ft = pkg.FtSgemm()
+    stream = torch.cuda.current_stream().cuda_stream
+    opts = pkg.make_opts(stream=stream)
+    opts_reuse = pkg.make_opts(stream=stream, reuse_b_checksums=True)
+    stat_vec = torch.zeros(4, device="cuda", dtype=torch.float64)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, nsteps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        for _ in range(nsteps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+        return ms
+
+    def step_ft():
+        ft.run(args.id, M, N, K, dA, dB, dC, alpha, beta, opts)
+        if dist is not None:  # the one exchange step of the sharded path: agree on the fault verdict
+            dist.all_reduce(stat_vec)
+
+    def reset_c():
+        dC.zero_()
+
+    # ---- warm-up + the timed region of the headline number
+    for _ in range(W):
+        step_ft()
+    reset_c()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    t_wall0 = time.time()
+    ms_total = timed(step_ft, steps)
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    st = ft.stats()
+    ms_step = ms_total / steps
+    flops = 2.0 * M * N * K
+    value = world * flops / (ms_step * 1e-3) / 1e9
+
+    # ---- dominant kernel alone (checksum panel reused -> no encode launch), same event method
+    reset_c()
+    k_ms = timed(lambda: ft.run(args.id, M, N, K, dA, dB, dC, alpha, beta, opts_reuse), steps) / steps
+    # ---- comparators on the same buffers: cuBLAS-TF32 (the bar), own non-FT kernel, non-fused baseline, cuBLAS FP32
+    comp = {}
+    plain_id = {31: 21, 32: 22}.get(args.id, args.id - 10)
+    for name, kid, reps in (("cublas_tf32", 7, steps), ("plain", plain_id, steps), ("cublas_fp32", 0, max(3, steps // 4)),
+                            ("abft_baseline_tf32", 30, 2), ("abft_baseline", 10, 2)):
+        reset_c()
+        o = pkg.make_opts(stream=stream, baseline_host_sync=True)
+        for _ in range(2):
+            ft.run(kid, M, N, K, dA, dB, dC, alpha, beta, o)
+        ms = timed(lambda: ft.run(kid, M, N, K, dA, dB, dC, alpha, beta, o), reps) / reps
+        comp[name] = flops / (ms * 1e-3) / 1e9
+    ft.stats()
+
+    # ---- e2e: the host-buffer C-ABI call, pinned host memory, H2D(A,B,C) + kernel + D2H(C) inside the timed region
+    hA = torch.empty(M * K, dtype=torch.float32).pin_memory(); hA.copy_(dA)
+    hB = torch.empty(N * K, dtype=torch.float32).pin_memory(); hB.copy_(dB)
+    hC = torch.zeros(M * N, dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, min(steps, 8))
+
+    def step_e2e():
+        ft.run_host(args.id, M, N, K, hA.data_ptr(), hB.data_ptr(), hC.data_ptr(), alpha, beta, opts)
+        if dist is not None:
+            dist.all_reduce(stat_vec)
+
+    step_e2e()
+    hC.zero_()
+    e2e_ms = timed(step_e2e, e2e_steps) / e2e_steps
+    e2e_val = world * flops / (e2e_ms * 1e-3) / 1e9
+    result_ok = bool(torch.isfinite(hC).all())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peaks = _peaks()
+    tf32_peak = peaks["bf16_tflops"] / 2.0  # kind::tf32 issues at half the kind::f16 rate on tcgen05
+    achieved = flops / (k_ms * 1e-3) / 1e12
+    info = [k for k in pkg.kernel_table() if k["id"] == args.id][0]
+    out = {
+        "metric": METRIC, "value": round(value, 1), "unit": "GFLOPS", "n_gpus": world, "steps": steps, "warmup": W,
+        "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": round(value / world / README_ABFT_HUGE_4096, 2) if n == 4096 else None,
+        "dtype": "tf32 multiply, f32 accumulate", "data": "synthetic",
+        "config": {"workload": f"fused ABFT SGEMM id {args.id} ({info['name']}, tile {info['tile'][0]}x{info['tile'][1]}), "
+                               f"M=N=K={n} per GPU, alpha=1, beta=-1.5 (sgemm.cu:22,234), reference input distribution",
+                   "sharding": f"{P}x{Q} C-block grid, A/B row-panels resident per GPU, NCCL all-reduce of fault counters per step" if world > 1 else "single GPU",
+                   "l2": f"inputs {3 * 4 * n * n / 2**20:.0f} MiB per step vs 126 MB L2: larger than L2, no flush needed" if n >= 4096 else "L2-resident working set (small size)",
+                   "baseline_note": "vs_baseline = per-GPU value / 4005 GFLOPS (README.md:53 abft_kernel_huge @4096, GPU unspecified)"},
+        "abft": {"overhead_pct_vs_cublas_tf32": round(100.0 * (comp["cublas_tf32"] / (value / world) - 1.0), 2),
+                 "overhead_pct_vs_own_plain_kernel": round(100.0 * (comp["plain"] / (value / world) - 1.0), 2),
+                 "cublas_tf32_gflops": round(comp["cublas_tf32"], 1), "cublas_fp32_gflops": round(comp["cublas_fp32"], 1),
+                 "plain_kernel_gflops": round(comp["plain"], 1), "abft_baseline_gflops": round(comp["abft_baseline"], 1),
+                 "abft_baseline_tf32_gflops": round(comp["abft_baseline_tf32"], 1),
+                 "tiles_checked": st["tiles"], "rows_checked": st["rows_checked"], "detected": st["detected"],
+                 "max_abs_residual": st["max_abs_residual"], "max_rel_residual": st["max_rel_residual"]},
+        "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
+                     "frac": round(achieved / tf32_peak, 4), "traffic": None,
+                     "note": f"kernel ftsgemm_tc_kernel alone (encode reused), 2*M*N*K per launch / CUDA-event mean; peak = bf16 burst {peaks['bf16_tflops']} / 2, {peaks['src']}"},
+        "e2e": {"value": round(e2e_val, 1), "unit": "GFLOPS", "h2d_bytes_per_step": 3 * 4 * n * n, "d2h_bytes_per_step": 4 * n * n,
+                "steps": e2e_steps, "finite": result_ok},
+        "gpu_launches": 2 * steps,  # encode_b_kernel + ftsgemm_tc_kernel per step
+        "clocks": clocks,
+    }
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            out["roofline"]["traffic"] = json.loads(tp.read_text()).get(str(args.id))
+        except Exception:
+            pass
+    if not args.no_cpu and world >= 1:
+        out["cpu_baseline"] = _cpu_port_baseline(n if n <= 4096 else 4096)
+    if args.sweep:
+        sizes = [s for s in range(1024, 16385, 1024) if 3 * 4 * s * s < 60e9]
+        ids = [0, 7, 2, 6, 5, 21, 12, 16, 15, 31]
+        sys.stderr.write("Matrix Size         |" + "".join(f"{s:8d}|" for s in sizes) + "\n")
+        names = {k["id"]: k["name"] for k in pkg.kernel_table()}
+        big = max(sizes)
+        bA, bB, bC = ref_dist(big * big), ref_dist(big * big), torch.zeros(big * big, device="cuda")
+        for kid in ids:
+            row = f"{names[kid]:<20s}|"
+            for s in sizes:
+                bC.zero_()
+                for _ in range(2):
+                    ft.run(kid, s, s, s, bA, bB, bC, alpha, beta, opts)
+                reps = 10 if s <= 4096 else 3
+                ms = timed(lambda: ft.run(kid, s, s, s, bA, bB, bC, alpha, beta, opts), reps) / reps
+                row += f"{2.0 * s ** 3 / ms / 1e6:8.0f}|"
+            sys.stderr.write(row + "\n")
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

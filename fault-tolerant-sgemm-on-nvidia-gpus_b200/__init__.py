@@ -98,9 +98,10 @@ def lib():
     """Load libftsgemm.so (raises if it has not been built: the product path never falls back to the CPU)."""
     global _lib
     if _lib is None:
-        if not LIB_PATH.exists():
-            raise FtsgemmError(-4, f"{LIB_PATH} not built (run __graft_entry__.build())")
-        L = C.CDLL(str(LIB_PATH))
+        path = Path(os.environ.get("FTSGEMM_LIB", str(LIB_PATH)))  # override only for A/B experiments
+        if not path.exists():
+            raise FtsgemmError(-4, f"{path} not built (run __graft_entry__.build())")
+        L = C.CDLL(str(path))
         vp, ip, fp = C.c_void_p, C.c_int, C.c_float
         L.ftsgemm_create.argtypes = [C.POINTER(vp)]
         L.ftsgemm_destroy.argtypes = [vp]

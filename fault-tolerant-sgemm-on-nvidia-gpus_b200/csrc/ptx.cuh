@@ -146,7 +146,8 @@ __device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  // default semantics (.release.cta): a cluster-scope release here costs a full fence per call
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // TMA load whose completion bytes are credited to an mbarrier of the pair's leader CTA (cluster address).
 __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap *tm, uint32_t cluster_bar, int c0, int c1) {
