@@ -140,6 +140,27 @@ int make_tmap_2d(ftsgemm_handle_t h, CUtensorMap *tm, const float *base, uint64_
   return FTSGEMM_OK;
 }
 
+// 3-D view {32, K, rows/32} of a column-major rows x K operand (rows % 32 == 0): element (i, k, a) = base[(a*32+i) + k*ld].
+// One box {32, kBK, atoms} lands in shared memory as [atom][k][32 floats] -- exactly the canonical MN-major layout the
+// UMMA descriptors describe -- with a single TMA instruction.
+int make_tmap_3d(ftsgemm_handle_t h, CUtensorMap *tm, const float *base, uint64_t rows, uint64_t kdim, uint64_t ld_elems,
+                 uint32_t atoms_per_box) {
+  cuuint64_t dims[3] = {kAtomMN, kdim, rows / kAtomMN};
+  cuuint64_t strides[2] = {ld_elems * sizeof(float), kAtomMN * sizeof(float)};
+  cuuint32_t box[3] = {kAtomMN, kBK, atoms_per_box};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw =
+      static_cast<CUtensorMapSwizzle>(dbg("tma_swizzle", static_cast<long long>(CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)));
+  CUresult r = h->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    h->last_cuda_error = static_cast<int>(r);
+    return FTSGEMM_ERR_CUDA;
+  }
+  return FTSGEMM_OK;
+}
+
 template <int BN, bool FT, int CG>
 int launch_tc(ftsgemm_handle_t h, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
               const KernelParams &p, cudaStream_t stream) {
@@ -224,18 +245,32 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
   p.stats = h->d_stats;
 
   CUtensorMap tmA, tmB, tmC;
-  int rc = make_tmap_2d(h, &tmA, dA, M, K, M, kAtomMN, kBK);
+  const bool allow3d = dbg("tma3d", 1) != 0;
+  int rc;
+  if (allow3d && M % kAtomMN == 0) {
+    rc = make_tmap_3d(h, &tmA, dA, M, K, M, kBM / kAtomMN);
+    p.tma3d |= 1;
+  } else {
+    rc = make_tmap_2d(h, &tmA, dA, M, K, M, kAtomMN, kBK);
+  }
   if (rc) return rc;
-  rc = make_tmap_2d(h, &tmB, dB, N, K, N, kAtomMN, kBK);
+  if (allow3d && N % kAtomMN == 0) {
+    rc = make_tmap_3d(h, &tmB, dB, N, K, N, BN / CG / kAtomMN);
+    p.tma3d |= 2;
+  } else {
+    rc = make_tmap_2d(h, &tmB, dB, N, K, N, kAtomMN, kBK);
+  }
   if (rc) return rc;
   tmC = tmB;
   if (ft) {
     // checksum vectors of B: 8 columns per N-tile, appended to B as extra tile-columns of the same GEMM
     p.n_chk_cols = p.tiles_n * kChkPerTile;
     p.tiles_c = (p.n_chk_cols + BN - 1) / BN;
+    const int chk_ld = (p.n_chk_cols + kAtomMN - 1) / kAtomMN * kAtomMN;  // padded so the 3-D TMA view is exact; pad
+                                                                          // columns are never stored (n_chk_cols mask)
     const int n_slabs = p.tiles_m * CG * (kBM / 32);
     const float *chk_before = h->d_chk;
-    rc = ensure_buf(h, &h->d_chk, &h->chk_bytes, static_cast<size_t>(K) * p.n_chk_cols * sizeof(float));
+    rc = ensure_buf(h, &h->d_chk, &h->chk_bytes, static_cast<size_t>(K) * chk_ld * sizeof(float));
     if (rc) return rc;
     if (h->d_chk != chk_before) h->chk_for_b = nullptr;  // reallocated: the cached encode is gone
     const size_t out_floats = static_cast<size_t>(M) * p.n_chk_cols;
@@ -247,12 +282,17 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     const bool reuse = o.reuse_b_checksums && h->chk_for_b == dB && h->chk_n == N && h->chk_k == K && h->chk_bn == BN;
     if (!reuse) {
       dim3 grid(p.tiles_n, (K + kEncWarps * kEncKPerWarp - 1) / (kEncWarps * kEncKPerWarp));
-      encode_b_kernel<<<grid, kEncWarps * 32, 0, stream>>>(dB, N, K, N, BN, h->d_chk, p.n_chk_cols,
+      encode_b_kernel<<<grid, kEncWarps * 32, 0, stream>>>(dB, N, K, N, BN, h->d_chk, chk_ld,
                                                            static_cast<int>(dbg("enc_rounding", 0)));
       FT_CUDA(h, cudaGetLastError());
       h->chk_for_b = dB; h->chk_n = N; h->chk_k = K; h->chk_bn = BN;
     }
-    rc = make_tmap_2d(h, &tmC, h->d_chk, p.n_chk_cols, K, p.n_chk_cols, kAtomMN, kBK);
+    if (allow3d) {
+      rc = make_tmap_3d(h, &tmC, h->d_chk, chk_ld, K, chk_ld, BN / CG / kAtomMN);
+      p.tma3d |= 4;
+    } else {
+      rc = make_tmap_2d(h, &tmC, h->d_chk, chk_ld, K, chk_ld, kAtomMN, kBK);
+    }
     if (rc) return rc;
   }
   h->last_stream = stream;

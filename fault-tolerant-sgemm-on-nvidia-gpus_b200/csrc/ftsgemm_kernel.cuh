@@ -74,6 +74,9 @@ struct KernelParams {
   int tiles_m, tiles_n, group_n;
   // UMMA shared-memory descriptor parameters (runtime so the bring-up probe can sweep them)
   unsigned int lbo_bytes, sbo_bytes, layout_type, kstep_bytes;
+  // bit 0 / 1 / 2: the A / B / checksum tensor map is 3-D {32, K, rows/32} so that ONE TMA instruction fetches a whole
+  // operand stage (rows % 32 == 0); otherwise the map is 2-D {rows, K} and a stage takes one instruction per 32-row atom
+  int tma3d;
   // fault tolerance: checksum tile-columns
   int tiles_c;          // number of BN-wide checksum tile-columns (0 when FT is off)
   int n_chk_cols;       // tiles_n * kChkPerTile
@@ -435,30 +438,39 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const TileCoord tc = decode_tile(p, t);
       const int m0 = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;        // this CTA's 128 rows of A
       const int nb0 = tc.n_blk * BN + static_cast<int>(cta_rank) * Cfg::kBNLocal;  // this CTA's share of B rows
-      const CUtensorMap *tmb = (FT && tc.is_chk) ? &tmChk : &tmB;
+      const bool b_is_chk = FT && tc.is_chk;
+      const CUtensorMap *tmb = b_is_chk ? &tmChk : &tmB;
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sA = smem_base + stage * Cfg::kStageBytes;
         const uint32_t sB = sA + Cfg::kABytes;
         const int k0 = kb * kBK;
+        const uint32_t bar = (CG == 2) ? ptx::mapa(full_bar(stage), 0) : full_bar(stage);  // the leader collects the bytes
         if (CG == 2) {
-          const uint32_t lbar = ptx::mapa(full_bar(stage), 0);  // the leader's barrier collects both CTAs' bytes
           if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-          else ptx::mbar_arrive_cluster(lbar);
-#pragma unroll
-          for (int i = 0; i < kBM / kAtomMN; ++i)
-            ptx::tma_load_2d_cg2(sA + i * (kBK * 128), &tmA, lbar, m0 + i * kAtomMN, k0);
-#pragma unroll
-          for (int i = 0; i < Cfg::kBNLocal / kAtomMN; ++i)
-            ptx::tma_load_2d_cg2(sB + i * (kBK * 128), tmb, lbar, nb0 + i * kAtomMN, k0);
+          else ptx::mbar_arrive_cluster(bar);
         } else {
           ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+        }
+        if (p.tma3d & 1) {
+          if (CG == 2) ptx::tma_load_3d_cg2(sA, &tmA, bar, 0, k0, m0 / kAtomMN);
+          else ptx::tma_load_3d(sA, &tmA, bar, 0, k0, m0 / kAtomMN);
+        } else {
 #pragma unroll
-          for (int i = 0; i < kBM / kAtomMN; ++i)
-            ptx::tma_load_2d(sA + i * (kBK * 128), &tmA, full_bar(stage), m0 + i * kAtomMN, k0);
+          for (int i = 0; i < kBM / kAtomMN; ++i) {
+            if (CG == 2) ptx::tma_load_2d_cg2(sA + i * (kBK * 128), &tmA, bar, m0 + i * kAtomMN, k0);
+            else ptx::tma_load_2d(sA + i * (kBK * 128), &tmA, bar, m0 + i * kAtomMN, k0);
+          }
+        }
+        if (p.tma3d & (b_is_chk ? 4 : 2)) {
+          if (CG == 2) ptx::tma_load_3d_cg2(sB, tmb, bar, 0, k0, nb0 / kAtomMN);
+          else ptx::tma_load_3d(sB, tmb, bar, 0, k0, nb0 / kAtomMN);
+        } else {
 #pragma unroll
-          for (int i = 0; i < Cfg::kBNLocal / kAtomMN; ++i)
-            ptx::tma_load_2d(sB + i * (kBK * 128), tmb, full_bar(stage), nb0 + i * kAtomMN, k0);
+          for (int i = 0; i < Cfg::kBNLocal / kAtomMN; ++i) {
+            if (CG == 2) ptx::tma_load_2d_cg2(sB + i * (kBK * 128), tmb, bar, nb0 + i * kAtomMN, k0);
+            else ptx::tma_load_2d(sB + i * (kBK * 128), tmb, bar, nb0 + i * kAtomMN, k0);
+          }
         }
         if (++stage == kStages) {
           stage = 0;
