@@ -266,6 +266,8 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     // checksum vectors of B: 8 columns per N-tile, appended to B as extra tile-columns of the same GEMM
     p.n_chk_cols = p.tiles_n * kChkPerTile;
     p.tiles_c = (p.n_chk_cols + BN - 1) / BN;
+    p.dbg_flags = static_cast<int>(dbg("ft_dbg", 0)) & 1;
+    if (dbg("ft_dbg", 0) & 2) p.tiles_c = 0;  // experiment: no checksum tile-columns (expected checksums are garbage)
     const int chk_ld = (p.n_chk_cols + kAtomMN - 1) / kAtomMN * kAtomMN;  // padded so the 3-D TMA view is exact; pad
                                                                           // columns are never stored (n_chk_cols mask)
     const int n_slabs = p.tiles_m * CG * (kBM / 32);
@@ -278,14 +280,15 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     if (rc) return rc;
     p.chk_out = h->d_chk_out;
     p.chk_flags = reinterpret_cast<int *>(h->d_chk_out + out_floats);
-    FT_CUDA(h, cudaMemsetAsync(p.chk_flags, 0, n_slabs * sizeof(int), stream));
     const bool reuse = o.reuse_b_checksums && h->chk_for_b == dB && h->chk_n == N && h->chk_k == K && h->chk_bn == BN;
     if (!reuse) {
       dim3 grid(p.tiles_n, (K + kEncWarps * kEncKPerWarp - 1) / (kEncWarps * kEncKPerWarp));
       encode_b_kernel<<<grid, kEncWarps * 32, 0, stream>>>(dB, N, K, N, BN, h->d_chk, chk_ld,
-                                                           static_cast<int>(dbg("enc_rounding", 0)));
+                                                           static_cast<int>(dbg("enc_rounding", 0)), p.chk_flags, n_slabs);
       FT_CUDA(h, cudaGetLastError());
       h->chk_for_b = dB; h->chk_n = N; h->chk_k = K; h->chk_bn = BN;
+    } else {
+      FT_CUDA(h, cudaMemsetAsync(p.chk_flags, 0, n_slabs * sizeof(int), stream));
     }
     if (allow3d) {
       rc = make_tmap_3d(h, &tmC, h->d_chk, chk_ld, K, chk_ld, BN / CG / kAtomMN);

@@ -77,6 +77,7 @@ struct KernelParams {
   // bit 0 / 1 / 2: the A / B / checksum tensor map is 3-D {32, K, rows/32} so that ONE TMA instruction fetches a whole
   // operand stage (rows % 32 == 0); otherwise the map is 2-D {rows, K} and a stage takes one instruction per 32-row atom
   int tma3d;
+  int dbg_flags;        // experiments only: bit 0 = skip the epilogue ABFT check of data tiles
   // fault tolerance: checksum tile-columns
   int tiles_c;          // number of BN-wide checksum tile-columns (0 when FT is off)
   int n_chk_cols;       // tiles_n * kChkPerTile
@@ -140,6 +141,15 @@ __device__ __forceinline__ TileCoord decode_tile(const KernelParams &p, int t) {
   tc.n_blk = first_n + local % gsz;
   tc.m_blk = local / gsz;
   return tc;
+}
+
+// Checksum tile-columns only hold n_chk_cols real columns; the last one is narrowed to the next multiple of
+// 32*CG so that its UMMA N (and its tensor time) shrinks accordingly (e.g. 128 instead of 256 at N = 4096).
+template <int BN, int CG>
+__device__ __forceinline__ int chk_tile_width(const KernelParams &p, int c_blk) {
+  const int cols = min(BN, p.n_chk_cols - c_blk * BN);
+  const int q = 32 * CG;
+  return min(BN, (cols + q - 1) / q * q);
 }
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
@@ -437,8 +447,9 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int t = unit; t < num_tiles; t += num_units) {
       const TileCoord tc = decode_tile(p, t);
       const int m0 = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;        // this CTA's 128 rows of A
-      const int nb0 = tc.n_blk * BN + static_cast<int>(cta_rank) * Cfg::kBNLocal;  // this CTA's share of B rows
       const bool b_is_chk = FT && tc.is_chk;
+      const int n_eff = b_is_chk ? chk_tile_width<BN, CG>(p, tc.n_blk) : BN;
+      const int nb0 = tc.n_blk * BN + static_cast<int>(cta_rank) * (n_eff / CG);  // this CTA's share of B rows
       const CUtensorMap *tmb = b_is_chk ? &tmChk : &tmB;
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -486,6 +497,11 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = unit; t < num_tiles; t += num_units) {
+      uint32_t idesc_t = idesc;
+      if (FT) {
+        const TileCoord tc = decode_tile(p, t);
+        if (tc.is_chk) idesc_t = ptx::make_idesc_tf32(kBM * CG, chk_tile_width<BN, CG>(p, tc.n_blk), 1, 1);
+      }
       ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
@@ -499,8 +515,8 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint64_t da = ptx::make_smem_desc(sA + j * p.kstep_bytes, p.lbo_bytes, p.sbo_bytes, p.layout_type);
           const uint64_t db = ptx::make_smem_desc(sB + j * p.kstep_bytes, p.lbo_bytes, p.sbo_bytes, p.layout_type);
           const uint32_t accum = (kb | j) != 0 ? 1u : 0u;
-          if (CG == 2) ptx::mma_tf32_cg2(d_tmem, da, db, idesc, accum);
-          else ptx::mma_tf32(d_tmem, da, db, idesc, accum);
+          if (CG == 2) ptx::mma_tf32_cg2(d_tmem, da, db, idesc_t, accum);
+          else ptx::mma_tf32(d_tmem, da, db, idesc_t, accum);
         }
         // frees the smem slot (in both CTAs) once these MMAs have read it
         if (CG == 2) ptx::mma_commit_cg2(empty_bar(stage), 0x3);
@@ -544,7 +560,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       } else {
         int fix_col = -1;
         float fix_val = 0.0f;
-        if (FT) abft_check<BN>(p, taddr, q, lane, m, m0_cta, n0, tc.n_blk, fix_col, fix_val);
+        if (FT && !(p.dbg_flags & 1)) abft_check<BN>(p, taddr, q, lane, m, m0_cta, n0, tc.n_blk, fix_col, fix_val);
         store_tile<BN>(taddr, p.C + m, m < p.M, n0, p.N, p.ldc, p.alpha, p.beta, fix_col, fix_val);
       }
       // release this accumulator stage back to the MMA warp (of the leader CTA)
@@ -600,9 +616,14 @@ __device__ __forceinline__ void split3_tf32(double x, float &h, float &m, float 
 constexpr int kEncWarps = 8;
 constexpr int kEncKPerWarp = 4;
 
+// grid = (tiles_n, ceil(K / 32)), 8 warps x 4 k-rows each.  Every lane keeps kEncKPerWarp x (BN/128) 16-byte loads
+// in flight (B is N-contiguous), so the pass runs at HBM speed; it also clears the checksum slab flags of the GEMM
+// launch that follows it in the stream (one memset launch less).
 __global__ void __launch_bounds__(kEncWarps * 32)
 encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, float *__restrict__ chk, int chk_ld,
-                int rounding) {
+                int rounding, int *__restrict__ flags, int n_flags) {
+  if (flags != nullptr && blockIdx.x == 0 && blockIdx.y == 0)
+    for (int i = threadIdx.x; i < n_flags; i += blockDim.x) flags[i] = 0;
   const int t = blockIdx.x;
   const int n0 = t * BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -610,16 +631,37 @@ encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, floa
   double e[kEncKPerWarp], w[kEncKPerWarp];
 #pragma unroll
   for (int u = 0; u < kEncKPerWarp; ++u) e[u] = w[u] = 0.0;
-  for (int j = lane; j < BN; j += 32) {
-    const int n = n0 + j;
-    if (n < N) {
+  const bool vec_ok = (n0 + BN <= N);  // full tile: 16-byte loads (ldb % 4 == 0 and n0 % 4 == 0 by construction)
+  if (vec_ok) {
+    for (int j4 = lane; j4 < BN / 4; j4 += 32) {
+      float4 v[kEncKPerWarp];
 #pragma unroll
       for (int u = 0; u < kEncKPerWarp; ++u) {
         const int k = kbase + u;
-        if (k < K) {
-          const float b = tf32_bits(__ldg(B + static_cast<size_t>(k) * ldb + n), rounding);
-          e[u] += static_cast<double>(b);
-          w[u] += static_cast<double>(b) * static_cast<double>(j + 1);
+        v[u] = (k < K) ? __ldg(reinterpret_cast<const float4 *>(B + static_cast<size_t>(k) * ldb + n0) + j4)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const double wj = static_cast<double>(4 * j4 + 1);
+#pragma unroll
+      for (int u = 0; u < kEncKPerWarp; ++u) {
+        const double b0 = tf32_bits(v[u].x, rounding), b1 = tf32_bits(v[u].y, rounding),
+                     b2 = tf32_bits(v[u].z, rounding), b3 = tf32_bits(v[u].w, rounding);
+        e[u] += (b0 + b1) + (b2 + b3);
+        w[u] += b0 * wj + b1 * (wj + 1.0) + b2 * (wj + 2.0) + b3 * (wj + 3.0);
+      }
+    }
+  } else {
+    for (int j = lane; j < BN; j += 32) {
+      const int n = n0 + j;
+      if (n < N) {
+#pragma unroll
+        for (int u = 0; u < kEncKPerWarp; ++u) {
+          const int k = kbase + u;
+          if (k < K) {
+            const double b = tf32_bits(__ldg(B + static_cast<size_t>(k) * ldb + n), rounding);
+            e[u] += b;
+            w[u] += b * static_cast<double>(j + 1);
+          }
         }
       }
     }

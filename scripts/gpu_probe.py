@@ -89,6 +89,8 @@ def case_main(spec):
         res["gflops"] = {}
         for kid in ids:
             opts = None
+            if spec.get("reuse") or spec.get("tau_abs"):
+                opts = pkg.make_opts(reuse_b_checksums=bool(spec.get("reuse")), tau_abs=spec.get("tau_abs", 0))
             try:
                 for _ in range(3):
                     ft.run(kid, M, N, K, dA, dB, dC, alpha, beta, opts)
