@@ -80,7 +80,7 @@ class Stats(C.Structure):
 EXPORTED_SYMBOLS = [
     "ftsgemm_create", "ftsgemm_destroy", "ftsgemm_abi_version", "ftsgemm_error_string", "ftsgemm_last_cuda_error",
     "ftsgemm_default_opts", "ftsgemm_kernel_table", "ftsgemm_kernel_lookup", "ftsgemm_run", "ftsgemm_get_stats",
-    "ftsgemm_run_host", "ftsgemm_baseline", "ftsgemm_verify", "ftsgemm_debug_set",
+    "ftsgemm_run_host", "ftsgemm_baseline", "ftsgemm_verify", "ftsgemm_debug_set", "ftsgemm_debug_schedule",
 ]
 
 _lib = None
@@ -118,6 +118,7 @@ def lib():
         L.ftsgemm_baseline.argtypes = [vp, ip, ip, ip, vp, vp, vp, fp, fp, ip, C.POINTER(Opts), vp]
         L.ftsgemm_verify.argtypes = [vp, vp, vp, ip, ip, C.POINTER(C.c_longlong), C.POINTER(C.c_double), vp]
         L.ftsgemm_debug_set.argtypes = [C.c_char_p, C.c_longlong]
+        L.ftsgemm_debug_schedule.argtypes = [ip, ip, ip, ip, ip, C.POINTER(C.c_int), C.POINTER(C.c_int), ip]
         _lib = L
     return _lib
 
@@ -167,6 +168,19 @@ def make_opts(stream=None, selftest=None, faults=None, tau_abs=0.0, tau_rel=0.0,
     o.reuse_b_checksums = int(reuse_b_checksums)
     o.baseline_host_sync = int(baseline_host_sync)
     return o
+
+
+def debug_schedule(kernel_id: int, M: int, N: int, K: int, num_sms: int = 148):
+    """Work decomposition of one launch, enumerated on the host (no GPU needed): (header dict, list of segment dicts)."""
+    hdr = (C.c_int * 6)()
+    n = lib().ftsgemm_debug_schedule(kernel_id, M, N, K, num_sms, hdr, None, 0)
+    if n < 0:
+        _check(n)
+    rows = (C.c_int * (8 * max(n, 1)))()
+    lib().ftsgemm_debug_schedule(kernel_id, M, N, K, num_sms, hdr, rows, n)
+    keys = ("unit", "tile", "is_chk", "m_blk", "n_blk", "kb_begin", "kb_end", "kind")
+    segs = [dict(zip(keys, rows[8 * i:8 * i + 8])) for i in range(n)]
+    return dict(zip(("units", "num_tiles", "n_chk_tiles", "sk_tiles", "num_kb", "cta_group"), hdr)), segs
 
 
 def debug_set(key: str, value: int) -> None:

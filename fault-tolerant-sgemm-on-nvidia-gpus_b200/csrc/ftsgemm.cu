@@ -95,6 +95,9 @@ struct ftsgemm_handle_s {
   int chk_n = 0, chk_k = 0, chk_bn = 0;
   float *d_aux = nullptr;       // baseline vectors
   size_t aux_floats = 0;
+  float *d_sk = nullptr;        // stream-K partial tiles + flags
+  size_t sk_bytes = 0;
+  int sk_epoch = 0;
   float *d_stage[3] = {nullptr, nullptr, nullptr};  // run_host staging A, B, C
   size_t stage_bytes[3] = {0, 0, 0};
   double *d_verify = nullptr;   // {first_bad (as long long), num, den}
@@ -163,7 +166,7 @@ int make_tmap_3d(ftsgemm_handle_t h, CUtensorMap *tm, const float *base, uint64_
 
 template <int BN, bool FT, int CG>
 int launch_tc(ftsgemm_handle_t h, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
-              const KernelParams &p, cudaStream_t stream) {
+              const KernelParams &p, int units, cudaStream_t stream) {
   using Cfg = TileCfg<BN, FT, CG>;
   auto kern = ftsgemm_tc_kernel<BN, FT, CG>;
   static bool attr_set = false;
@@ -171,10 +174,6 @@ int launch_tc(ftsgemm_handle_t h, const CUtensorMap &tmA, const CUtensorMap &tmB
     FT_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int num_tiles = p.tiles_m * (p.tiles_n + p.tiles_c);
-  int units = static_cast<int>(dbg("grid", 0));
-  if (units <= 0) units = h->num_sms / CG;
-  if (units > num_tiles) units = num_tiles;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(units * CG);
@@ -190,6 +189,42 @@ int launch_tc(ftsgemm_handle_t h, const CUtensorMap &tmA, const CUtensorMap &tmB
   cfg.numAttrs = (CG > 1) ? 1 : 0;
   FT_CUDA(h, cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p));
   return FTSGEMM_OK;
+}
+
+// Tile grid + stream-K head for one launch; returns the number of persistent work units (CTAs or CTA pairs).
+// Fills tiles_m/tiles_n/group_n (and, for FT, n_chk_cols/tiles_c) and sk_tiles of *p.
+int plan_schedule(int num_sms, int CG, int K, KernelParams *p) {
+  const int num_tiles = p->tiles_m * (p->tiles_n + p->tiles_c);
+  int units = static_cast<int>(dbg("grid", 0));
+  if (units <= 0) units = num_sms / CG;
+  const int num_kb = (K + kBK - 1) / kBK;
+  p->sk_tiles = 0;
+  const int n_chk_tiles = p->tiles_c * p->tiles_m;
+  if (dbg("streamk", 1) != 0 && num_tiles % units != 0) {
+    // head = the remainder wave plus one full wave (1-2 tiles of k-blocks per unit keeps every tile's partial sums to a
+    // couple of contributors), at least all checksum tiles, and such that the data-parallel body is whole waves
+    int base = units < num_tiles ? units : num_tiles;
+    if (n_chk_tiles > base) base = n_chk_tiles;
+    p->sk_tiles = num_tiles - (num_tiles - base) / units * units;
+    if (static_cast<long long>(p->sk_tiles) * num_kb < units) p->sk_tiles = 0;  // nothing to balance
+  }
+  if (p->sk_tiles == 0 && units > num_tiles) units = num_tiles;
+  return units;
+}
+
+void plan_tiles(int M, int N, int BN, int CG, bool ft, KernelParams *p) {
+  p->tiles_m = (M + kBM * CG - 1) / (kBM * CG);
+  p->tiles_n = (N + BN - 1) / BN;
+  long long g = dbg("group_n", 0);
+  p->group_n = g > 0 ? static_cast<int>(g) : (2048 / BN > 0 ? 2048 / BN : 1);
+  if (p->group_n > p->tiles_n) p->group_n = p->tiles_n;
+  p->n_chk_cols = 0;
+  p->tiles_c = 0;
+  if (ft) {
+    p->n_chk_cols = p->tiles_n * kChkPerTile;
+    p->tiles_c = (p->n_chk_cols + BN - 1) / BN;
+    if (dbg("ft_dbg", 0) & 2) p->tiles_c = 0;  // experiment: no checksum tile-columns (expected checksums are garbage)
+  }
 }
 
 int ensure_buf(ftsgemm_handle_t h, float **buf, size_t *have, size_t bytes) {
@@ -215,11 +250,7 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
   p.M = M; p.N = N; p.K = K;
   p.C = dC; p.ldc = M;
   p.alpha = alpha; p.beta = beta;
-  p.tiles_m = (M + kBM * CG - 1) / (kBM * CG);
-  p.tiles_n = (N + BN - 1) / BN;
-  long long g = dbg("group_n", 0);
-  p.group_n = g > 0 ? static_cast<int>(g) : (2048 / BN > 0 ? 2048 / BN : 1);
-  if (p.group_n > p.tiles_n) p.group_n = p.tiles_n;
+  plan_tiles(M, N, BN, CG, ft, &p);
   // MN-major fp32 operands: 128B swizzle with 32B atoms.  One TMA box = 32 (M|N) x 32 (K) floats = 32 rows of
   // 128 bytes, so successive M|N atoms are kBK*128 bytes apart (LBO), successive groups of 4 K-rows 512 bytes (SBO),
   // and one UMMA k-step (8 K-rows) advances the start address by 1024 bytes.
@@ -264,10 +295,7 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
   tmC = tmB;
   if (ft) {
     // checksum vectors of B: 8 columns per N-tile, appended to B as extra tile-columns of the same GEMM
-    p.n_chk_cols = p.tiles_n * kChkPerTile;
-    p.tiles_c = (p.n_chk_cols + BN - 1) / BN;
     p.dbg_flags = static_cast<int>(dbg("ft_dbg", 0)) & 1;
-    if (dbg("ft_dbg", 0) & 2) p.tiles_c = 0;  // experiment: no checksum tile-columns (expected checksums are garbage)
     const int chk_ld = (p.n_chk_cols + kAtomMN - 1) / kAtomMN * kAtomMN;  // padded so the 3-D TMA view is exact; pad
                                                                           // columns are never stored (n_chk_cols mask)
     const int n_slabs = p.tiles_m * CG * (kBM / 32);
@@ -298,11 +326,27 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     }
     if (rc) return rc;
   }
+  // ---- work decomposition: stream-K head + data-parallel body (SegIter in ftsgemm_kernel.cuh)
+  int units = plan_schedule(h->num_sms, CG, K, &p);
+  if (p.sk_tiles > 0) {
+    const size_t flag_bytes = 4096;  // fixed location at the start of the buffer: (units * CG * 4) ints <= 2368 bytes
+    const size_t ws_floats = static_cast<size_t>(units) * CG * kBM * BN;
+    const float *before = h->d_sk;
+    rc = ensure_buf(h, &h->d_sk, &h->sk_bytes, flag_bytes + ws_floats * sizeof(float));
+    if (rc) return rc;
+    p.sk_flags = reinterpret_cast<int *>(h->d_sk);
+    p.sk_ws = h->d_sk + flag_bytes / sizeof(float);
+    if (h->d_sk != before || h->sk_epoch > (1 << 30)) {  // fresh buffer (or epoch wrap): no flag may alias a live epoch
+      FT_CUDA(h, cudaMemsetAsync(p.sk_flags, 0, flag_bytes, stream));
+      h->sk_epoch = 0;
+    }
+    p.sk_epoch = ++h->sk_epoch;
+  }
   h->last_stream = stream;
 #define FT_DISPATCH(bn, cg)                                                          \
   if (BN == bn && CG == cg)                                                          \
-    return ft ? launch_tc<bn, true, cg>(h, tmA, tmB, tmC, p, stream)                 \
-              : launch_tc<bn, false, cg>(h, tmA, tmB, tmC, p, stream);
+    return ft ? launch_tc<bn, true, cg>(h, tmA, tmB, tmC, p, units, stream)          \
+              : launch_tc<bn, false, cg>(h, tmA, tmB, tmC, p, units, stream);
   FT_DISPATCH(32, 1)
   FT_DISPATCH(64, 1)
   FT_DISPATCH(128, 1)
@@ -397,6 +441,39 @@ int ftsgemm_kernel_lookup(int kernel_id, ftsgemm_kernel_info *out) {
   return FTSGEMM_OK;
 }
 
+// Enumerate the work decomposition of one launch on the HOST (same inline code the device runs): for every work unit,
+// in processing order, rows of 8 ints {unit, tile, is_chk, m_blk, n_blk, kb_begin, kb_end, kind}.  Returns the number
+// of rows (fills min(cap, rows)); hdr[0..5] = {units, num_tiles, n_chk_tiles, sk_tiles, num_kb, cta_group}.
+int ftsgemm_debug_schedule(int kernel_id, int M, int N, int K, int num_sms, int *hdr, int *rows, int cap) {
+  const Variant *v = find_variant(kernel_id);
+  if (!v || v->info.engine != 1 || M <= 0 || N <= 0 || K <= 0 || num_sms <= 0) return FTSGEMM_ERR_INVALID_ARG;
+  KernelParams p;
+  memset(&p, 0, sizeof(p));
+  plan_tiles(M, N, v->bn, v->cg, v->info.fault_tolerant != 0, &p);
+  const int units = plan_schedule(num_sms, v->cg, K, &p);
+  const int num_tiles = p.tiles_m * (p.tiles_n + p.tiles_c);
+  const int num_kb = (K + kBK - 1) / kBK;
+  if (hdr) {
+    hdr[0] = units; hdr[1] = num_tiles; hdr[2] = p.tiles_c * p.tiles_m; hdr[3] = p.sk_tiles; hdr[4] = num_kb;
+    hdr[5] = v->cg;
+  }
+  int n = 0;
+  for (int u = 0; u < units; ++u) {
+    SegIter it(p, u, units, num_kb, num_tiles);
+    Segment sg;
+    while (it.next(sg)) {
+      if (rows && n < cap) {
+        const TileCoord tc = decode_tile(p, sg.tile);
+        int *r = rows + 8 * n;
+        r[0] = u; r[1] = sg.tile; r[2] = tc.is_chk ? 1 : 0; r[3] = tc.m_blk; r[4] = tc.n_blk;
+        r[5] = sg.kb_begin; r[6] = sg.kb_end; r[7] = sg.kind;
+      }
+      ++n;
+    }
+  }
+  return n;
+}
+
 int ftsgemm_debug_set(const char *key, long long value) {
   if (!key) return FTSGEMM_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(g_dbg_mu);
@@ -446,6 +523,7 @@ int ftsgemm_destroy(ftsgemm_handle_t h) {
   cudaFree(h->d_stats);
   cudaFree(h->d_chk);
   cudaFree(h->d_chk_out);
+  cudaFree(h->d_sk);
   cudaFree(h->d_aux);
   cudaFree(h->d_verify);
   for (int i = 0; i < 3; ++i) cudaFree(h->d_stage[i]);

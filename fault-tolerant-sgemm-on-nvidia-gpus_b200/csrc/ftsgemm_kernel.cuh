@@ -78,6 +78,12 @@ struct KernelParams {
   // operand stage (rows % 32 == 0); otherwise the map is 2-D {rows, K} and a stage takes one instruction per 32-row atom
   int tma3d;
   int dbg_flags;        // experiments only: bit 0 = skip the epilogue ABFT check of data tiles
+  // stream-K head: the first sk_tiles tiles (in decode order) are cut into equal k-block ranges, one per work unit, so
+  // that a tile count that is not a multiple of the unit count does not leave SMs idle in the last wave
+  int sk_tiles;
+  float *sk_ws;         // per unit, per CTA of the group: one raw 128 x BN accumulator tile (column-major, ld = 128)
+  int *sk_flags;        // [(unit*CG + cta_rank)*4 + quadrant] = sk_epoch once that slab of the partial tile is written
+  int sk_epoch;
   // fault tolerance: checksum tile-columns
   int tiles_c;          // number of BN-wide checksum tile-columns (0 when FT is off)
   int n_chk_cols;       // tiles_n * kChkPerTile
@@ -119,24 +125,28 @@ struct TileCoord {
   bool is_chk;
 };
 
-// Tile order: all checksum tile-columns first (so their results are published long before the data tiles that need
-// them reach their epilogue), then the data tiles in groups of group_n tile-columns, M fastest inside a group, so
-// that one wave of CTAs shares few A row-panels and few B row-panels in L2.
-__device__ __forceinline__ TileCoord decode_tile(const KernelParams &p, int t) {
+// Tile order.  Data tiles run in groups of group_n tile-columns, M fastest inside a group, so that one wave of CTAs
+// shares few A row-panels and few B row-panels in L2.  Checksum tile-columns must be finished early, and no work unit
+// may meet a data tile before a checksum tile it owns (its epilogue would wait for itself):
+//   * without a stream-K head they are simply the first tiles;
+//   * with a stream-K head they are the LAST indices of the head, because units walk their head range backwards.
+__host__ __device__ __forceinline__ TileCoord decode_tile(const KernelParams &p, int t) {
   TileCoord tc;
   const int n_chk_tiles = p.tiles_c * p.tiles_m;
-  if (t < n_chk_tiles) {
+  const int chk_first = p.sk_tiles > 0 ? p.sk_tiles - n_chk_tiles : 0;
+  if (t >= chk_first && t < chk_first + n_chk_tiles) {
+    const int c = t - chk_first;
     tc.is_chk = true;
-    tc.m_blk = t % p.tiles_m;
-    tc.n_blk = t / p.tiles_m;
+    tc.m_blk = c % p.tiles_m;
+    tc.n_blk = c / p.tiles_m;
     return tc;
   }
-  t -= n_chk_tiles;
+  if (t >= chk_first) t -= n_chk_tiles;
   tc.is_chk = false;
   const int per_group = p.group_n * p.tiles_m;
   const int g = t / per_group;
   const int first_n = g * p.group_n;
-  const int gsz = min(p.group_n, p.tiles_n - first_n);
+  const int gsz = p.group_n < p.tiles_n - first_n ? p.group_n : p.tiles_n - first_n;
   const int local = t - g * per_group;
   tc.n_blk = first_n + local % gsz;
   tc.m_blk = local / gsz;
@@ -146,11 +156,63 @@ __device__ __forceinline__ TileCoord decode_tile(const KernelParams &p, int t) {
 // Checksum tile-columns only hold n_chk_cols real columns; the last one is narrowed to the next multiple of
 // 32*CG so that its UMMA N (and its tensor time) shrinks accordingly (e.g. 128 instead of 256 at N = 4096).
 template <int BN, int CG>
-__device__ __forceinline__ int chk_tile_width(const KernelParams &p, int c_blk) {
-  const int cols = min(BN, p.n_chk_cols - c_blk * BN);
+__host__ __device__ __forceinline__ int chk_tile_width(const KernelParams &p, int c_blk) {
+  const int rest = p.n_chk_cols - c_blk * BN;
+  const int cols = rest < BN ? rest : BN;
   const int q = 32 * CG;
-  return min(BN, (cols + q - 1) / q * q);
+  const int w = (cols + q - 1) / q * q;
+  return w < BN ? w : BN;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Work decomposition.  Every role (producer, MMA issuer, epilogue) walks the same list of segments:
+//   stream-K head  tiles [0, sk_tiles) linearised as (tile, k-block); unit u owns the contiguous k-block range
+//                  [total*u/P, total*(u+1)/P) and walks it BACKWARDS, so the piece that only starts a tile (a
+//                  "contributor": partial sums go to the workspace) is done first and the piece that ends a tile (the
+//                  "finisher": adds the contributors' partial sums, then runs the normal epilogue) is done last --
+//                  finishers therefore only ever wait for work other units did at the start of their range
+//   data-parallel  tiles sk_tiles + u, + P, ... whole tiles
+// ------------------------------------------------------------------------------------------------------------
+struct Segment {
+  int tile, kb_begin, kb_end;
+  int kind;  // 0 whole tile, 1 contributor, 2 finisher
+};
+
+struct SegIter {
+  long long b, cur;
+  int dp_tile, num_kb, num_tiles, stride;
+  __host__ __device__ __forceinline__ SegIter(const KernelParams &p, int unit, int num_units, int num_kb_, int num_tiles_) {
+    num_kb = num_kb_;
+    num_tiles = num_tiles_;
+    stride = num_units;
+    const long long total = static_cast<long long>(p.sk_tiles) * num_kb;
+    b = total * unit / num_units;
+    cur = total * (unit + 1) / num_units;
+    dp_tile = p.sk_tiles + unit;
+  }
+  __host__ __device__ __forceinline__ bool next(Segment &s) {
+    if (cur > b) {
+      const int tile = static_cast<int>((cur - 1) / num_kb);
+      const long long t0 = static_cast<long long>(tile) * num_kb;
+      const long long sb = b > t0 ? b : t0;
+      s.tile = tile;
+      s.kb_begin = static_cast<int>(sb - t0);
+      s.kb_end = static_cast<int>(cur - t0);
+      s.kind = (s.kb_end == num_kb) ? (s.kb_begin == 0 ? 0 : 2) : 1;
+      cur = sb;
+      return true;
+    }
+    if (dp_tile < num_tiles) {
+      s.tile = dp_tile;
+      s.kb_begin = 0;
+      s.kb_end = num_kb;
+      s.kind = 0;
+      dp_tile += stride;
+      return true;
+    }
+    return false;
+  }
+};
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
   int v;
@@ -376,6 +438,49 @@ __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Stream-K fix-up (epilogue warps, lane = row).  A contributor dumps its raw accumulator slab; a finisher adds the
+// slabs of every unit that worked on the earlier k-blocks of its tile back INTO tensor memory, so that the ABFT
+// check and the store pass that follow see the complete sum.
+// ------------------------------------------------------------------------------------------------------------
+template <int BN>
+__device__ __forceinline__ void sk_dump_partial(const KernelParams &p, uint32_t taddr, float *ws, int *flag, int lane) {
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t v[32];
+    ptx::tmem_ld_x32(taddr + c * 32, v);
+    ptx::tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) __stcg(ws + (c * 32 + i) * kBM, u2f(v[i]));
+  }
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) atomicExch(flag, p.sk_epoch);
+}
+
+template <int BN>
+__device__ __forceinline__ void sk_add_partial(const KernelParams &p, uint32_t taddr, const float *ws, const int *flag,
+                                               int lane) {
+  if (lane == 0) {
+    unsigned spins = 0;
+    while (ld_acquire(flag) != p.sk_epoch) {
+      __nanosleep(64);
+      if (++spins > (1u << 24)) __trap();
+    }
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t v[32];
+    ptx::tmem_ld_x32(taddr + c * 32, v);
+    ptx::tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = f2u(u2f(v[i]) + __ldcg(ws + (c * 32 + i) * kBM));
+    ptx::tmem_st_x32(taddr + c * 32, v);
+    ptx::tmem_wait_st();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // The kernel.
 // ------------------------------------------------------------------------------------------------------------
 template <int BN, bool FT, int CG>
@@ -444,48 +549,78 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================================================================== TMA producer (every CTA)
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = unit; t < num_tiles; t += num_units) {
-      const TileCoord tc = decode_tile(p, t);
+    SegIter it(p, unit, num_units, num_kb, num_tiles);
+    Segment sg;
+    while (it.next(sg)) {
+      const TileCoord tc = decode_tile(p, sg.tile);
       const int m0 = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;        // this CTA's 128 rows of A
       const bool b_is_chk = FT && tc.is_chk;
       const int n_eff = b_is_chk ? chk_tile_width<BN, CG>(p, tc.n_blk) : BN;
       const int nb0 = tc.n_blk * BN + static_cast<int>(cta_rank) * (n_eff / CG);  // this CTA's share of B rows
       const CUtensorMap *tmb = b_is_chk ? &tmChk : &tmB;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t sA = smem_base + stage * Cfg::kStageBytes;
-        const uint32_t sB = sA + Cfg::kABytes;
-        const int k0 = kb * kBK;
-        const uint32_t bar = (CG == 2) ? ptx::mapa(full_bar(stage), 0) : full_bar(stage);  // the leader collects the bytes
-        if (CG == 2) {
-          if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-          else ptx::mbar_arrive_cluster(bar);
-        } else {
-          ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-        }
-        if (p.tma3d & 1) {
-          if (CG == 2) ptx::tma_load_3d_cg2(sA, &tmA, bar, 0, k0, m0 / kAtomMN);
-          else ptx::tma_load_3d(sA, &tmA, bar, 0, k0, m0 / kAtomMN);
-        } else {
-#pragma unroll
-          for (int i = 0; i < kBM / kAtomMN; ++i) {
-            if (CG == 2) ptx::tma_load_2d_cg2(sA + i * (kBK * 128), &tmA, bar, m0 + i * kAtomMN, k0);
-            else ptx::tma_load_2d(sA + i * (kBK * 128), &tmA, bar, m0 + i * kAtomMN, k0);
+      // The loop body is specialised OUTSIDE the k loop: with 3-D tensor maps a stage is exactly two TMA instructions
+      // (predicated-off TMA instructions still cost issue time on the single producer thread).
+      const bool all3d = (p.tma3d & 1) && (p.tma3d & (b_is_chk ? 4 : 2));
+      const int a_atom = m0 / kAtomMN, b_atom = nb0 / kAtomMN;
+      if (all3d) {
+        for (int kb = sg.kb_begin; kb < sg.kb_end; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sA = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sB = sA + Cfg::kABytes;
+          const int k0 = kb * kBK;
+          if (CG == 2) {
+            const uint32_t bar = ptx::mapa(full_bar(stage), 0);  // the leader's barrier collects both CTAs' bytes
+            if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+            else ptx::mbar_arrive_cluster(bar);
+            ptx::tma_load_3d_cg2(sA, &tmA, bar, 0, k0, a_atom);
+            ptx::tma_load_3d_cg2(sB, tmb, bar, 0, k0, b_atom);
+          } else {
+            ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            ptx::tma_load_3d(sA, &tmA, full_bar(stage), 0, k0, a_atom);
+            ptx::tma_load_3d(sB, tmb, full_bar(stage), 0, k0, b_atom);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
-        if (p.tma3d & (b_is_chk ? 4 : 2)) {
-          if (CG == 2) ptx::tma_load_3d_cg2(sB, tmb, bar, 0, k0, nb0 / kAtomMN);
-          else ptx::tma_load_3d(sB, tmb, bar, 0, k0, nb0 / kAtomMN);
-        } else {
-#pragma unroll
-          for (int i = 0; i < Cfg::kBNLocal / kAtomMN; ++i) {
-            if (CG == 2) ptx::tma_load_2d_cg2(sB + i * (kBK * 128), tmb, bar, nb0 + i * kAtomMN, k0);
-            else ptx::tma_load_2d(sB + i * (kBK * 128), tmb, bar, nb0 + i * kAtomMN, k0);
+      } else {
+        for (int kb = sg.kb_begin; kb < sg.kb_end; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sA = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sB = sA + Cfg::kABytes;
+          const int k0 = kb * kBK;
+          const uint32_t bar = (CG == 2) ? ptx::mapa(full_bar(stage), 0) : full_bar(stage);
+          if (CG == 2) {
+            if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+            else ptx::mbar_arrive_cluster(bar);
+          } else {
+            ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
           }
-        }
-        if (++stage == kStages) {
-          stage = 0;
-          phase ^= 1u;
+          if (p.tma3d & 1) {
+            if (CG == 2) ptx::tma_load_3d_cg2(sA, &tmA, bar, 0, k0, a_atom);
+            else ptx::tma_load_3d(sA, &tmA, bar, 0, k0, a_atom);
+          } else {
+#pragma unroll
+            for (int i = 0; i < kBM / kAtomMN; ++i) {
+              if (CG == 2) ptx::tma_load_2d_cg2(sA + i * (kBK * 128), &tmA, bar, m0 + i * kAtomMN, k0);
+              else ptx::tma_load_2d(sA + i * (kBK * 128), &tmA, bar, m0 + i * kAtomMN, k0);
+            }
+          }
+          if (p.tma3d & (b_is_chk ? 4 : 2)) {
+            if (CG == 2) ptx::tma_load_3d_cg2(sB, tmb, bar, 0, k0, b_atom);
+            else ptx::tma_load_3d(sB, tmb, bar, 0, k0, b_atom);
+          } else {
+#pragma unroll
+            for (int i = 0; i < Cfg::kBNLocal / kAtomMN; ++i) {
+              if (CG == 2) ptx::tma_load_2d_cg2(sB + i * (kBK * 128), tmb, bar, nb0 + i * kAtomMN, k0);
+              else ptx::tma_load_2d(sB + i * (kBK * 128), tmb, bar, nb0 + i * kAtomMN, k0);
+            }
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
       }
     }
@@ -496,16 +631,18 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = unit; t < num_tiles; t += num_units) {
+    SegIter it(p, unit, num_units, num_kb, num_tiles);
+    Segment sg;
+    while (it.next(sg)) {
       uint32_t idesc_t = idesc;
       if (FT) {
-        const TileCoord tc = decode_tile(p, t);
+        const TileCoord tc = decode_tile(p, sg.tile);
         if (tc.is_chk) idesc_t = ptx::make_idesc_tf32(kBM * CG, chk_tile_width<BN, CG>(p, tc.n_blk), 1, 1);
       }
       ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = sg.kb_begin; kb < sg.kb_end; ++kb) {
         ptx::mbar_wait(full_bar(stage), phase);
         ptx::tc_fence_after();
         const uint32_t sA = smem_base + stage * Cfg::kStageBytes;
@@ -514,7 +651,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int j = 0; j < kBK / 8; ++j) {
           const uint64_t da = ptx::make_smem_desc(sA + j * p.kstep_bytes, p.lbo_bytes, p.sbo_bytes, p.layout_type);
           const uint64_t db = ptx::make_smem_desc(sB + j * p.kstep_bytes, p.lbo_bytes, p.sbo_bytes, p.layout_type);
-          const uint32_t accum = (kb | j) != 0 ? 1u : 0u;
+          const uint32_t accum = (kb != sg.kb_begin || j != 0) ? 1u : 0u;
           if (CG == 2) ptx::mma_tf32_cg2(d_tmem, da, db, idesc_t, accum);
           else ptx::mma_tf32(d_tmem, da, db, idesc_t, accum);
         }
@@ -542,8 +679,12 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t tempty_leader = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = unit; t < num_tiles; t += num_units) {
-      const TileCoord tc = decode_tile(p, t);
+    SegIter it(p, unit, num_units, num_kb, num_tiles);
+    Segment sg;
+    const long long sk_total = static_cast<long long>(p.sk_tiles) * num_kb;
+    const size_t ws_slab = static_cast<size_t>(kBM) * BN;  // floats per (unit, CTA) partial tile
+    while (it.next(sg)) {
+      const TileCoord tc = decode_tile(p, sg.tile);
       const int m0_cta = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;
       const int n0 = tc.n_blk * BN;
       const int m = m0_cta + row;
@@ -551,7 +692,24 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
-      if (FT && tc.is_chk) {
+      if (sg.kind == 1) {
+        // stream-K contributor: park the raw partial sums of this slab for the unit that finishes the tile
+        const int slot = unit * CG + static_cast<int>(cta_rank);
+        sk_dump_partial<BN>(p, taddr, p.sk_ws + slot * ws_slab + row, p.sk_flags + slot * 4 + q, lane);
+      } else if (sg.kind == 2) {
+        // stream-K finisher: fold in every unit that covered the earlier k-blocks of this tile (units u-1, u-2, ...)
+        const long long t0 = static_cast<long long>(sg.tile) * num_kb;
+        for (int v = unit - 1; v >= 0; --v) {
+          const long long vb = sk_total * v / num_units, ve = sk_total * (v + 1) / num_units;
+          if (ve <= t0) break;
+          const int slot = v * CG + static_cast<int>(cta_rank);
+          sk_add_partial<BN>(p, taddr, p.sk_ws + slot * ws_slab + row, p.sk_flags + slot * 4 + q, lane);
+          if (vb <= t0) break;
+        }
+      }
+      if (sg.kind == 1) {
+        // nothing to store yet
+      } else if (FT && tc.is_chk) {
         // checksum tile-column: publish R = A * [e, w]^T for these 128 rows, then raise the slab flag
         store_tile<BN>(taddr, p.chk_out + m, m < p.M, n0, p.n_chk_cols, p.M, 1.0f, 0.0f, -1, 0.0f);
         __threadfence();
@@ -614,7 +772,7 @@ __device__ __forceinline__ void split3_tf32(double x, float &h, float &m, float 
 }
 
 constexpr int kEncWarps = 8;
-constexpr int kEncKPerWarp = 4;
+constexpr int kEncKPerWarp = 8;
 
 // grid = (tiles_n, ceil(K / 32)), 8 warps x 4 k-rows each.  Every lane keeps kEncKPerWarp x (BN/128) 16-byte loads
 // in flight (B is N-contiguous), so the pass runs at HBM speed; it also clears the checksum slab flags of the GEMM

@@ -1,0 +1,128 @@
+"""CPU checks of the kernel's work decomposition (stream-K head + data-parallel body + checksum tile-columns), using
+the host-side enumeration of the SAME inline code the device runs (ftsgemm_debug_schedule):
+  * every (tile, k-block) is computed exactly once; every tile has exactly one finishing segment;
+  * a finisher's contributors are exactly the units the kernel's lookup rule visits;
+  * no circular wait: with in-order roles, 2 (or 1) TMEM accumulator stages per unit, finishers waiting for
+    contributors and ABFT data tiles waiting for their checksum tile-columns, every segment completes."""
+import itertools
+
+import pytest
+
+TILE_N = {1: 32, 2: 64, 6: 128, 5: 256, 21: 256, 22: 128, 11: 32, 12: 64, 16: 128, 15: 256, 31: 256, 32: 128}
+
+
+def _simulate(hdr, segs, acc_stages):
+    units = hdr["units"]
+    per_unit = [[] for _ in range(units)]
+    for s in segs:
+        per_unit[s["unit"]].append(s)
+    tiles_c = 0
+    chk_done = {}     # (m_blk, c) -> bool
+    contrib = {}      # tile -> list of (unit, idx)
+    for u, lst in enumerate(per_unit):
+        for i, s in enumerate(lst):
+            if s["is_chk"]:
+                chk_done[(s["m_blk"], s["n_blk"])] = False
+                tiles_c = max(tiles_c, s["n_blk"] + 1)
+            if s["kind"] == 1:
+                contrib.setdefault(s["tile"], []).append((u, i))
+    mma_done = [0] * units   # number of segments whose MMA finished
+    epi_done = [0] * units
+    done_epi = set()         # (unit, idx)
+    progress = True
+    while progress:
+        progress = False
+        for u, lst in enumerate(per_unit):
+            # MMA of segment i needs the accumulator stage used by segment i - acc_stages to be drained
+            while mma_done[u] < len(lst) and mma_done[u] - epi_done[u] < acc_stages:
+                mma_done[u] += 1
+                progress = True
+            while epi_done[u] < mma_done[u]:
+                i = epi_done[u]
+                s = lst[i]
+                ok = True
+                if s["kind"] == 2:
+                    ok = all(c in done_epi for c in contrib.get(s["tile"], []))
+                if ok and hdr["n_chk_tiles"] and not s["is_chk"] and s["kind"] != 1:
+                    ok = all(chk_done[(s["m_blk"], c)] for c in range(tiles_c))
+                if not ok:
+                    break
+                epi_done[u] += 1
+                done_epi.add((u, i))
+                if s["is_chk"] and s["kind"] != 1:
+                    chk_done[(s["m_blk"], s["n_blk"])] = True
+                progress = True
+    return all(epi_done[u] == len(per_unit[u]) for u in range(units))
+
+
+@pytest.mark.parametrize("kid", [1, 6, 5, 21, 22, 12, 16, 15, 31, 32])
+@pytest.mark.parametrize("shape", [(4096, 4096, 4096), (2048, 2048, 2048), (1024, 1024, 1024), (8192, 8192, 512),
+                                   (1536, 2560, 1000), (256, 256, 64), (128, 4096, 32), (5120, 384, 4096),
+                                   (16384, 16384, 1024), (32768, 1024, 256)])
+@pytest.mark.parametrize("num_sms", [148, 16, 6])
+def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms):
+    M, N, K = shape
+    hdr, segs = ft.debug_schedule(kid, M, N, K, num_sms)
+    units, num_kb, sk = hdr["units"], hdr["num_kb"], hdr["sk_tiles"]
+    assert hdr["num_kb"] == -(-K // 32)
+    cover = {}
+    finishers = {}
+    for s in segs:
+        assert 0 <= s["kb_begin"] < s["kb_end"] <= num_kb
+        cover.setdefault(s["tile"], []).append((s["kb_begin"], s["kb_end"], s["unit"], s["kind"]))
+        if s["kind"] != 1:
+            assert s["kb_end"] == num_kb
+            assert s["tile"] not in finishers
+            finishers[s["tile"]] = s
+        else:
+            assert s["kb_end"] < num_kb and s["tile"] < sk
+    assert sorted(cover) == list(range(hdr["num_tiles"]))
+    total = sk * num_kb
+    for t, pieces in cover.items():
+        pieces.sort()
+        assert pieces[0][0] == 0 and pieces[-1][1] == num_kb
+        for a, b in zip(pieces, pieces[1:]):
+            assert a[1] == b[0]  # contiguous, no overlap
+        fin = finishers[t]
+        contributors = sorted(p[2] for p in pieces if p[3] == 1)
+        if fin["kind"] == 0:
+            assert not contributors
+        else:
+            # the kernel's lookup rule (epilogue, kind == 2)
+            visited, t0, u = [], t * num_kb, fin["unit"]
+            for v in range(u - 1, -1, -1):
+                vb, ve = total * v // units, total * (v + 1) // units
+                if ve <= t0:
+                    break
+                visited.append(v)
+                if vb <= t0:
+                    break
+            assert sorted(visited) == contributors and contributors
+    # at most one contributor segment per unit (one workspace slot per unit)
+    per_unit_contrib = {}
+    for s in segs:
+        if s["kind"] == 1:
+            per_unit_contrib[s["unit"]] = per_unit_contrib.get(s["unit"], 0) + 1
+    assert all(v == 1 for v in per_unit_contrib.values())
+    # checksum tiles: n_chk_tiles of them, 8 columns per N-tile
+    chk = {(s["m_blk"], s["n_blk"]) for s in segs if s["is_chk"]}
+    assert len(chk) == hdr["n_chk_tiles"]
+    if kid in (11, 12, 16, 15, 31, 32):
+        tiles_n = -(-N // TILE_N[kid])
+        assert hdr["n_chk_tiles"] == -(-M // (128 * hdr["cta_group"])) * -(-(tiles_n * 8) // TILE_N[kid])
+    acc_stages = 2 if 2 * TILE_N[kid] <= 512 else 1
+    assert _simulate(hdr, segs, acc_stages), "circular wait in the schedule"
+
+
+def test_balanced_head(ft):
+    """The stream-K head gives every unit the same number of k-blocks (+-1) and whole waves afterwards."""
+    hdr, segs = ft.debug_schedule(21, 4096, 4096, 4096, 148)
+    assert hdr["units"] == 74 and hdr["num_tiles"] == 256 and hdr["sk_tiles"] == 108  # 256 = 108 + 2 * 74
+    work = [0] * hdr["units"]
+    for s in segs:
+        work[s["unit"]] += s["kb_end"] - s["kb_begin"]
+    assert max(work) - min(work) <= 1
+    hdr, segs = ft.debug_schedule(21, 8192, 8192, 8192, 148)
+    assert hdr["num_tiles"] == 1024 and (hdr["num_tiles"] - hdr["sk_tiles"]) % 74 == 0
+    hdr, segs = ft.debug_schedule(21, 2048, 2048, 2048, 148)  # fewer tiles than units: everything is split
+    assert hdr["sk_tiles"] == hdr["num_tiles"] == 64
