@@ -172,15 +172,15 @@ def make_opts(stream=None, selftest=None, faults=None, tau_abs=0.0, tau_rel=0.0,
 
 def debug_schedule(kernel_id: int, M: int, N: int, K: int, num_sms: int = 148):
     """Work decomposition of one launch, enumerated on the host (no GPU needed): (header dict, list of segment dicts)."""
-    hdr = (C.c_int * 6)()
+    hdr = (C.c_int * 7)()
     n = lib().ftsgemm_debug_schedule(kernel_id, M, N, K, num_sms, hdr, None, 0)
     if n < 0:
         _check(n)
-    rows = (C.c_int * (8 * max(n, 1)))()
+    rows = (C.c_int * (9 * max(n, 1)))()
     lib().ftsgemm_debug_schedule(kernel_id, M, N, K, num_sms, hdr, rows, n)
-    keys = ("unit", "tile", "is_chk", "m_blk", "n_blk", "kb_begin", "kb_end", "kind")
-    segs = [dict(zip(keys, rows[8 * i:8 * i + 8])) for i in range(n)]
-    return dict(zip(("units", "num_tiles", "n_chk_tiles", "sk_tiles", "num_kb", "cta_group"), hdr)), segs
+    keys = ("unit", "tile", "is_chk", "m_blk", "n_blk", "kb_begin", "kb_end", "kind", "slice")
+    segs = [dict(zip(keys, rows[9 * i:9 * i + 9])) for i in range(n)]
+    return dict(zip(("units", "num_tiles", "n_chk_tiles", "sk_tiles", "num_kb", "cta_group", "sk_slices"), hdr)), segs
 
 
 def debug_set(key: str, value: int) -> None:

@@ -191,24 +191,60 @@ int launch_tc(ftsgemm_handle_t h, const CUtensorMap &tmA, const CUtensorMap &tmB
   return FTSGEMM_OK;
 }
 
-// Tile grid + stream-K head for one launch; returns the number of persistent work units (CTAs or CTA pairs).
-// Fills tiles_m/tiles_n/group_n (and, for FT, n_chk_cols/tiles_c) and sk_tiles of *p.
-int plan_schedule(int num_sms, int CG, int K, KernelParams *p) {
+// Work decomposition of one launch; returns the number of persistent work units (CTAs or CTA pairs) and fills
+// sk_tiles / sk_slices of *p (tile grid already set by plan_tiles).  Candidates: no split; split the remainder wave;
+// split the remainder wave plus one full wave; 2..8 slices.  The estimate is the makespan in tile-times of the
+// round-robin item assignment SegIter performs, with a per-slice overhead for the partial-sum round trip.
+int plan_schedule(int num_sms, int CG, int BN, int K, KernelParams *p) {
   const int num_tiles = p->tiles_m * (p->tiles_n + p->tiles_c);
   int units = static_cast<int>(dbg("grid", 0));
   if (units <= 0) units = num_sms / CG;
   const int num_kb = (K + kBK - 1) / kBK;
-  p->sk_tiles = 0;
   const int n_chk_tiles = p->tiles_c * p->tiles_m;
-  if (dbg("streamk", 1) != 0 && num_tiles % units != 0) {
-    // head = the remainder wave plus one full wave (1-2 tiles of k-blocks per unit keeps every tile's partial sums to a
-    // couple of contributors), at least all checksum tiles, and such that the data-parallel body is whole waves
-    int base = units < num_tiles ? units : num_tiles;
-    if (n_chk_tiles > base) base = n_chk_tiles;
-    p->sk_tiles = num_tiles - (num_tiles - base) / units * units;
-    if (static_cast<long long>(p->sk_tiles) * num_kb < units) p->sk_tiles = 0;  // nothing to balance
+  p->sk_tiles = 0;
+  p->sk_slices = 1;
+  const long long force = dbg("splitk", -2);  // -2 auto, 0 off, s>0: force s slices on the auto-chosen head
+  if (force != 0) {
+    const double slice_overhead = 0.05;  // tile-times per split item (dump or fold-in of a 128 x BN fp32 slab)
+    auto makespan = [&](int skt, int sl) {
+      // items are dealt round-robin; unit u gets head items u, u+P, ... and then body tiles
+      const long long head = static_cast<long long>(skt) * sl;
+      double worst = 0.0;
+      for (int u = 0; u < units; ++u) {
+        const long long n_head = head > u ? (head - u + units - 1) / units : 0;
+        const long long first_body = u + n_head * units;  // first item index >= head owned by u
+        const long long total_items = head + (num_tiles - skt);
+        const long long n_body = total_items > first_body ? (total_items - first_body + units - 1) / units : 0;
+        const double t = n_head * (1.0 / sl + (sl > 1 ? slice_overhead : 0.0)) + n_body;
+        if (t > worst) worst = t;
+      }
+      return worst;
+    };
+    double best = makespan(0, 1);
+    const int rem = num_tiles % units;
+    int cands[3] = {num_tiles < units ? num_tiles : rem, rem + units, num_tiles < 2 * units ? num_tiles : 0};
+    for (int ci = 0; ci < 3; ++ci) {
+      int skt = cands[ci];
+      if (skt <= 0 || skt > num_tiles) continue;
+      if (skt < n_chk_tiles) continue;  // checksum tiles are the first tiles: keep them inside or outside as a block
+      for (int sl = 2; sl <= 8; ++sl) {
+        if (num_kb / sl < 4) break;  // keep slices at least 4 k-blocks long
+        if (force > 0 && sl != force) continue;
+        const size_t ws = static_cast<size_t>(skt) * (sl - 1) * CG * kBM * BN * sizeof(float);
+        if (ws > (static_cast<size_t>(256) << 20)) break;
+        if (static_cast<size_t>(skt) * (sl - 1) * CG * 4 * sizeof(int) > 65536) break;
+        const double t = makespan(skt, sl);
+        if (t < best * 0.97 || (force > 0 && p->sk_tiles == 0)) {  // must buy at least 3 %
+          best = t;
+          p->sk_tiles = skt;
+          p->sk_slices = sl;
+        }
+      }
+    }
   }
   if (p->sk_tiles == 0 && units > num_tiles) units = num_tiles;
+  if (p->sk_tiles > 0 && units > p->sk_tiles * p->sk_slices + (num_tiles - p->sk_tiles))
+    units = p->sk_tiles * p->sk_slices + (num_tiles - p->sk_tiles);
   return units;
 }
 
@@ -327,10 +363,10 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     if (rc) return rc;
   }
   // ---- work decomposition: stream-K head + data-parallel body (SegIter in ftsgemm_kernel.cuh)
-  int units = plan_schedule(h->num_sms, CG, K, &p);
+  int units = plan_schedule(h->num_sms, CG, BN, K, &p);
   if (p.sk_tiles > 0) {
-    const size_t flag_bytes = 4096;  // fixed location at the start of the buffer: (units * CG * 4) ints <= 2368 bytes
-    const size_t ws_floats = static_cast<size_t>(units) * CG * kBM * BN;
+    const size_t flag_bytes = 65536;  // fixed location at the start of the buffer
+    const size_t ws_floats = static_cast<size_t>(p.sk_tiles) * (p.sk_slices - 1) * CG * kBM * BN;
     const float *before = h->d_sk;
     rc = ensure_buf(h, &h->d_sk, &h->sk_bytes, flag_bytes + ws_floats * sizeof(float));
     if (rc) return rc;
@@ -442,20 +478,20 @@ int ftsgemm_kernel_lookup(int kernel_id, ftsgemm_kernel_info *out) {
 }
 
 // Enumerate the work decomposition of one launch on the HOST (same inline code the device runs): for every work unit,
-// in processing order, rows of 8 ints {unit, tile, is_chk, m_blk, n_blk, kb_begin, kb_end, kind}.  Returns the number
-// of rows (fills min(cap, rows)); hdr[0..5] = {units, num_tiles, n_chk_tiles, sk_tiles, num_kb, cta_group}.
+// in processing order, rows of 9 ints {unit, tile, is_chk, m_blk, n_blk, kb_begin, kb_end, kind, slice}.  Returns the
+// number of rows (fills min(cap, rows)); hdr[0..6] = {units, num_tiles, n_chk_tiles, sk_tiles, num_kb, cta_group, sk_slices}.
 int ftsgemm_debug_schedule(int kernel_id, int M, int N, int K, int num_sms, int *hdr, int *rows, int cap) {
   const Variant *v = find_variant(kernel_id);
   if (!v || v->info.engine != 1 || M <= 0 || N <= 0 || K <= 0 || num_sms <= 0) return FTSGEMM_ERR_INVALID_ARG;
   KernelParams p;
   memset(&p, 0, sizeof(p));
   plan_tiles(M, N, v->bn, v->cg, v->info.fault_tolerant != 0, &p);
-  const int units = plan_schedule(num_sms, v->cg, K, &p);
+  const int units = plan_schedule(num_sms, v->cg, v->bn, K, &p);
   const int num_tiles = p.tiles_m * (p.tiles_n + p.tiles_c);
   const int num_kb = (K + kBK - 1) / kBK;
   if (hdr) {
     hdr[0] = units; hdr[1] = num_tiles; hdr[2] = p.tiles_c * p.tiles_m; hdr[3] = p.sk_tiles; hdr[4] = num_kb;
-    hdr[5] = v->cg;
+    hdr[5] = v->cg; hdr[6] = p.sk_slices;
   }
   int n = 0;
   for (int u = 0; u < units; ++u) {
@@ -464,9 +500,9 @@ int ftsgemm_debug_schedule(int kernel_id, int M, int N, int K, int num_sms, int 
     while (it.next(sg)) {
       if (rows && n < cap) {
         const TileCoord tc = decode_tile(p, sg.tile);
-        int *r = rows + 8 * n;
+        int *r = rows + 9 * n;
         r[0] = u; r[1] = sg.tile; r[2] = tc.is_chk ? 1 : 0; r[3] = tc.m_blk; r[4] = tc.n_blk;
-        r[5] = sg.kb_begin; r[6] = sg.kb_end; r[7] = sg.kind;
+        r[5] = sg.kb_begin; r[6] = sg.kb_end; r[7] = sg.kind; r[8] = sg.slice;
       }
       ++n;
     }

@@ -78,11 +78,12 @@ struct KernelParams {
   // operand stage (rows % 32 == 0); otherwise the map is 2-D {rows, K} and a stage takes one instruction per 32-row atom
   int tma3d;
   int dbg_flags;        // experiments only: bit 0 = skip the epilogue ABFT check of data tiles
-  // stream-K head: the first sk_tiles tiles (in decode order) are cut into equal k-block ranges, one per work unit, so
-  // that a tile count that is not a multiple of the unit count does not leave SMs idle in the last wave
-  int sk_tiles;
-  float *sk_ws;         // per unit, per CTA of the group: one raw 128 x BN accumulator tile (column-major, ld = 128)
-  int *sk_flags;        // [(unit*CG + cta_rank)*4 + quadrant] = sk_epoch once that slab of the partial tile is written
+  // split-K head: each of the first sk_tiles tiles (in decode order) is cut into sk_slices equal k-ranges that are
+  // scheduled as separate work items, so that a tile count that is not a multiple of the unit count does not leave
+  // SMs idle in the last wave (and tiny problems still fill the machine)
+  int sk_tiles, sk_slices;
+  float *sk_ws;         // per (slice < sk_slices-1, tile, CTA of the group): one raw 128 x BN accumulator tile
+  int *sk_flags;        // [((slice*sk_tiles + tile)*CG + cta_rank)*4 + quadrant] = sk_epoch once that slab is written
   int sk_epoch;
   // fault tolerance: checksum tile-columns
   int tiles_c;          // number of BN-wide checksum tile-columns (0 when FT is off)
@@ -125,23 +126,19 @@ struct TileCoord {
   bool is_chk;
 };
 
-// Tile order.  Data tiles run in groups of group_n tile-columns, M fastest inside a group, so that one wave of CTAs
-// shares few A row-panels and few B row-panels in L2.  Checksum tile-columns must be finished early, and no work unit
-// may meet a data tile before a checksum tile it owns (its epilogue would wait for itself):
-//   * without a stream-K head they are simply the first tiles;
-//   * with a stream-K head they are the LAST indices of the head, because units walk their head range backwards.
+// Tile order: all checksum tile-columns first (so their results are published before the data tiles that need them
+// reach their epilogue), then the data tiles in groups of group_n tile-columns, M fastest inside a group, so that one
+// wave of CTAs shares few A row-panels and few B row-panels in L2.
 __host__ __device__ __forceinline__ TileCoord decode_tile(const KernelParams &p, int t) {
   TileCoord tc;
   const int n_chk_tiles = p.tiles_c * p.tiles_m;
-  const int chk_first = p.sk_tiles > 0 ? p.sk_tiles - n_chk_tiles : 0;
-  if (t >= chk_first && t < chk_first + n_chk_tiles) {
-    const int c = t - chk_first;
+  if (t < n_chk_tiles) {
     tc.is_chk = true;
-    tc.m_blk = c % p.tiles_m;
-    tc.n_blk = c / p.tiles_m;
+    tc.m_blk = t % p.tiles_m;
+    tc.n_blk = t / p.tiles_m;
     return tc;
   }
-  if (t >= chk_first) t -= n_chk_tiles;
+  t -= n_chk_tiles;
   tc.is_chk = false;
   const int per_group = p.group_n * p.tiles_m;
   const int g = t / per_group;
@@ -165,49 +162,52 @@ __host__ __device__ __forceinline__ int chk_tile_width(const KernelParams &p, in
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Work decomposition.  Every role (producer, MMA issuer, epilogue) walks the same list of segments:
-//   stream-K head  tiles [0, sk_tiles) linearised as (tile, k-block); unit u owns the contiguous k-block range
-//                  [total*u/P, total*(u+1)/P) and walks it BACKWARDS, so the piece that only starts a tile (a
-//                  "contributor": partial sums go to the workspace) is done first and the piece that ends a tile (the
-//                  "finisher": adds the contributors' partial sums, then runs the normal epilogue) is done last --
-//                  finishers therefore only ever wait for work other units did at the start of their range
-//   data-parallel  tiles sk_tiles + u, + P, ... whole tiles
+// Work decomposition.  Every role (producer, MMA issuer, epilogue) of work unit u walks the same list of items
+// u, u + P, u + 2P, ... of the global item sequence
+//   split-K head   item i < sk_tiles*sk_slices  ->  k-slice (i / sk_tiles) of tile (i % sk_tiles).  Slice-major order: at
+//                  any time all units work on the SAME k-range of neighbouring tiles, so A/B panels are still shared
+//                  in L2 (a contiguous stream-K split de-synchronises the k offsets and turned out HBM-bound).
+//                  Slices 0..S-2 are "contributors" (raw partial sums go to the workspace), slice S-1 is the "finisher"
+//                  (adds the contributors' partial sums in TMEM, then runs the normal epilogue).
+//   data-parallel  the remaining tiles, whole.
+// Every wait (finisher -> contributors, ABFT data tile -> checksum tiles) points to an item with a SMALLER index, and each
+// unit handles its items in increasing index, so the schedule cannot deadlock (tests/test_schedule.py simulates it).
 // ------------------------------------------------------------------------------------------------------------
 struct Segment {
   int tile, kb_begin, kb_end;
-  int kind;  // 0 whole tile, 1 contributor, 2 finisher
+  int kind;   // 0 whole tile, 1 contributor, 2 finisher
+  int slice;
 };
 
 struct SegIter {
-  long long b, cur;
-  int dp_tile, num_kb, num_tiles, stride;
+  int item, stride, num_kb, num_tiles, sk_tiles, sk_slices;
   __host__ __device__ __forceinline__ SegIter(const KernelParams &p, int unit, int num_units, int num_kb_, int num_tiles_) {
+    item = unit;
+    stride = num_units;
     num_kb = num_kb_;
     num_tiles = num_tiles_;
-    stride = num_units;
-    const long long total = static_cast<long long>(p.sk_tiles) * num_kb;
-    b = total * unit / num_units;
-    cur = total * (unit + 1) / num_units;
-    dp_tile = p.sk_tiles + unit;
+    sk_tiles = p.sk_tiles;
+    sk_slices = p.sk_tiles > 0 ? p.sk_slices : 1;
   }
   __host__ __device__ __forceinline__ bool next(Segment &s) {
-    if (cur > b) {
-      const int tile = static_cast<int>((cur - 1) / num_kb);
-      const long long t0 = static_cast<long long>(tile) * num_kb;
-      const long long sb = b > t0 ? b : t0;
-      s.tile = tile;
-      s.kb_begin = static_cast<int>(sb - t0);
-      s.kb_end = static_cast<int>(cur - t0);
-      s.kind = (s.kb_end == num_kb) ? (s.kb_begin == 0 ? 0 : 2) : 1;
-      cur = sb;
+    const int head = sk_tiles * sk_slices;
+    if (item < head) {
+      s.slice = item / sk_tiles;
+      s.tile = item - s.slice * sk_tiles;
+      s.kb_begin = static_cast<int>(static_cast<long long>(num_kb) * s.slice / sk_slices);
+      s.kb_end = static_cast<int>(static_cast<long long>(num_kb) * (s.slice + 1) / sk_slices);
+      s.kind = (s.slice == sk_slices - 1) ? (sk_slices == 1 ? 0 : 2) : 1;
+      item += stride;
       return true;
     }
-    if (dp_tile < num_tiles) {
-      s.tile = dp_tile;
+    const int t = sk_tiles + (item - head);
+    if (t < num_tiles) {
+      s.tile = t;
+      s.slice = 0;
       s.kb_begin = 0;
       s.kb_end = num_kb;
       s.kind = 0;
-      dp_tile += stride;
+      item += stride;
       return true;
     }
     return false;
@@ -438,7 +438,7 @@ __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Stream-K fix-up (epilogue warps, lane = row).  A contributor dumps its raw accumulator slab; a finisher adds the
+// Split-K fix-up (epilogue warps, lane = row).  A contributor dumps its raw accumulator slab; a finisher adds the
 // slabs of every unit that worked on the earlier k-blocks of its tile back INTO tensor memory, so that the ABFT
 // check and the store pass that follow see the complete sum.
 // ------------------------------------------------------------------------------------------------------------
@@ -681,7 +681,6 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t acc_phase = 0;
     SegIter it(p, unit, num_units, num_kb, num_tiles);
     Segment sg;
-    const long long sk_total = static_cast<long long>(p.sk_tiles) * num_kb;
     const size_t ws_slab = static_cast<size_t>(kBM) * BN;  // floats per (unit, CTA) partial tile
     while (it.next(sg)) {
       const TileCoord tc = decode_tile(p, sg.tile);
@@ -693,18 +692,14 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
       if (sg.kind == 1) {
-        // stream-K contributor: park the raw partial sums of this slab for the unit that finishes the tile
-        const int slot = unit * CG + static_cast<int>(cta_rank);
+        // split-K contributor: park the raw partial sums of this slab for the unit that finishes the tile
+        const int slot = (sg.slice * p.sk_tiles + sg.tile) * CG + static_cast<int>(cta_rank);
         sk_dump_partial<BN>(p, taddr, p.sk_ws + slot * ws_slab + row, p.sk_flags + slot * 4 + q, lane);
       } else if (sg.kind == 2) {
-        // stream-K finisher: fold in every unit that covered the earlier k-blocks of this tile (units u-1, u-2, ...)
-        const long long t0 = static_cast<long long>(sg.tile) * num_kb;
-        for (int v = unit - 1; v >= 0; --v) {
-          const long long vb = sk_total * v / num_units, ve = sk_total * (v + 1) / num_units;
-          if (ve <= t0) break;
-          const int slot = v * CG + static_cast<int>(cta_rank);
+        // split-K finisher: fold in the earlier k-slices of this tile
+        for (int sl = 0; sl < p.sk_slices - 1; ++sl) {
+          const int slot = (sl * p.sk_tiles + sg.tile) * CG + static_cast<int>(cta_rank);
           sk_add_partial<BN>(p, taddr, p.sk_ws + slot * ws_slab + row, p.sk_flags + slot * 4 + q, lane);
-          if (vb <= t0) break;
         }
       }
       if (sg.kind == 1) {

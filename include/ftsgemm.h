@@ -166,9 +166,9 @@ int ftsgemm_verify(ftsgemm_handle_t h, const float *d_ref, const float *d_x, int
 
 /* ---- internal / experiments (not part of the drop-in surface) ---------------------------------------------- */
 int ftsgemm_debug_set(const char *key, long long value);
-/* Host-side enumeration of the work decomposition of one launch (stream-K head + data-parallel body), for tests:
- * rows of 8 ints {unit, tile, is_chk, m_blk, n_blk, kb_begin, kb_end, kind(0 whole,1 contributor,2 finisher)};
- * hdr = {units, num_tiles, n_chk_tiles, sk_tiles, num_kb, cta_group}.  Needs no GPU. */
+/* Host-side enumeration of the work decomposition of one launch (split-K head + data-parallel body), for tests:
+ * rows of 9 ints {unit, tile, is_chk, m_blk, n_blk, kb_begin, kb_end, kind(0 whole,1 contributor,2 finisher), slice};
+ * hdr[7] = {units, num_tiles, n_chk_tiles, sk_tiles, num_kb, cta_group, sk_slices}.  Needs no GPU. */
 int ftsgemm_debug_schedule(int kernel_id, int M, int N, int K, int num_sms, int *hdr, int *rows, int cap);
 
 #ifdef __cplusplus

@@ -17,7 +17,7 @@ def main():
     for n in (1024, 2048, 3072, 4096, 6144, 8192):
         reps = 10 if n <= 4096 else 4
         run_case({"kind": "timing", "M": n, "N": n, "K": n, "ids": [7, 6, 5, 21, 16, 15, 31], "reps": reps, "tag": "sk"}, timeout=600)
-        run_case({"kind": "timing", "M": n, "N": n, "K": n, "ids": [5, 21, 31], "reps": reps, "dbg": {"streamk": 0}, "tag": "no-sk"}, timeout=600)
+        run_case({"kind": "timing", "M": n, "N": n, "K": n, "ids": [5, 21, 31], "reps": reps, "dbg": {"splitk": 0}, "tag": "no-sk"}, timeout=600)
     for n in (4096, 8192):
         run_case({"kind": "timing", "M": n, "N": n, "K": n, "ids": [31], "reps": 10 if n <= 4096 else 4, "reuse": 1, "tag": "reuse-encode"}, timeout=600)
 

@@ -78,14 +78,47 @@ def test_reference_inputs_vs_golden_and_oracle(cuda, ft, dev, oracle, n, name):
 
 
 def test_ft_equals_plain_bitwise_when_fault_free(cuda, ft, dev):
+    """With the same K decomposition (split-K head off) the ABFT kernel must not perturb a single bit of a fault-free
+    product; with the head on, FT and plain may slice K differently, so they agree to FP32 accumulation order only."""
     rng = np.random.default_rng(3)
     M, N, K = 512, 768, 640
     A, B = _rand(rng, M * K), _rand(rng, N * K)
     C0 = np.zeros(M * N, np.float32)
-    for name in ("medium", "huge", "wide"):
+    try:
+        ft.debug_set("splitk", 0)
+        for name in ("medium", "huge", "wide", "giant"):
+            a = _run(cuda, dev, ft.SGEMM_IDS[name], M, N, K, A, B, C0)
+            b = _run(cuda, dev, ft.ABFT_IDS[name], M, N, K, A, B, C0)
+            assert np.array_equal(a, b), name
+    finally:
+        ft.debug_set("splitk", -1)
+    for name in ("huge", "giant"):
         a = _run(cuda, dev, ft.SGEMM_IDS[name], M, N, K, A, B, C0)
         b = _run(cuda, dev, ft.ABFT_IDS[name], M, N, K, A, B, C0)
-        assert np.array_equal(a, b), name
+        assert np.abs(a - b).max() < 1e-4 * np.abs(a).max()
+
+
+@pytest.mark.parametrize("slices", [2, 3, 5])
+def test_split_k_head_forced(cuda, ft, dev, oracle, slices):
+    """Force the split-K head (contributor dump + finisher fold-in through TMEM) on shapes where the planner would not
+    pick it, with and without ABFT + injected faults."""
+    rng = np.random.default_rng(slices)
+    M, N, K = 768, 1024, 1600
+    A, B = _rand(rng, M * K), _rand(rng, N * K)
+    C0 = rng.standard_normal(M * N).astype(np.float32)
+    model = oracle.sgemm_nt_tf32_model(M, N, K, 1.0, A, B, -1.5, C0, "trunc")
+    try:
+        ft.debug_set("splitk", slices)
+        for kid in (6, 21, 16, 31):
+            got = _run(cuda, dev, kid, M, N, K, A, B, C0, 1.0, -1.5)
+            assert oracle.error_metrics(model, got)["rel_fro"] < TOL_MODEL, kid
+        dev.stats()
+        got = _run(cuda, dev, 31, M, N, K, A, B, C0, 1.0, -1.5, opts=ft.make_opts(selftest=(10000.0, 17, 5)))
+        st = dev.stats()
+        assert st["detected"] == st["corrected"] == st["tiles"] == 3 * 4
+        assert oracle.error_metrics(model, got)["rel_fro"] < TOL_MODEL
+    finally:
+        ft.debug_set("splitk", -1)
 
 
 @pytest.mark.parametrize("shape", [(128, 128, 8), (128, 32, 40), (200, 136, 100), (260, 388, 72), (1024, 256, 2048),

@@ -88,22 +88,20 @@ def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms):
         if fin["kind"] == 0:
             assert not contributors
         else:
-            # the kernel's lookup rule (epilogue, kind == 2)
-            visited, t0, u = [], t * num_kb, fin["unit"]
-            for v in range(u - 1, -1, -1):
-                vb, ve = total * v // units, total * (v + 1) // units
-                if ve <= t0:
-                    break
-                visited.append(v)
-                if vb <= t0:
-                    break
-            assert sorted(visited) == contributors and contributors
-    # at most one contributor segment per unit (one workspace slot per unit)
-    per_unit_contrib = {}
-    for s in segs:
-        if s["kind"] == 1:
-            per_unit_contrib[s["unit"]] = per_unit_contrib.get(s["unit"], 0) + 1
-    assert all(v == 1 for v in per_unit_contrib.values())
+            # slice-major head: the finisher is the last of sk_slices equal slices, all earlier slices contribute
+            assert len(contributors) == hdr["sk_slices"] - 1 and t < sk
+            assert sorted(p[3] for p in pieces) == [1] * (hdr["sk_slices"] - 1) + [2]
+    # every wait points to a smaller item index: items are dealt round-robin, so item index = unit + P * position
+    pos = {}
+    index = {}
+    for s_ in segs:
+        k = pos.get(s_["unit"], 0)
+        pos[s_["unit"]] = k + 1
+        index[(s_["tile"], s_["slice"])] = s_["unit"] + units * k
+    for s_ in segs:
+        me = index[(s_["tile"], s_["slice"])]
+        if s_["kind"] == 2:
+            assert all(index[(s_["tile"], sl)] < me for sl in range(hdr["sk_slices"] - 1))
     # checksum tiles: n_chk_tiles of them, 8 columns per N-tile
     chk = {(s["m_blk"], s["n_blk"]) for s in segs if s["is_chk"]}
     assert len(chk) == hdr["n_chk_tiles"]
@@ -115,14 +113,16 @@ def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms):
 
 
 def test_balanced_head(ft):
-    """The stream-K head gives every unit the same number of k-blocks (+-1) and whole waves afterwards."""
-    hdr, segs = ft.debug_schedule(21, 4096, 4096, 4096, 148)
-    assert hdr["units"] == 74 and hdr["num_tiles"] == 256 and hdr["sk_tiles"] == 108  # 256 = 108 + 2 * 74
-    work = [0] * hdr["units"]
-    for s in segs:
-        work[s["unit"]] += s["kb_end"] - s["kb_begin"]
-    assert max(work) - min(work) <= 1
-    hdr, segs = ft.debug_schedule(21, 8192, 8192, 8192, 148)
-    assert hdr["num_tiles"] == 1024 and (hdr["num_tiles"] - hdr["sk_tiles"]) % 74 == 0
-    hdr, segs = ft.debug_schedule(21, 2048, 2048, 2048, 148)  # fewer tiles than units: everything is split
-    assert hdr["sk_tiles"] == hdr["num_tiles"] == 64
+    """The split-K head removes the wave-quantisation loss where it matters."""
+    def makespan(kid, n):
+        hdr, segs = ft.debug_schedule(kid, n, n, n, 148)
+        work = [0.0] * hdr["units"]
+        for s in segs:
+            work[s["unit"]] += (s["kb_end"] - s["kb_begin"]) / hdr["num_kb"]
+        return hdr, max(work)
+    hdr, t = makespan(21, 4096)   # 256 tiles on 74 pairs: 3.46 waves -> the 34-tile remainder is split in two
+    assert (hdr["sk_tiles"], hdr["sk_slices"]) == (34, 2) and abs(t - 3.5) < 1e-9
+    hdr, t = makespan(21, 1024)   # 16 tiles: split-K by 4 fills 64 pairs
+    assert hdr["sk_slices"] == 4 and abs(t - 0.25) < 1e-9
+    hdr, t = makespan(21, 8192)   # 13.84 waves: not worth splitting
+    assert hdr["sk_tiles"] == 0 and t == 14.0
