@@ -205,7 +205,9 @@ int plan_schedule(int num_sms, int CG, int BN, int K, KernelParams *p) {
   p->sk_slices = 1;
   const long long force = dbg("splitk", -2);  // -2 auto, 0 off, s>0: force s slices on the auto-chosen head
   if (force != 0) {
-    const double slice_overhead = 0.05;  // tile-times per split item (dump or fold-in of a 128 x BN fp32 slab)
+    // measured on B200: a split item costs ~10 us extra (partial-sum round trip through L2, latency-bound), i.e.
+    // ~15k SM cycles, whatever K is; expressed in tile-times (one k-block = 4 UMMAs of ~128 cycles)
+    const double slice_overhead = 15000.0 / (static_cast<double>(num_kb) * 512.0);
     auto makespan = [&](int skt, int sl) {
       // items are dealt round-robin; unit u gets head items u, u+P, ... and then body tiles
       const long long head = static_cast<long long>(skt) * sl;

@@ -750,7 +750,8 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 //   chk[k][t*8 + 0..2] = 3-way TF32 split of  e = sum_{n in block t} tf32(B[n,k])
 //   chk[k][t*8 + 3..5] = 3-way TF32 split of  w = sum_{n in block t} (n - n0 + 1) * tf32(B[n,k])
 //   chk[k][t*8 + 6..7] = 0
-// Sums are accumulated in FP64, so the three TF32 terms carry the checksum to ~2^-33 relative.
+// Sums are accumulated as FP32 hi+lo pairs (error-free transformations), so the three TF32 terms carry the checksum
+// to ~2^-33 relative.
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float tf32_bits(float x, int rounding) {
   uint32_t u = __float_as_uint(x);
@@ -758,20 +759,43 @@ __device__ __forceinline__ float tf32_bits(float x, int rounding) {
   if (rounding != 2) u &= 0xFFFFE000u;
   return __uint_as_float(u);
 }
-__device__ __forceinline__ void split3_tf32(double x, float &h, float &m, float &l) {
-  h = tf32_bits(static_cast<float>(x), 0);
-  double r = x - static_cast<double>(h);
-  m = tf32_bits(static_cast<float>(r), 0);
-  r -= static_cast<double>(m);
-  l = tf32_bits(static_cast<float>(r), 0);
+// Double-float (hi + lo) arithmetic: the B200's FP64 pipe is far too slow for an HBM-speed pass (measured: the FP64
+// version of this kernel ran at 2.2 TB/s), so checksums are accumulated as unevaluated FP32 pairs with error-free
+// transformations (Knuth two-sum); relative error ~2^-45, far below the TF32 split that follows.
+struct ff {
+  float hi, lo;
+};
+__device__ __forceinline__ ff ff_add(ff a, float b) {  // a + b, b exact
+  const float s = a.hi + b;
+  const float bb = s - a.hi;
+  const float err = (a.hi - (s - bb)) + (b - bb);
+  ff r;
+  r.hi = s;
+  r.lo = a.lo + err;
+  return r;
+}
+__device__ __forceinline__ ff ff_add(ff a, ff b) {
+  ff r = ff_add(a, b.hi);
+  r.lo += b.lo;
+  const float s = r.hi + r.lo;  // renormalise
+  r.lo = r.lo - (s - r.hi);
+  r.hi = s;
+  return r;
+}
+__device__ __forceinline__ void split3_tf32(ff x, float &h, float &m, float &l) {
+  h = tf32_bits(x.hi, 0);
+  float r = (x.hi - h) + x.lo;  // x.hi - h is exact (h is x.hi with low bits cleared)
+  m = tf32_bits(r, 0);
+  r -= m;
+  l = tf32_bits(r, 0);
 }
 
 constexpr int kEncWarps = 8;
 constexpr int kEncKPerWarp = 8;
 
-// grid = (tiles_n, ceil(K / 32)), 8 warps x 4 k-rows each.  Every lane keeps kEncKPerWarp x (BN/128) 16-byte loads
-// in flight (B is N-contiguous), so the pass runs at HBM speed; it also clears the checksum slab flags of the GEMM
-// launch that follows it in the stream (one memset launch less).
+// grid = (tiles_n, ceil(K / 64)), 8 warps x 8 k-rows each.  Every lane keeps kEncKPerWarp 16-byte loads in flight
+// (B is N-contiguous), so the pass runs at HBM speed; it also clears the checksum slab flags of the GEMM launch that
+// follows it in the stream (one memset launch less).  (j+1)*b is exact in FP32: 9-bit weight x 11-bit TF32 significand.
 __global__ void __launch_bounds__(kEncWarps * 32)
 encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, float *__restrict__ chk, int chk_ld,
                 int rounding, int *__restrict__ flags, int n_flags) {
@@ -781,9 +805,9 @@ encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, floa
   const int n0 = t * BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kbase = (blockIdx.y * kEncWarps + warp) * kEncKPerWarp;
-  double e[kEncKPerWarp], w[kEncKPerWarp];
+  ff e[kEncKPerWarp], w[kEncKPerWarp];
 #pragma unroll
-  for (int u = 0; u < kEncKPerWarp; ++u) e[u] = w[u] = 0.0;
+  for (int u = 0; u < kEncKPerWarp; ++u) e[u].hi = e[u].lo = w[u].hi = w[u].lo = 0.0f;
   const bool vec_ok = (n0 + BN <= N);  // full tile: 16-byte loads (ldb % 4 == 0 and n0 % 4 == 0 by construction)
   if (vec_ok) {
     for (int j4 = lane; j4 < BN / 4; j4 += 32) {
@@ -794,13 +818,13 @@ encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, floa
         v[u] = (k < K) ? __ldg(reinterpret_cast<const float4 *>(B + static_cast<size_t>(k) * ldb + n0) + j4)
                        : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const double wj = static_cast<double>(4 * j4 + 1);
+      const float wj = static_cast<float>(4 * j4 + 1);
 #pragma unroll
       for (int u = 0; u < kEncKPerWarp; ++u) {
-        const double b0 = tf32_bits(v[u].x, rounding), b1 = tf32_bits(v[u].y, rounding),
-                     b2 = tf32_bits(v[u].z, rounding), b3 = tf32_bits(v[u].w, rounding);
-        e[u] += (b0 + b1) + (b2 + b3);
-        w[u] += b0 * wj + b1 * (wj + 1.0) + b2 * (wj + 2.0) + b3 * (wj + 3.0);
+        const float b0 = tf32_bits(v[u].x, rounding), b1 = tf32_bits(v[u].y, rounding),
+                    b2 = tf32_bits(v[u].z, rounding), b3 = tf32_bits(v[u].w, rounding);
+        e[u] = ff_add(ff_add(ff_add(ff_add(e[u], b0), b1), b2), b3);
+        w[u] = ff_add(ff_add(ff_add(ff_add(w[u], b0 * wj), b1 * (wj + 1.0f)), b2 * (wj + 2.0f)), b3 * (wj + 3.0f));
       }
     }
   } else {
@@ -811,9 +835,9 @@ encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, floa
         for (int u = 0; u < kEncKPerWarp; ++u) {
           const int k = kbase + u;
           if (k < K) {
-            const double b = tf32_bits(__ldg(B + static_cast<size_t>(k) * ldb + n), rounding);
-            e[u] += b;
-            w[u] += b * static_cast<double>(j + 1);
+            const float b = tf32_bits(__ldg(B + static_cast<size_t>(k) * ldb + n), rounding);
+            e[u] = ff_add(e[u], b);
+            w[u] = ff_add(w[u], b * static_cast<float>(j + 1));
           }
         }
       }
@@ -823,8 +847,13 @@ encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, floa
   for (int u = 0; u < kEncKPerWarp; ++u) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      e[u] += __shfl_xor_sync(0xffffffffu, e[u], o);
-      w[u] += __shfl_xor_sync(0xffffffffu, w[u], o);
+      ff oe, ow;
+      oe.hi = __shfl_xor_sync(0xffffffffu, e[u].hi, o);
+      oe.lo = __shfl_xor_sync(0xffffffffu, e[u].lo, o);
+      ow.hi = __shfl_xor_sync(0xffffffffu, w[u].hi, o);
+      ow.lo = __shfl_xor_sync(0xffffffffu, w[u].lo, o);
+      e[u] = ff_add(e[u], oe);
+      w[u] = ff_add(w[u], ow);
     }
     const int k = kbase + u;
     if (k < K && lane < kChkPerTile) {  // every lane holds the totals; lane i writes column i of the 8-float block

@@ -115,7 +115,7 @@ def test_split_k_head_forced(cuda, ft, dev, oracle, slices):
         dev.stats()
         got = _run(cuda, dev, 31, M, N, K, A, B, C0, 1.0, -1.5, opts=ft.make_opts(selftest=(10000.0, 17, 5)))
         st = dev.stats()
-        assert st["detected"] == st["corrected"] == st["tiles"] == 3 * 4
+        assert st["detected"] == st["corrected"] == st["tiles"] == 6 * 4  # one upset per 128-row CTA tile
         assert oracle.error_metrics(model, got)["rel_fro"] < TOL_MODEL
     finally:
         ft.debug_set("splitk", -1)
