@@ -348,9 +348,16 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     p.chk_flags = reinterpret_cast<int *>(h->d_chk_out + out_floats);
     const bool reuse = o.reuse_b_checksums && h->chk_for_b == dB && h->chk_n == N && h->chk_k == K && h->chk_bn == BN;
     if (!reuse) {
-      dim3 grid(p.tiles_n, (K + kEncWarps * kEncKPerWarp - 1) / (kEncWarps * kEncKPerWarp));
-      encode_b_kernel<<<grid, kEncWarps * 32, 0, stream>>>(dB, N, K, N, BN, h->d_chk, chk_ld,
-                                                           static_cast<int>(dbg("enc_rounding", 0)), p.chk_flags, n_slabs);
+      const int J = BN >= 128 ? BN / 128 : 0;  // float4 loads per lane and k-row (0: narrow tile, scalar path)
+      const int kw = kEncLoads / (J > 0 ? J : 1);
+      dim3 grid(p.tiles_n, (K + kEncWarps * kw - 1) / (kEncWarps * kw));
+      const int rounding = static_cast<int>(dbg("enc_rounding", 0));
+      if (J == 2)
+        encode_b_kernel<2><<<grid, kEncWarps * 32, 0, stream>>>(dB, N, K, N, BN, h->d_chk, chk_ld, rounding, p.chk_flags, n_slabs);
+      else if (J == 1)
+        encode_b_kernel<1><<<grid, kEncWarps * 32, 0, stream>>>(dB, N, K, N, BN, h->d_chk, chk_ld, rounding, p.chk_flags, n_slabs);
+      else
+        encode_b_kernel<0><<<grid, kEncWarps * 32, 0, stream>>>(dB, N, K, N, BN, h->d_chk, chk_ld, rounding, p.chk_flags, n_slabs);
       FT_CUDA(h, cudaGetLastError());
       h->chk_for_b = dB; h->chk_n = N; h->chk_k = K; h->chk_bn = BN;
     } else {

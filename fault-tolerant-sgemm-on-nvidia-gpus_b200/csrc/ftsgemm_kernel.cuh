@@ -545,8 +545,9 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     // ===================================================================== TMA producer (every CTA)
+    // warp-uniform loop, one elected lane issues the TMA instructions (see ptx::elect_one)
     int stage = 0;
     uint32_t phase = 0;
     SegIter it(p, unit, num_units, num_kb, num_tiles);
@@ -568,17 +569,20 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t sA = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sB = sA + Cfg::kABytes;
           const int k0 = kb * kBK;
-          if (CG == 2) {
-            const uint32_t bar = ptx::mapa(full_bar(stage), 0);  // the leader's barrier collects both CTAs' bytes
-            if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-            else ptx::mbar_arrive_cluster(bar);
-            ptx::tma_load_3d_cg2(sA, &tmA, bar, 0, k0, a_atom);
-            ptx::tma_load_3d_cg2(sB, tmb, bar, 0, k0, b_atom);
-          } else {
-            ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-            ptx::tma_load_3d(sA, &tmA, full_bar(stage), 0, k0, a_atom);
-            ptx::tma_load_3d(sB, tmb, full_bar(stage), 0, k0, b_atom);
+          if (ptx::elect_one()) {
+            if (CG == 2) {
+              const uint32_t bar = ptx::mapa(full_bar(stage), 0);  // the leader's barrier collects both CTAs' bytes
+              if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+              else ptx::mbar_arrive_cluster(bar);
+              ptx::tma_load_3d_cg2(sA, &tmA, bar, 0, k0, a_atom);
+              ptx::tma_load_3d_cg2(sB, tmb, bar, 0, k0, b_atom);
+            } else {
+              ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+              ptx::tma_load_3d(sA, &tmA, full_bar(stage), 0, k0, a_atom);
+              ptx::tma_load_3d(sB, tmb, full_bar(stage), 0, k0, b_atom);
+            }
           }
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
@@ -591,6 +595,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t sB = sA + Cfg::kABytes;
           const int k0 = kb * kBK;
           const uint32_t bar = (CG == 2) ? ptx::mapa(full_bar(stage), 0) : full_bar(stage);
+          if (ptx::elect_one()) {
           if (CG == 2) {
             if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
             else ptx::mbar_arrive_cluster(bar);
@@ -617,6 +622,8 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               else ptx::tma_load_2d(sB + i * (kBK * 128), tmb, bar, nb0 + i * kAtomMN, k0);
             }
           }
+          }
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
@@ -624,9 +631,14 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && is_leader) {
+  } else if (warp == 1 && is_leader) {
     // ===================================================================== MMA issuer (leader CTA only)
+    // The whole warp walks the loop (uniform control flow); one elected lane issues the UMMAs and their commits.
     const uint32_t idesc = ptx::make_idesc_tf32(kBM * CG, BN, 1, 1);
+    const uint64_t desc0 = ptx::make_smem_desc(smem_base, p.lbo_bytes, p.sbo_bytes, p.layout_type);
+    const uint64_t desc_hi = desc0 & 0xFFFFFFFF00000000ull;
+    const uint32_t desc_lo0 = static_cast<uint32_t>(desc0);
+    const uint32_t kstep16 = p.kstep_bytes >> 4;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -642,29 +654,40 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
+      // Lean issue loop: a single thread runs dependent integer chains at ~1 instruction per 4-6 cycles, and four UMMAs
+      // (one k-block) take only ~512 cycles, so the 64-bit descriptors are NOT rebuilt per UMMA: the high word
+      // (SBO, version, layout) and LBO are constant, only the 14-bit start-address field advances (+64 = 1024 B).
+      uint32_t first = 1u;  // the first UMMA of a segment overwrites the accumulator
       for (int kb = sg.kb_begin; kb < sg.kb_end; ++kb) {
         ptx::mbar_wait(full_bar(stage), phase);
         ptx::tc_fence_after();
-        const uint32_t sA = smem_base + stage * Cfg::kStageBytes;
-        const uint32_t sB = sA + Cfg::kABytes;
+        const uint32_t a_lo = desc_lo0 + static_cast<uint32_t>(stage) * (Cfg::kStageBytes >> 4);
+        const uint32_t b_lo = a_lo + (Cfg::kABytes >> 4);
+        const bool last_kb = (kb + 1 == sg.kb_end);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int j = 0; j < kBK / 8; ++j) {
-          const uint64_t da = ptx::make_smem_desc(sA + j * p.kstep_bytes, p.lbo_bytes, p.sbo_bytes, p.layout_type);
-          const uint64_t db = ptx::make_smem_desc(sB + j * p.kstep_bytes, p.lbo_bytes, p.sbo_bytes, p.layout_type);
-          const uint32_t accum = (kb != sg.kb_begin || j != 0) ? 1u : 0u;
-          if (CG == 2) ptx::mma_tf32_cg2(d_tmem, da, db, idesc_t, accum);
-          else ptx::mma_tf32(d_tmem, da, db, idesc_t, accum);
+          for (int j = 0; j < kBK / 8; ++j) {
+            const uint64_t da = desc_hi | static_cast<uint64_t>(a_lo + j * kstep16);
+            const uint64_t db = desc_hi | static_cast<uint64_t>(b_lo + j * kstep16);
+            const uint32_t accum = (j == 0) ? (first ^ 1u) : 1u;
+            if (CG == 2) ptx::mma_tf32_cg2(d_tmem, da, db, idesc_t, accum);
+            else ptx::mma_tf32(d_tmem, da, db, idesc_t, accum);
+          }
+          // frees the smem slot (in both CTAs) once these MMAs have read it
+          if (CG == 2) ptx::mma_commit_cg2(empty_bar(stage), 0x3);
+          else ptx::mma_commit(empty_bar(stage));
+          if (last_kb) {  // accumulator complete (both CTAs' epilogues)
+            if (CG == 2) ptx::mma_commit_cg2(tfull_bar(acc), 0x3);
+            else ptx::mma_commit(tfull_bar(acc));
+          }
         }
-        // frees the smem slot (in both CTAs) once these MMAs have read it
-        if (CG == 2) ptx::mma_commit_cg2(empty_bar(stage), 0x3);
-        else ptx::mma_commit(empty_bar(stage));
+        __syncwarp();
+        first = 0u;
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      if (CG == 2) ptx::mma_commit_cg2(tfull_bar(acc), 0x3);  // accumulator complete (both CTAs' epilogues)
-      else ptx::mma_commit(tfull_bar(acc));
       if (kAccStages == 2) {
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
@@ -791,38 +814,44 @@ __device__ __forceinline__ void split3_tf32(ff x, float &h, float &m, float &l) 
 }
 
 constexpr int kEncWarps = 8;
-constexpr int kEncKPerWarp = 8;
+constexpr int kEncLoads = 8;  // 16-byte loads in flight per lane
 
-// grid = (tiles_n, ceil(K / 64)), 8 warps x 8 k-rows each.  Every lane keeps kEncKPerWarp 16-byte loads in flight
-// (B is N-contiguous), so the pass runs at HBM speed; it also clears the checksum slab flags of the GEMM launch that
-// follows it in the stream (one memset launch less).  (j+1)*b is exact in FP32: 9-bit weight x 11-bit TF32 significand.
-__global__ void __launch_bounds__(kEncWarps * 32)
+// grid = (tiles_n, ceil(K / (8 warps * KW))), KW = kEncLoads / J k-rows per warp, J = BN/128 float4 per lane and row.
+// All kEncLoads loads of a lane are issued before the first is consumed and the kernel is capped at 64 registers so
+// that 4 blocks (32 warps) are resident per SM: ~128 KB in flight per SM, enough to run at HBM speed (the first two
+// versions were occupancy/latency-bound at ~2 TB/s).  It also clears the checksum slab flags of the GEMM launch that
+// follows it in the stream (one memset launch less).  (j+1)*b is exact in FP32: 9-bit weight x 11-bit significand.
+template <int J>
+__global__ void __launch_bounds__(kEncWarps * 32, 4)
 encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, float *__restrict__ chk, int chk_ld,
                 int rounding, int *__restrict__ flags, int n_flags) {
+  constexpr int KW = kEncLoads / (J > 0 ? J : 1);
   if (flags != nullptr && blockIdx.x == 0 && blockIdx.y == 0)
     for (int i = threadIdx.x; i < n_flags; i += blockDim.x) flags[i] = 0;
   const int t = blockIdx.x;
   const int n0 = t * BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kbase = (blockIdx.y * kEncWarps + warp) * kEncKPerWarp;
-  ff e[kEncKPerWarp], w[kEncKPerWarp];
+  const int kbase = (blockIdx.y * kEncWarps + warp) * KW;
+  ff e[KW], w[KW];
 #pragma unroll
-  for (int u = 0; u < kEncKPerWarp; ++u) e[u].hi = e[u].lo = w[u].hi = w[u].lo = 0.0f;
-  const bool vec_ok = (n0 + BN <= N);  // full tile: 16-byte loads (ldb % 4 == 0 and n0 % 4 == 0 by construction)
-  if (vec_ok) {
-    for (int j4 = lane; j4 < BN / 4; j4 += 32) {
-      float4 v[kEncKPerWarp];
+  for (int u = 0; u < KW; ++u) e[u].hi = e[u].lo = w[u].hi = w[u].lo = 0.0f;
+  if (J > 0 && n0 + BN <= N) {  // full tile of 128*J columns: 16-byte loads (ldb % 4 == 0, n0 % 4 == 0)
+    float4 v[KW][J > 0 ? J : 1];
 #pragma unroll
-      for (int u = 0; u < kEncKPerWarp; ++u) {
-        const int k = kbase + u;
-        v[u] = (k < K) ? __ldg(reinterpret_cast<const float4 *>(B + static_cast<size_t>(k) * ldb + n0) + j4)
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      const float wj = static_cast<float>(4 * j4 + 1);
+    for (int u = 0; u < KW; ++u) {
+      const int k = kbase + u;
 #pragma unroll
-      for (int u = 0; u < kEncKPerWarp; ++u) {
-        const float b0 = tf32_bits(v[u].x, rounding), b1 = tf32_bits(v[u].y, rounding),
-                    b2 = tf32_bits(v[u].z, rounding), b3 = tf32_bits(v[u].w, rounding);
+      for (int jj = 0; jj < J; ++jj)
+        v[u][jj] = (k < K) ? __ldg(reinterpret_cast<const float4 *>(B + static_cast<size_t>(k) * ldb + n0) + lane + 32 * jj)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < KW; ++u) {
+#pragma unroll
+      for (int jj = 0; jj < J; ++jj) {
+        const float wj = static_cast<float>(4 * (lane + 32 * jj) + 1);
+        const float b0 = tf32_bits(v[u][jj].x, rounding), b1 = tf32_bits(v[u][jj].y, rounding),
+                    b2 = tf32_bits(v[u][jj].z, rounding), b3 = tf32_bits(v[u][jj].w, rounding);
         e[u] = ff_add(ff_add(ff_add(ff_add(e[u], b0), b1), b2), b3);
         w[u] = ff_add(ff_add(ff_add(ff_add(w[u], b0 * wj), b1 * (wj + 1.0f)), b2 * (wj + 2.0f)), b3 * (wj + 3.0f));
       }
@@ -832,7 +861,7 @@ encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, floa
       const int n = n0 + j;
       if (n < N) {
 #pragma unroll
-        for (int u = 0; u < kEncKPerWarp; ++u) {
+        for (int u = 0; u < KW; ++u) {
           const int k = kbase + u;
           if (k < K) {
             const float b = tf32_bits(__ldg(B + static_cast<size_t>(k) * ldb + n), rounding);
@@ -844,7 +873,7 @@ encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, floa
     }
   }
 #pragma unroll
-  for (int u = 0; u < kEncKPerWarp; ++u) {
+  for (int u = 0; u < KW; ++u) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       ff oe, ow;
