@@ -12,12 +12,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <array>
 #include <map>
 #include <mutex>
 #include <string>
 
 #include "../../include/ftsgemm.h"
 #include "ftsgemm_kernel.cuh"
+#include "plan.h"
 
 namespace {
 
@@ -95,7 +97,15 @@ struct ftsgemm_handle_s {
   int chk_n = 0, chk_k = 0, chk_bn = 0;
   float *d_aux = nullptr;       // baseline vectors
   size_t aux_floats = 0;
-  float *d_sk = nullptr;        // stream-K partial tiles + flags
+  struct CachedPlan {
+    ftsgemm::Plan plan;
+    std::vector<int4> packed;   // host copy (kept alive for the async upload)
+    int4 *d_items = nullptr;
+    int *d_off = nullptr;
+    bool uploaded = false;
+  };
+  std::map<std::array<long long, 6>, CachedPlan> plans;  // key: kernel id, M, N, K, units, forced slices
+  float *d_sk = nullptr;        // split-K partial tiles + flags
   size_t sk_bytes = 0;
   int sk_epoch = 0;
   float *d_stage[3] = {nullptr, nullptr, nullptr};  // run_host staging A, B, C
@@ -191,63 +201,34 @@ int launch_tc(ftsgemm_handle_t h, const CUtensorMap &tmA, const CUtensorMap &tmB
   return FTSGEMM_OK;
 }
 
-// Work decomposition of one launch; returns the number of persistent work units (CTAs or CTA pairs) and fills
-// sk_tiles / sk_slices of *p (tile grid already set by plan_tiles).  Candidates: no split; split the remainder wave;
-// split the remainder wave plus one full wave; 2..8 slices.  The estimate is the makespan in tile-times of the
-// round-robin item assignment SegIter performs, with a per-slice overhead for the partial-sum round trip.
-int plan_schedule(int num_sms, int CG, int BN, int K, KernelParams *p) {
-  const int num_tiles = p->tiles_m * (p->tiles_n + p->tiles_c);
-  int units = static_cast<int>(dbg("grid", 0));
-  if (units <= 0) units = num_sms / CG;
-  const int num_kb = (K + kBK - 1) / kBK;
-  const int n_chk_tiles = p->tiles_c * p->tiles_m;
-  p->sk_tiles = 0;
-  p->sk_slices = 1;
-  const long long force = dbg("splitk", -2);  // -2 auto, 0 off, s>0: force s slices on the auto-chosen head
-  if (force != 0) {
-    // measured on B200: a split item costs ~10 us extra (partial-sum round trip through L2, latency-bound), i.e.
-    // ~15k SM cycles, whatever K is; expressed in tile-times (one k-block = 4 UMMAs of ~128 cycles)
-    const double slice_overhead = 15000.0 / (static_cast<double>(num_kb) * 512.0);
-    auto makespan = [&](int skt, int sl) {
-      // items are dealt round-robin; unit u gets head items u, u+P, ... and then body tiles
-      const long long head = static_cast<long long>(skt) * sl;
-      double worst = 0.0;
-      for (int u = 0; u < units; ++u) {
-        const long long n_head = head > u ? (head - u + units - 1) / units : 0;
-        const long long first_body = u + n_head * units;  // first item index >= head owned by u
-        const long long total_items = head + (num_tiles - skt);
-        const long long n_body = total_items > first_body ? (total_items - first_body + units - 1) / units : 0;
-        const double t = n_head * (1.0 / sl + (sl > 1 ? slice_overhead : 0.0)) + n_body;
-        if (t > worst) worst = t;
-      }
-      return worst;
-    };
-    double best = makespan(0, 1);
-    const int rem = num_tiles % units;
-    int cands[3] = {num_tiles < units ? num_tiles : rem, rem + units, num_tiles < 2 * units ? num_tiles : 0};
-    for (int ci = 0; ci < 3; ++ci) {
-      int skt = cands[ci];
-      if (skt <= 0 || skt > num_tiles) continue;
-      if (skt < n_chk_tiles) continue;  // checksum tiles are the first tiles: keep them inside or outside as a block
-      for (int sl = 2; sl <= 8; ++sl) {
-        if (num_kb / sl < 4) break;  // keep slices at least 4 k-blocks long
-        if (force > 0 && sl != force) continue;
-        const size_t ws = static_cast<size_t>(skt) * (sl - 1) * CG * kBM * BN * sizeof(float);
-        if (ws > (static_cast<size_t>(256) << 20)) break;
-        if (static_cast<size_t>(skt) * (sl - 1) * CG * 4 * sizeof(int) > 65536) break;
-        const double t = makespan(skt, sl);
-        if (t < best * 0.97 || (force > 0 && p->sk_tiles == 0)) {  // must buy at least 3 %
-          best = t;
-          p->sk_tiles = skt;
-          p->sk_slices = sl;
-        }
-      }
-    }
-  }
-  if (p->sk_tiles == 0 && units > num_tiles) units = num_tiles;
-  if (p->sk_tiles > 0 && units > p->sk_tiles * p->sk_slices + (num_tiles - p->sk_tiles))
-    units = p->sk_tiles * p->sk_slices + (num_tiles - p->sk_tiles);
-  return units;
+// Planner input for one launch (tile grid already set by plan_tiles).
+template <int BNv, int CGv>
+void chk_costs(const KernelParams &p, std::vector<double> *out) {
+  for (int c = 0; c < p.tiles_c; ++c) out->push_back(static_cast<double>(chk_tile_width<BNv, CGv>(p, c)) / BNv);
+}
+
+PlanInput make_plan_input(int num_sms, int CG, int BN, int K, const KernelParams &p) {
+  PlanInput in;
+  long long units = dbg("grid", 0);
+  in.units = units > 0 ? static_cast<int>(units) : num_sms / CG;
+  in.n_chk_tiles = p.tiles_c * p.tiles_m;
+  in.n_data_tiles = p.tiles_m * p.tiles_n;
+  in.num_kb = (K + kBK - 1) / kBK;
+  in.tiles_m = p.tiles_m;
+  if (BN == 32) chk_costs<32, 1>(p, &in.chk_col_cost);
+  else if (BN == 64) chk_costs<64, 1>(p, &in.chk_col_cost);
+  else if (BN == 128 && CG == 1) chk_costs<128, 1>(p, &in.chk_col_cost);
+  else if (BN == 128) chk_costs<128, 2>(p, &in.chk_col_cost);
+  else if (CG == 1) chk_costs<256, 1>(p, &in.chk_col_cost);
+  else chk_costs<256, 2>(p, &in.chk_col_cost);
+  // measured on B200: a split item costs ~10 us extra (partial-sum round trip through L2, latency-bound), i.e.
+  // ~15k SM cycles, whatever K is; expressed in tile-times (one k-block = 4 UMMAs of ~128 cycles)
+  in.slice_overhead = static_cast<double>(dbg("slice_overhead_cycles", 15000)) / (static_cast<double>(in.num_kb) * 512.0);
+  const long long force = dbg("splitk", -2);  // -2 auto, 0 off, s > 1: force s slices
+  in.max_slices = force == 0 ? 1 : 8;
+  in.force_slices = force > 1 ? static_cast<int>(force) : 0;
+  in.slab_bytes = static_cast<size_t>(CG) * kBM * BN * sizeof(float);
+  return in;
 }
 
 void plan_tiles(int M, int N, int BN, int CG, bool ft, KernelParams *p) {
@@ -371,8 +352,36 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     }
     if (rc) return rc;
   }
-  // ---- work decomposition: stream-K head + data-parallel body (SegIter in ftsgemm_kernel.cuh)
-  int units = plan_schedule(h->num_sms, CG, BN, K, &p);
+  // ---- work plan (plan.h), cached per shape on the handle
+  const PlanInput pin = make_plan_input(h->num_sms, CG, BN, K, p);
+  const std::array<long long, 6> key = {v.info.id, M, N, K, pin.units, pin.force_slices * 16 + pin.max_slices};
+  ftsgemm_handle_s::CachedPlan &cp = h->plans[key];
+  if (!cp.uploaded) {
+    if (h->plans.size() > 64) {  // bound the cache: drop everything but this entry
+      for (auto it = h->plans.begin(); it != h->plans.end();) {
+        if (&it->second == &cp) { ++it; continue; }
+        cudaFree(it->second.d_items);
+        cudaFree(it->second.d_off);
+        it = h->plans.erase(it);
+      }
+    }
+    cp.plan = build_plan(pin);
+    cp.packed.resize(cp.plan.items.size());
+    for (size_t i = 0; i < cp.plan.items.size(); ++i) {
+      const PlanItem &it = cp.plan.items[i];
+      cp.packed[i] = make_int4(it.tile, it.kb_begin | (it.kb_end << 16), it.kind | (it.slice << 8), it.split_idx);
+    }
+    FT_CUDA(h, cudaMalloc(&cp.d_items, std::max<size_t>(1, cp.packed.size()) * sizeof(int4)));
+    FT_CUDA(h, cudaMalloc(&cp.d_off, cp.plan.offsets.size() * sizeof(int)));
+    FT_CUDA(h, cudaMemcpyAsync(cp.d_items, cp.packed.data(), cp.packed.size() * sizeof(int4), cudaMemcpyHostToDevice, stream));
+    FT_CUDA(h, cudaMemcpyAsync(cp.d_off, cp.plan.offsets.data(), cp.plan.offsets.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    cp.uploaded = true;
+  }
+  const int units = cp.plan.units;
+  p.plan = cp.d_items;
+  p.plan_off = cp.d_off;
+  p.sk_tiles = cp.plan.sk_tiles;
+  p.sk_slices = cp.plan.sk_slices;
   if (p.sk_tiles > 0) {
     const size_t flag_bytes = 65536;  // fixed location at the start of the buffer
     const size_t ws_floats = static_cast<size_t>(p.sk_tiles) * (p.sk_slices - 1) * CG * kBM * BN;
@@ -495,23 +504,21 @@ int ftsgemm_debug_schedule(int kernel_id, int M, int N, int K, int num_sms, int 
   KernelParams p;
   memset(&p, 0, sizeof(p));
   plan_tiles(M, N, v->bn, v->cg, v->info.fault_tolerant != 0, &p);
-  const int units = plan_schedule(num_sms, v->cg, v->bn, K, &p);
-  const int num_tiles = p.tiles_m * (p.tiles_n + p.tiles_c);
-  const int num_kb = (K + kBK - 1) / kBK;
+  const PlanInput pin = make_plan_input(num_sms, v->cg, v->bn, K, p);
+  const Plan plan = build_plan(pin);
   if (hdr) {
-    hdr[0] = units; hdr[1] = num_tiles; hdr[2] = p.tiles_c * p.tiles_m; hdr[3] = p.sk_tiles; hdr[4] = num_kb;
-    hdr[5] = v->cg; hdr[6] = p.sk_slices;
+    hdr[0] = plan.units; hdr[1] = pin.n_chk_tiles + pin.n_data_tiles; hdr[2] = pin.n_chk_tiles; hdr[3] = plan.sk_tiles;
+    hdr[4] = pin.num_kb; hdr[5] = v->cg; hdr[6] = plan.sk_slices;
   }
   int n = 0;
-  for (int u = 0; u < units; ++u) {
-    SegIter it(p, u, units, num_kb, num_tiles);
-    Segment sg;
-    while (it.next(sg)) {
+  for (int u = 0; u < plan.units; ++u) {
+    for (int i = plan.offsets[u]; i < plan.offsets[u + 1]; ++i) {
+      const PlanItem &it = plan.items[i];
       if (rows && n < cap) {
-        const TileCoord tc = decode_tile(p, sg.tile);
+        const TileCoord tc = decode_tile(p, it.tile);
         int *r = rows + 9 * n;
-        r[0] = u; r[1] = sg.tile; r[2] = tc.is_chk ? 1 : 0; r[3] = tc.m_blk; r[4] = tc.n_blk;
-        r[5] = sg.kb_begin; r[6] = sg.kb_end; r[7] = sg.kind; r[8] = sg.slice;
+        r[0] = u; r[1] = it.tile; r[2] = tc.is_chk ? 1 : 0; r[3] = tc.m_blk; r[4] = tc.n_blk;
+        r[5] = it.kb_begin; r[6] = it.kb_end; r[7] = it.kind; r[8] = it.slice;
       }
       ++n;
     }
@@ -569,6 +576,10 @@ int ftsgemm_destroy(ftsgemm_handle_t h) {
   cudaFree(h->d_chk);
   cudaFree(h->d_chk_out);
   cudaFree(h->d_sk);
+  for (auto &kv : h->plans) {
+    cudaFree(kv.second.d_items);
+    cudaFree(kv.second.d_off);
+  }
   cudaFree(h->d_aux);
   cudaFree(h->d_verify);
   for (int i = 0; i < 3; ++i) cudaFree(h->d_stage[i]);

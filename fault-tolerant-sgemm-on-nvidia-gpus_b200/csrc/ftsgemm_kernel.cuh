@@ -78,12 +78,16 @@ struct KernelParams {
   // operand stage (rows % 32 == 0); otherwise the map is 2-D {rows, K} and a stage takes one instruction per 32-row atom
   int tma3d;
   int dbg_flags;        // experiments only: bit 0 = skip the epilogue ABFT check of data tiles
-  // split-K head: each of the first sk_tiles tiles (in decode order) is cut into sk_slices equal k-ranges that are
-  // scheduled as separate work items, so that a tile count that is not a multiple of the unit count does not leave
-  // SMs idle in the last wave (and tiny problems still fill the machine)
+  // Work plan (built on the host, plan.h): unit u executes items plan[plan_off[u] .. plan_off[u+1]) in order.
+  //   item.x = tile (decode order: checksum tiles first), item.y = kb_begin | kb_end << 16,
+  //   item.z = kind (0 whole tile, 1 split-K contributor, 2 split-K finisher) | slice << 8, item.w = index among split tiles
+  // The last sk_tiles data tiles are cut into sk_slices k-slices each ("split-K tail") so that the list scheduler can
+  // level the units' finishing times; contributors park raw partial sums, the finisher folds them in (through TMEM).
+  const int4 *plan;
+  const int *plan_off;
   int sk_tiles, sk_slices;
-  float *sk_ws;         // per (slice < sk_slices-1, tile, CTA of the group): one raw 128 x BN accumulator tile
-  int *sk_flags;        // [((slice*sk_tiles + tile)*CG + cta_rank)*4 + quadrant] = sk_epoch once that slab is written
+  float *sk_ws;         // per (slice < sk_slices-1, split tile, CTA of the group): one raw 128 x BN accumulator tile
+  int *sk_flags;        // [((slice*sk_tiles + split tile)*CG + cta_rank)*4 + quadrant] = sk_epoch once written
   int sk_epoch;
   // fault tolerance: checksum tile-columns
   int tiles_c;          // number of BN-wide checksum tile-columns (0 when FT is off)
@@ -162,55 +166,37 @@ __host__ __device__ __forceinline__ int chk_tile_width(const KernelParams &p, in
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Work decomposition.  Every role (producer, MMA issuer, epilogue) of work unit u walks the same list of items
-// u, u + P, u + 2P, ... of the global item sequence
-//   split-K head   item i < sk_tiles*sk_slices  ->  k-slice (i / sk_tiles) of tile (i % sk_tiles).  Slice-major order: at
-//                  any time all units work on the SAME k-range of neighbouring tiles, so A/B panels are still shared
-//                  in L2 (a contiguous stream-K split de-synchronises the k offsets and turned out HBM-bound).
-//                  Slices 0..S-2 are "contributors" (raw partial sums go to the workspace), slice S-1 is the "finisher"
-//                  (adds the contributors' partial sums in TMEM, then runs the normal epilogue).
-//   data-parallel  the remaining tiles, whole.
-// Every wait (finisher -> contributors, ABFT data tile -> checksum tiles) points to an item with a SMALLER index, and each
-// unit handles its items in increasing index, so the schedule cannot deadlock (tests/test_schedule.py simulates it).
+// Work decomposition.  Every role (producer, MMA issuer, epilogue) of work unit u walks the same item list, which the
+// host built with a cost-aware list scheduler (plan.h).  Global item order = [checksum tiles][whole data tiles, raster
+// order][split-K tail, slice-major]; each unit's list is increasing in that order and every wait (finisher ->
+// contributors of the same tile, ABFT data tile -> checksum tiles) points to an EARLIER item, so the schedule cannot
+// deadlock (tests/test_schedule.py simulates it, including the two-accumulator-stage constraint).  Slice-major order
+// keeps all units on the same k-range of neighbouring tiles, so A/B panels stay shared in L2 (a contiguous stream-K
+// split de-synchronised the k offsets and turned HBM-bound).
 // ------------------------------------------------------------------------------------------------------------
 struct Segment {
   int tile, kb_begin, kb_end;
   int kind;   // 0 whole tile, 1 contributor, 2 finisher
   int slice;
+  int split_idx;
 };
 
 struct SegIter {
-  int item, stride, num_kb, num_tiles, sk_tiles, sk_slices;
-  __host__ __device__ __forceinline__ SegIter(const KernelParams &p, int unit, int num_units, int num_kb_, int num_tiles_) {
-    item = unit;
-    stride = num_units;
-    num_kb = num_kb_;
-    num_tiles = num_tiles_;
-    sk_tiles = p.sk_tiles;
-    sk_slices = p.sk_tiles > 0 ? p.sk_slices : 1;
+  const int4 *cur, *end;
+  __device__ __forceinline__ SegIter(const KernelParams &p, int unit) {
+    cur = p.plan + p.plan_off[unit];
+    end = p.plan + p.plan_off[unit + 1];
   }
-  __host__ __device__ __forceinline__ bool next(Segment &s) {
-    const int head = sk_tiles * sk_slices;
-    if (item < head) {
-      s.slice = item / sk_tiles;
-      s.tile = item - s.slice * sk_tiles;
-      s.kb_begin = static_cast<int>(static_cast<long long>(num_kb) * s.slice / sk_slices);
-      s.kb_end = static_cast<int>(static_cast<long long>(num_kb) * (s.slice + 1) / sk_slices);
-      s.kind = (s.slice == sk_slices - 1) ? (sk_slices == 1 ? 0 : 2) : 1;
-      item += stride;
-      return true;
-    }
-    const int t = sk_tiles + (item - head);
-    if (t < num_tiles) {
-      s.tile = t;
-      s.slice = 0;
-      s.kb_begin = 0;
-      s.kb_end = num_kb;
-      s.kind = 0;
-      item += stride;
-      return true;
-    }
-    return false;
+  __device__ __forceinline__ bool next(Segment &s) {
+    if (cur == end) return false;
+    const int4 e = __ldg(cur++);
+    s.tile = e.x;
+    s.kb_begin = e.y & 0xFFFF;
+    s.kb_end = (e.y >> 16) & 0xFFFF;
+    s.kind = e.z & 0xFF;
+    s.slice = e.z >> 8;
+    s.split_idx = e.w;
+    return true;
   }
 };
 
@@ -509,9 +495,6 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
   const bool is_leader = cta_rank == 0;
   const int unit = blockIdx.x / CG;        // persistent work unit = CTA (CG=1) or CTA pair (CG=2)
-  const int num_units = gridDim.x / CG;
-  const int num_tiles = p.tiles_m * (p.tiles_n + p.tiles_c);
-  const int num_kb = (p.K + kBK - 1) / kBK;
 
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&tmA);
@@ -550,7 +533,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // warp-uniform loop, one elected lane issues the TMA instructions (see ptx::elect_one)
     int stage = 0;
     uint32_t phase = 0;
-    SegIter it(p, unit, num_units, num_kb, num_tiles);
+    SegIter it(p, unit);
     Segment sg;
     while (it.next(sg)) {
       const TileCoord tc = decode_tile(p, sg.tile);
@@ -643,7 +626,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    SegIter it(p, unit, num_units, num_kb, num_tiles);
+    SegIter it(p, unit);
     Segment sg;
     while (it.next(sg)) {
       uint32_t idesc_t = idesc;
@@ -702,7 +685,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t tempty_leader = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    SegIter it(p, unit, num_units, num_kb, num_tiles);
+    SegIter it(p, unit);
     Segment sg;
     const size_t ws_slab = static_cast<size_t>(kBM) * BN;  // floats per (unit, CTA) partial tile
     while (it.next(sg)) {
@@ -716,12 +699,12 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
       if (sg.kind == 1) {
         // split-K contributor: park the raw partial sums of this slab for the unit that finishes the tile
-        const int slot = (sg.slice * p.sk_tiles + sg.tile) * CG + static_cast<int>(cta_rank);
+        const int slot = (sg.slice * p.sk_tiles + sg.split_idx) * CG + static_cast<int>(cta_rank);
         sk_dump_partial<BN>(p, taddr, p.sk_ws + slot * ws_slab + row, p.sk_flags + slot * 4 + q, lane);
       } else if (sg.kind == 2) {
         // split-K finisher: fold in the earlier k-slices of this tile
         for (int sl = 0; sl < p.sk_slices - 1; ++sl) {
-          const int slot = (sl * p.sk_tiles + sg.tile) * CG + static_cast<int>(cta_rank);
+          const int slot = (sl * p.sk_tiles + sg.split_idx) * CG + static_cast<int>(cta_rank);
           sk_add_partial<BN>(p, taddr, p.sk_ws + slot * ws_slab + row, p.sk_flags + slot * 4 + q, lane);
         }
       }
@@ -782,45 +765,24 @@ __device__ __forceinline__ float tf32_bits(float x, int rounding) {
   if (rounding != 2) u &= 0xFFFFE000u;
   return __uint_as_float(u);
 }
-// Double-float (hi + lo) arithmetic: the B200's FP64 pipe is far too slow for an HBM-speed pass (measured: the FP64
-// version of this kernel ran at 2.2 TB/s), so checksums are accumulated as unevaluated FP32 pairs with error-free
-// transformations (Knuth two-sum); relative error ~2^-45, far below the TF32 split that follows.
-struct ff {
-  float hi, lo;
-};
-__device__ __forceinline__ ff ff_add(ff a, float b) {  // a + b, b exact
-  const float s = a.hi + b;
-  const float bb = s - a.hi;
-  const float err = (a.hi - (s - bb)) + (b - bb);
-  ff r;
-  r.hi = s;
-  r.lo = a.lo + err;
-  return r;
-}
-__device__ __forceinline__ ff ff_add(ff a, ff b) {
-  ff r = ff_add(a, b.hi);
-  r.lo += b.lo;
-  const float s = r.hi + r.lo;  // renormalise
-  r.lo = r.lo - (s - r.hi);
-  r.hi = s;
-  return r;
-}
-__device__ __forceinline__ void split3_tf32(ff x, float &h, float &m, float &l) {
-  h = tf32_bits(x.hi, 0);
-  float r = (x.hi - h) + x.lo;  // x.hi - h is exact (h is x.hi with low bits cleared)
-  m = tf32_bits(r, 0);
-  r -= m;
-  l = tf32_bits(r, 0);
+__device__ __forceinline__ void split3_tf32(double x, float &h, float &m, float &l) {
+  h = tf32_bits(static_cast<float>(x), 0);
+  double r = x - static_cast<double>(h);
+  m = tf32_bits(static_cast<float>(r), 0);
+  r -= static_cast<double>(m);
+  l = tf32_bits(static_cast<float>(r), 0);
 }
 
 constexpr int kEncWarps = 8;
 constexpr int kEncLoads = 8;  // 16-byte loads in flight per lane
 
 // grid = (tiles_n, ceil(K / (8 warps * KW))), KW = kEncLoads / J k-rows per warp, J = BN/128 float4 per lane and row.
-// All kEncLoads loads of a lane are issued before the first is consumed and the kernel is capped at 64 registers so
-// that 4 blocks (32 warps) are resident per SM: ~128 KB in flight per SM, enough to run at HBM speed (the first two
-// versions were occupancy/latency-bound at ~2 TB/s).  It also clears the checksum slab flags of the GEMM launch that
-// follows it in the stream (one memset launch less).  (j+1)*b is exact in FP32: 9-bit weight x 11-bit significand.
+// Arithmetic budget matters here (the first versions were instruction-bound at ~2.5 TB/s: FP64 or double-float work
+// on every element):  each lane sums its <= 8 elements of a row in plain FP32 -- TF32 inputs have 11-bit significands
+// and (j+1)*b is an exact 20-bit product, so these short sums are exact unless the elements differ by > 2^10 in
+// magnitude -- and only the 32-way cross-lane reduction runs in FP64 (10 DADD per row).  All kEncLoads loads of a lane
+// are issued before the first is consumed; 4 blocks (32 warps) are resident per SM.  The kernel also clears the checksum
+// slab flags of the GEMM launch that follows it in the stream (one memset launch less).
 template <int J>
 __global__ void __launch_bounds__(kEncWarps * 32, 4)
 encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, float *__restrict__ chk, int chk_ld,
@@ -832,9 +794,9 @@ encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, floa
   const int n0 = t * BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kbase = (blockIdx.y * kEncWarps + warp) * KW;
-  ff e[KW], w[KW];
+  float e[KW], w[KW];
 #pragma unroll
-  for (int u = 0; u < KW; ++u) e[u].hi = e[u].lo = w[u].hi = w[u].lo = 0.0f;
+  for (int u = 0; u < KW; ++u) e[u] = w[u] = 0.0f;
   if (J > 0 && n0 + BN <= N) {  // full tile of 128*J columns: 16-byte loads (ldb % 4 == 0, n0 % 4 == 0)
     float4 v[KW][J > 0 ? J : 1];
 #pragma unroll
@@ -852,8 +814,8 @@ encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, floa
         const float wj = static_cast<float>(4 * (lane + 32 * jj) + 1);
         const float b0 = tf32_bits(v[u][jj].x, rounding), b1 = tf32_bits(v[u][jj].y, rounding),
                     b2 = tf32_bits(v[u][jj].z, rounding), b3 = tf32_bits(v[u][jj].w, rounding);
-        e[u] = ff_add(ff_add(ff_add(ff_add(e[u], b0), b1), b2), b3);
-        w[u] = ff_add(ff_add(ff_add(ff_add(w[u], b0 * wj), b1 * (wj + 1.0f)), b2 * (wj + 2.0f)), b3 * (wj + 3.0f));
+        e[u] += (b0 + b1) + (b2 + b3);
+        w[u] += (b0 * wj + b1 * (wj + 1.0f)) + (b2 * (wj + 2.0f) + b3 * (wj + 3.0f));
       }
     }
   } else {
@@ -865,8 +827,8 @@ encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, floa
           const int k = kbase + u;
           if (k < K) {
             const float b = tf32_bits(__ldg(B + static_cast<size_t>(k) * ldb + n), rounding);
-            e[u] = ff_add(e[u], b);
-            w[u] = ff_add(w[u], b * static_cast<float>(j + 1));
+            e[u] += b;
+            w[u] += b * static_cast<float>(j + 1);
           }
         }
       }
@@ -874,21 +836,17 @@ encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, floa
   }
 #pragma unroll
   for (int u = 0; u < KW; ++u) {
+    double de = static_cast<double>(e[u]), dw = static_cast<double>(w[u]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      ff oe, ow;
-      oe.hi = __shfl_xor_sync(0xffffffffu, e[u].hi, o);
-      oe.lo = __shfl_xor_sync(0xffffffffu, e[u].lo, o);
-      ow.hi = __shfl_xor_sync(0xffffffffu, w[u].hi, o);
-      ow.lo = __shfl_xor_sync(0xffffffffu, w[u].lo, o);
-      e[u] = ff_add(e[u], oe);
-      w[u] = ff_add(w[u], ow);
+      de += __shfl_xor_sync(0xffffffffu, de, o);
+      dw += __shfl_xor_sync(0xffffffffu, dw, o);
     }
     const int k = kbase + u;
     if (k < K && lane < kChkPerTile) {  // every lane holds the totals; lane i writes column i of the 8-float block
       float eh, em, el, wh, wm, wl;
-      split3_tf32(e[u], eh, em, el);
-      split3_tf32(w[u], wh, wm, wl);
+      split3_tf32(de, eh, em, el);
+      split3_tf32(dw, wh, wm, wl);
       const float val = lane == 0 ? eh : lane == 1 ? em : lane == 2 ? el : lane == 3 ? wh : lane == 4 ? wm
                         : lane == 5 ? wl : 0.0f;
       chk[static_cast<size_t>(k) * chk_ld + t * kChkPerTile + lane] = val;

@@ -63,8 +63,9 @@ def _simulate(hdr, segs, acc_stages):
 def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms):
     M, N, K = shape
     hdr, segs = ft.debug_schedule(kid, M, N, K, num_sms)
-    units, num_kb, sk = hdr["units"], hdr["num_kb"], hdr["sk_tiles"]
+    units, num_kb, H, S = hdr["units"], hdr["num_kb"], hdr["sk_tiles"], hdr["sk_slices"]
     assert hdr["num_kb"] == -(-K // 32)
+    first_tail = hdr["num_tiles"] - H
     cover = {}
     finishers = {}
     for s in segs:
@@ -75,33 +76,31 @@ def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms):
             assert s["tile"] not in finishers
             finishers[s["tile"]] = s
         else:
-            assert s["kb_end"] < num_kb and s["tile"] < sk
+            assert s["kb_end"] < num_kb and s["tile"] >= first_tail and not s["is_chk"]
     assert sorted(cover) == list(range(hdr["num_tiles"]))
-    total = sk * num_kb
     for t, pieces in cover.items():
         pieces.sort()
         assert pieces[0][0] == 0 and pieces[-1][1] == num_kb
         for a, b in zip(pieces, pieces[1:]):
             assert a[1] == b[0]  # contiguous, no overlap
         fin = finishers[t]
-        contributors = sorted(p[2] for p in pieces if p[3] == 1)
         if fin["kind"] == 0:
-            assert not contributors
+            assert len(pieces) == 1
         else:
-            # slice-major head: the finisher is the last of sk_slices equal slices, all earlier slices contribute
-            assert len(contributors) == hdr["sk_slices"] - 1 and t < sk
-            assert sorted(p[3] for p in pieces) == [1] * (hdr["sk_slices"] - 1) + [2]
-    # every wait points to a smaller item index: items are dealt round-robin, so item index = unit + P * position
-    pos = {}
-    index = {}
+            assert t >= first_tail and sorted(p[3] for p in pieces) == [1] * (S - 1) + [2]
+    # global item order [checksum tiles][whole data tiles][tail, slice-major]: every unit's list is increasing in it,
+    # so every wait (finisher -> earlier slices of its tile, data tile -> checksum tiles) points to an earlier item
+    def gidx(s_):
+        if s_["tile"] < first_tail or S == 1:
+            return s_["tile"]
+        return first_tail + s_["slice"] * H + (s_["tile"] - first_tail)
+    last = {}
     for s_ in segs:
-        k = pos.get(s_["unit"], 0)
-        pos[s_["unit"]] = k + 1
-        index[(s_["tile"], s_["slice"])] = s_["unit"] + units * k
-    for s_ in segs:
-        me = index[(s_["tile"], s_["slice"])]
-        if s_["kind"] == 2:
-            assert all(index[(s_["tile"], sl)] < me for sl in range(hdr["sk_slices"] - 1))
+        g = gidx(s_)
+        assert last.get(s_["unit"], -1) < g
+        last[s_["unit"]] = g
+        if s_["is_chk"]:
+            assert s_["tile"] < hdr["n_chk_tiles"]
     # checksum tiles: n_chk_tiles of them, 8 columns per N-tile
     chk = {(s["m_blk"], s["n_blk"]) for s in segs if s["is_chk"]}
     assert len(chk) == hdr["n_chk_tiles"]
@@ -112,13 +111,13 @@ def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms):
     assert _simulate(hdr, segs, acc_stages), "circular wait in the schedule"
 
 
-def test_balanced_head(ft):
-    """The split-K head removes the wave-quantisation loss where it matters."""
+def test_planner_levels_the_units(ft):
+    """The list scheduler + split-K tail removes the wave-quantisation loss where it pays for the fold-in."""
     def makespan(kid, n):
         hdr, segs = ft.debug_schedule(kid, n, n, n, 148)
         work = [0.0] * hdr["units"]
         for s in segs:
-            work[s["unit"]] += (s["kb_end"] - s["kb_begin"]) / hdr["num_kb"]
+            work[s["unit"]] += (0.5 if s["is_chk"] and n == 4096 else 1.0) * (s["kb_end"] - s["kb_begin"]) / hdr["num_kb"]
         return hdr, max(work)
     hdr, t = makespan(21, 4096)   # 256 tiles on 74 pairs: 3.46 waves -> the 34-tile remainder is split in two
     assert (hdr["sk_tiles"], hdr["sk_slices"]) == (34, 2) and abs(t - 3.5) < 1e-9
@@ -126,3 +125,5 @@ def test_balanced_head(ft):
     assert hdr["sk_tiles"] == 0 and t == 1.0
     hdr, t = makespan(21, 8192)   # 13.84 waves: not worth splitting
     assert hdr["sk_tiles"] == 0 and t == 14.0
+    hdr, t = makespan(31, 8192)   # ABFT adds 32 checksum tiles: 14.27 waves -> 14.5 instead of 15
+    assert hdr["sk_slices"] == 2 and t <= 14.5 + 1e-9
