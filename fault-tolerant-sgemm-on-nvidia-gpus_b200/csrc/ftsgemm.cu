@@ -225,7 +225,11 @@ PlanInput make_plan_input(int num_sms, int CG, int BN, int K, const KernelParams
   // ~15k SM cycles, whatever K is; expressed in tile-times (one k-block = 4 UMMAs of ~128 cycles)
   in.slice_overhead = static_cast<double>(dbg("slice_overhead_cycles", 15000)) / (static_cast<double>(in.num_kb) * 512.0);
   const long long force = dbg("splitk", -2);  // -2 auto, 0 off, s > 1: force s slices
-  in.max_slices = force == 0 ? 1 : 8;
+  // ABFT tiles are never K-split: the tensor core's FP32 accumulation has a small systematic (truncation-like) bias that
+  // is the same for a data row and its checksum as long as both accumulate over the same k sequence; restarting the data
+  // accumulation at a slice boundary breaks that cancellation (measured: fault-free residual 7.6e-7 -> 5.3e-6 of sum|acc|
+  // at K = 8192, profiles/r01_probe8_residual_vs_splitk.jsonl), which would eat the detection margin.
+  in.max_slices = (force == 0 || (p.tiles_c > 0 && force <= 1)) ? 1 : 8;
   in.force_slices = force > 1 ? static_cast<int>(force) : 0;
   in.slab_bytes = static_cast<size_t>(CG) * kBM * BN * sizeof(float);
   return in;
@@ -241,7 +245,8 @@ void plan_tiles(int M, int N, int BN, int CG, bool ft, KernelParams *p) {
   p->tiles_c = 0;
   if (ft) {
     p->n_chk_cols = p->tiles_n * kChkPerTile;
-    p->tiles_c = (p->n_chk_cols + BN - 1) / BN;
+    const int cw = chk_cols_per_tile(BN);
+    p->tiles_c = (p->n_chk_cols + cw - 1) / cw;
     if (dbg("ft_dbg", 0) & 2) p->tiles_c = 0;  // experiment: no checksum tile-columns (expected checksums are garbage)
   }
 }

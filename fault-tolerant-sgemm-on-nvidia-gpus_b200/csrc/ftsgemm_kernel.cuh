@@ -44,6 +44,7 @@ constexpr int kBM = 128;          // rows per CTA (UMMA M = 128 * CG)
 constexpr int kBK = 32;           // K extent of one shared-memory stage (4 UMMA k-steps of 8)
 constexpr int kAtomMN = 32;       // floats per 128-byte swizzle row
 constexpr int kChkPerTile = 8;    // checksum columns per N-tile (6 used: e hi/mid/lo, w hi/mid/lo)
+constexpr int kChkTileCols = 64;  // width of one checksum work item (narrow UMMA N): small items level the schedule
 constexpr int kThreads = 256;
 constexpr int kMaxFaults = 8;
 constexpr int kMaxEvents = 16;
@@ -90,7 +91,7 @@ struct KernelParams {
   int *sk_flags;        // [((slice*sk_tiles + split tile)*CG + cta_rank)*4 + quadrant] = sk_epoch once written
   int sk_epoch;
   // fault tolerance: checksum tile-columns
-  int tiles_c;          // number of BN-wide checksum tile-columns (0 when FT is off)
+  int tiles_c;          // number of kChkTileCols-wide checksum tile-columns (0 when FT is off)
   int n_chk_cols;       // tiles_n * kChkPerTile
   float *chk_out;       // M x n_chk_cols, column-major (ld = M): expected checksums r1/r2 (3-way split)
   int *chk_flags;       // one counter per 32-row slab; == tiles_c once that slab's checksums are published
@@ -154,12 +155,14 @@ __host__ __device__ __forceinline__ TileCoord decode_tile(const KernelParams &p,
   return tc;
 }
 
-// Checksum tile-columns only hold n_chk_cols real columns; the last one is narrowed to the next multiple of
-// 32*CG so that its UMMA N (and its tensor time) shrinks accordingly (e.g. 128 instead of 256 at N = 4096).
+// Checksum tile-column c covers checksum columns [c*kChkTileCols, (c+1)*kChkTileCols) (the last one fewer); its UMMA N
+// is that width rounded up to 32*CG, so a checksum work item costs only N/BN of a data tile.
+__host__ __device__ __forceinline__ int chk_cols_per_tile(int BN) { return kChkTileCols < BN ? kChkTileCols : BN; }
 template <int BN, int CG>
 __host__ __device__ __forceinline__ int chk_tile_width(const KernelParams &p, int c_blk) {
-  const int rest = p.n_chk_cols - c_blk * BN;
-  const int cols = rest < BN ? rest : BN;
+  const int cw = chk_cols_per_tile(BN);
+  const int rest = p.n_chk_cols - c_blk * cw;
+  const int cols = rest < cw ? rest : cw;
   const int q = 32 * CG;
   const int w = (cols + q - 1) / q * q;
   return w < BN ? w : BN;
@@ -540,7 +543,8 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int m0 = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;        // this CTA's 128 rows of A
       const bool b_is_chk = FT && tc.is_chk;
       const int n_eff = b_is_chk ? chk_tile_width<BN, CG>(p, tc.n_blk) : BN;
-      const int nb0 = tc.n_blk * BN + static_cast<int>(cta_rank) * (n_eff / CG);  // this CTA's share of B rows
+      const int nb0 = (b_is_chk ? tc.n_blk * chk_cols_per_tile(BN) : tc.n_blk * BN) +
+                      static_cast<int>(cta_rank) * (n_eff / CG);  // this CTA's share of B rows
       const CUtensorMap *tmb = b_is_chk ? &tmChk : &tmB;
       // The loop body is specialised OUTSIDE the k loop: with 3-D tensor maps a stage is exactly two TMA instructions
       // (predicated-off TMA instructions still cost issue time on the single producer thread).
@@ -691,7 +695,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     while (it.next(sg)) {
       const TileCoord tc = decode_tile(p, sg.tile);
       const int m0_cta = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;
-      const int n0 = tc.n_blk * BN;
+      const int n0 = (FT && tc.is_chk) ? tc.n_blk * chk_cols_per_tile(BN) : tc.n_blk * BN;
       const int m = m0_cta + row;
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
@@ -712,7 +716,8 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // nothing to store yet
       } else if (FT && tc.is_chk) {
         // checksum tile-column: publish R = A * [e, w]^T for these 128 rows, then raise the slab flag
-        store_tile<BN>(taddr, p.chk_out + m, m < p.M, n0, p.n_chk_cols, p.M, 1.0f, 0.0f, -1, 0.0f);
+        const int n_hi = min(p.n_chk_cols, n0 + chk_cols_per_tile(BN));  // columns beyond belong to the next item
+        store_tile<BN>(taddr, p.chk_out + m, m < p.M, n0, n_hi, p.M, 1.0f, 0.0f, -1, 0.0f);
         __threadfence();
         __syncwarp();
         if (lane == 0) atomicAdd(p.chk_flags + (m0_cta >> 5) + q, 1);

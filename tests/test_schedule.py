@@ -106,7 +106,7 @@ def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms):
     assert len(chk) == hdr["n_chk_tiles"]
     if kid in (11, 12, 16, 15, 31, 32):
         tiles_n = -(-N // TILE_N[kid])
-        assert hdr["n_chk_tiles"] == -(-M // (128 * hdr["cta_group"])) * -(-(tiles_n * 8) // TILE_N[kid])
+        assert hdr["n_chk_tiles"] == -(-M // (128 * hdr["cta_group"])) * -(-(tiles_n * 8) // min(64, TILE_N[kid]))
     acc_stages = 2 if 2 * TILE_N[kid] <= 512 else 1
     assert _simulate(hdr, segs, acc_stages), "circular wait in the schedule"
 
@@ -125,5 +125,9 @@ def test_planner_levels_the_units(ft):
     assert hdr["sk_tiles"] == 0 and t == 1.0
     hdr, t = makespan(21, 8192)   # 13.84 waves: not worth splitting
     assert hdr["sk_tiles"] == 0 and t == 14.0
-    hdr, t = makespan(31, 8192)   # ABFT adds 32 checksum tiles: 14.27 waves -> 14.5 instead of 15
-    assert hdr["sk_slices"] == 2 and t <= 14.5 + 1e-9
+    hdr, t = makespan(31, 8192)   # ABFT: 128 quarter-cost checksum items level 14.27 waves to <= 14.5 (not 15)
+    assert hdr["sk_slices"] == 1 and hdr["n_chk_tiles"] == 128
+    work = [0.0] * hdr["units"]
+    for s in ft.debug_schedule(31, 8192, 8192, 8192, 148)[1]:
+        work[s["unit"]] += 0.25 if s["is_chk"] else 1.0
+    assert max(work) <= 14.5 + 1e-9
