@@ -44,53 +44,56 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons DURING the timed region.  The timed region of this benchmark is only a few
+    milliseconds, so the sampler polls NVML directly from a thread (~1 kHz) instead of `nvidia-smi -lms` (>= 100 ms
+    granularity); it falls back to nvidia-smi if pynvml is unavailable."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index=0):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.samples, self.stop_flag, self.thread, self.nvml = index, [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception:
-            self.proc = None
+            self.nvml = None
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.time(), sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.0005)
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, pw, reasons = [], [], [], set()
-        for ts, line in self.lines:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            if t0 <= ts <= t1 + 0.1:
-                try:
-                    sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
-                except ValueError:
-                    continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-        if not sm:  # region shorter than the sampling period: use the nearest samples
-            for ts, line in self.lines[-3:]:
-                f = [x.strip() for x in line.split(",")]
-                try:
-                    sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
-                except Exception:
-                    pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        if self.nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        inside = [x for x in self.samples if t0 <= x[0] <= t1]
+        if not inside:  # region shorter than one NVML round trip: nearest samples
+            inside = sorted(self.samples, key=lambda x: abs(x[0] - 0.5 * (t0 + t1)))[:3]
+        reasons = set()
+        for _, _, _, rs in inside:
+            for bit, name in self.REASONS.items():
+                if rs & bit:
+                    reasons.add(name)
+        sm = [x[1] for x in inside]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_sm,
+                "power_w_max": max((x[2] for x in inside), default=None), "samples": len(inside),
+                "reasons": sorted(reasons), "how": "pynvml polled from a thread during the timed region"}
 
 
 def _cpu_port_baseline(n, seconds_target=12.0):
@@ -163,7 +166,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--size", type=int, default=4096)

@@ -20,11 +20,11 @@
 // ABFT scheme.  With b~ = the TF32 value the tensor core actually consumes and J_t the columns
 // of N-tile t:
 //   encode    (pre-pass encode_b_kernel; reference ENCODE ft_sgemm_huge.cuh:150-168)
-//             e_t[k] = sum_{n in J_t} b~[n,k]      w_t[k] = sum_{n in J_t} (n-n0+1) b~[n,k]     (3-way TF32 split each)
-//   checksum GEMM (reference CHECKSUM-GEMV :171-213): the 8 checksum vectors of every N-tile are appended to B as extra
+//             e_t[k] = sum_{n in J_t} b~[n,k]      w_t[k] = sum_{n in J_t} (n-n0+1) b~[n,k]     (2-way TF32 split each)
+//   checksum GEMM (reference CHECKSUM-GEMV :171-213): the 4 checksum vectors of every N-tile are appended to B as extra
 //             "rows", i.e. the SAME kernel computes extra tile-columns  R = A * [e_t, w_t]^T  first (FP32 accumulate in
 //             TMEM, identical operand rounding), writes them to a small workspace and publishes a per-32-row flag.
-//             Cost: 8 columns per BN data columns (3 % at BN = 256) instead of a second pass over A.
+//             Cost: 4 columns per BN data columns (1.6 % at BN = 256) instead of a second pass over A.
 //   detect    (epilogue; reference :328-421)  d1[m] = r1[m] - sum_n acc[m,n],  d2[m] = r2[m] - sum_n (n-n0+1) acc[m,n],
 //             flagged iff |d1| > tau_abs + tau_rel * sum_n |acc[m,n]|
 //   locate    column j = round(d2/d1) - 1   (weighted checksum; the reference intersects a row and a column residual)
@@ -43,8 +43,7 @@ namespace ftsgemm {
 constexpr int kBM = 128;          // rows per CTA (UMMA M = 128 * CG)
 constexpr int kBK = 32;           // K extent of one shared-memory stage (4 UMMA k-steps of 8)
 constexpr int kAtomMN = 32;       // floats per 128-byte swizzle row
-constexpr int kChkPerTile = 8;    // checksum columns per N-tile (6 used: e hi/mid/lo, w hi/mid/lo)
-constexpr int kChkTileCols = 64;  // width of one checksum work item (narrow UMMA N): small items level the schedule
+constexpr int kChkPerTile = 4;    // checksum columns per N-tile: e hi/lo, w hi/lo (2 x 11-bit TF32 terms = 2^-22 relative)
 constexpr int kThreads = 256;
 constexpr int kMaxFaults = 8;
 constexpr int kMaxEvents = 16;
@@ -91,9 +90,9 @@ struct KernelParams {
   int *sk_flags;        // [((slice*sk_tiles + split tile)*CG + cta_rank)*4 + quadrant] = sk_epoch once written
   int sk_epoch;
   // fault tolerance: checksum tile-columns
-  int tiles_c;          // number of kChkTileCols-wide checksum tile-columns (0 when FT is off)
+  int tiles_c;          // number of BN-wide checksum tile-columns (0 when FT is off)
   int n_chk_cols;       // tiles_n * kChkPerTile
-  float *chk_out;       // M x n_chk_cols, column-major (ld = M): expected checksums r1/r2 (3-way split)
+  float *chk_out;       // M x n_chk_cols, column-major (ld = M): expected checksums r1/r2 (hi, lo each)
   int *chk_flags;       // one counter per 32-row slab; == tiles_c once that slab's checksums are published
   float tau_abs, tau_rel;
   int detect_only;
@@ -155,9 +154,12 @@ __host__ __device__ __forceinline__ TileCoord decode_tile(const KernelParams &p,
   return tc;
 }
 
-// Checksum tile-column c covers checksum columns [c*kChkTileCols, (c+1)*kChkTileCols) (the last one fewer); its UMMA N
-// is that width rounded up to 32*CG, so a checksum work item costs only N/BN of a data tile.
-__host__ __device__ __forceinline__ int chk_cols_per_tile(int BN) { return kChkTileCols < BN ? kChkTileCols : BN; }
+// Checksum tile-column c covers checksum columns [c*BN, (c+1)*BN) (the last one fewer); its UMMA N is that width
+// rounded up to 32*CG.  Measured: a checksum tile costs about as much as a data tile whatever its N, because its main
+// loop is bound by the A-operand feed (L2 -> shared memory), not by the tensor pipe -- so checksum tile-columns are kept
+// as wide as possible (narrow 64-column items made ABFT 5 % slower, profiles/r01_probe7_*), and only the last one is
+// narrowed.
+__host__ __device__ __forceinline__ int chk_cols_per_tile(int BN) { return BN; }
 template <int BN, int CG>
 __host__ __device__ __forceinline__ int chk_tile_width(const KernelParams &p, int c_blk) {
   const int cw = chk_cols_per_tile(BN);
@@ -312,11 +314,10 @@ __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr
   float r1 = 0.0f, r2 = 0.0f;
   if (m < p.M) {
     const float *cp = p.chk_out + static_cast<size_t>(n_blk) * kChkPerTile * p.M + m;
-    const float e0 = __ldcg(cp), e1 = __ldcg(cp + p.M), e2 = __ldcg(cp + 2 * static_cast<size_t>(p.M));
-    const float w0 = __ldcg(cp + 3 * static_cast<size_t>(p.M)), w1 = __ldcg(cp + 4 * static_cast<size_t>(p.M)),
-                w2 = __ldcg(cp + 5 * static_cast<size_t>(p.M));
-    r1 = e0 + (e1 + e2);
-    r2 = w0 + (w1 + w2);
+    const float e0 = __ldcg(cp), e1 = __ldcg(cp + p.M);
+    const float w0 = __ldcg(cp + 2 * static_cast<size_t>(p.M)), w1 = __ldcg(cp + 3 * static_cast<size_t>(p.M));
+    r1 = e0 + e1;
+    r2 = w0 + w1;
   }
   const float d1 = r1 - s1, d2 = r2 - s2;
   const float thr = p.tau_abs + p.tau_rel * sabs;
@@ -550,7 +551,9 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // (predicated-off TMA instructions still cost issue time on the single producer thread).
       const bool all3d = (p.tma3d & 1) && (p.tma3d & (b_is_chk ? 4 : 2));
       const int a_atom = m0 / kAtomMN, b_atom = nb0 / kAtomMN;
-      if (all3d) {
+      // (the B descriptor is a kernel-parameter address known at compile time in each copy of the loop: a run-time
+      //  selected descriptor pointer measurably slows the TMA issue)
+      auto fast_loop = [&](const CUtensorMap *tmb_const) {
         for (int kb = sg.kb_begin; kb < sg.kb_end; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sA = smem_base + stage * Cfg::kStageBytes;
@@ -562,11 +565,11 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
               else ptx::mbar_arrive_cluster(bar);
               ptx::tma_load_3d_cg2(sA, &tmA, bar, 0, k0, a_atom);
-              ptx::tma_load_3d_cg2(sB, tmb, bar, 0, k0, b_atom);
+              ptx::tma_load_3d_cg2(sB, tmb_const, bar, 0, k0, b_atom);
             } else {
               ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
               ptx::tma_load_3d(sA, &tmA, full_bar(stage), 0, k0, a_atom);
-              ptx::tma_load_3d(sB, tmb, full_bar(stage), 0, k0, b_atom);
+              ptx::tma_load_3d(sB, tmb_const, full_bar(stage), 0, k0, b_atom);
             }
           }
           __syncwarp();
@@ -575,6 +578,10 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             phase ^= 1u;
           }
         }
+      };
+      if (all3d) {
+        if (b_is_chk) fast_loop(&tmChk);
+        else fast_loop(&tmB);
       } else {
         for (int kb = sg.kb_begin; kb < sg.kb_end; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -758,11 +765,10 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // Encode pre-pass (reference: ft_sgemm_huge.cuh:150-168 ENCODE of B, done there per CTA and per k-step with
 // shuffles; here once per GEMM and per BN-wide column block, because a CUDA-core re-read of every shared-memory
 // stage does not fit next to a tensor-core main loop -- DESIGN.md section 3).
-//   chk[k][t*8 + 0..2] = 3-way TF32 split of  e = sum_{n in block t} tf32(B[n,k])
-//   chk[k][t*8 + 3..5] = 3-way TF32 split of  w = sum_{n in block t} (n - n0 + 1) * tf32(B[n,k])
-//   chk[k][t*8 + 6..7] = 0
+//   chk[k][t*4 + 0..1] = (hi, lo) TF32 split of  e = sum_{n in block t} tf32(B[n,k])
+//   chk[k][t*4 + 2..3] = (hi, lo) TF32 split of  w = sum_{n in block t} (n - n0 + 1) * tf32(B[n,k])
 // Sums are accumulated as FP32 hi+lo pairs (error-free transformations), so the three TF32 terms carry the checksum
-// to ~2^-33 relative.
+// to ~2^-22 relative (enough: its contribution to the residual is < 3 % of the measured floor).
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float tf32_bits(float x, int rounding) {
   uint32_t u = __float_as_uint(x);
@@ -770,12 +776,9 @@ __device__ __forceinline__ float tf32_bits(float x, int rounding) {
   if (rounding != 2) u &= 0xFFFFE000u;
   return __uint_as_float(u);
 }
-__device__ __forceinline__ void split3_tf32(double x, float &h, float &m, float &l) {
+__device__ __forceinline__ void split2_tf32(double x, float &h, float &l) {
   h = tf32_bits(static_cast<float>(x), 0);
-  double r = x - static_cast<double>(h);
-  m = tf32_bits(static_cast<float>(r), 0);
-  r -= static_cast<double>(m);
-  l = tf32_bits(static_cast<float>(r), 0);
+  l = tf32_bits(static_cast<float>(x - static_cast<double>(h)), 0);  // x - h is exact in FP64
 }
 
 constexpr int kEncWarps = 8;
@@ -848,12 +851,11 @@ encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, floa
       dw += __shfl_xor_sync(0xffffffffu, dw, o);
     }
     const int k = kbase + u;
-    if (k < K && lane < kChkPerTile) {  // every lane holds the totals; lane i writes column i of the 8-float block
-      float eh, em, el, wh, wm, wl;
-      split3_tf32(de, eh, em, el);
-      split3_tf32(dw, wh, wm, wl);
-      const float val = lane == 0 ? eh : lane == 1 ? em : lane == 2 ? el : lane == 3 ? wh : lane == 4 ? wm
-                        : lane == 5 ? wl : 0.0f;
+    if (k < K && lane < kChkPerTile) {  // every lane holds the totals; lane i writes column i of the 4-float block
+      float eh, el, wh, wl;
+      split2_tf32(de, eh, el);
+      split2_tf32(dw, wh, wl);
+      const float val = lane == 0 ? eh : lane == 1 ? el : lane == 2 ? wh : wl;
       chk[static_cast<size_t>(k) * chk_ld + t * kChkPerTile + lane] = val;
     }
   }

@@ -56,8 +56,10 @@ struct Cand {
   int H, S;
 };
 
-// list scheduling in global item order; returns makespan, optionally records the assignment
-inline double schedule(const PlanInput &in, int H, int S, Plan *out) {
+// list scheduling in global item order; returns makespan, optionally records the assignment.
+// head_first: [checksum][split slices, slice-major][whole tiles] -- the finishers' fold-in is hidden behind the whole
+// tiles that follow (cheaper per item) but small-items-first levels worse; otherwise [checksum][whole][split slices].
+inline double schedule(const PlanInput &in, int H, int S, bool head_first, Plan *out) {
   typedef std::pair<double, int> LU;  // (load, unit): least load first, ties to the lowest unit id
   std::priority_queue<LU, std::vector<LU>, std::greater<LU>> pq;
   for (int u = 0; u < in.units; ++u) pq.push(LU(0.0, u));
@@ -73,17 +75,30 @@ inline double schedule(const PlanInput &in, int H, int S, Plan *out) {
     pq.push(lu);
   };
   const int whole = in.n_data_tiles - H;
+  // the split tiles are always the LAST H data tiles of the raster; only their position in the item order changes
+  auto give_whole = [&]() {
+    for (int d = 0; d < whole; ++d) give(PlanItem{in.n_chk_tiles + d, 0, in.num_kb, 0, 0, -1}, 1.0);
+  };
+  auto give_split = [&]() {
+    const double ovh = S > 1 ? in.slice_overhead * (head_first ? 0.35 : 1.0) : 0.0;
+    for (int s = 0; s < S; ++s) {
+      const int kb0 = static_cast<int>(static_cast<long long>(in.num_kb) * s / S);
+      const int kb1 = static_cast<int>(static_cast<long long>(in.num_kb) * (s + 1) / S);
+      for (int i = 0; i < H; ++i) {
+        const int kind = (S == 1) ? 0 : (s == S - 1 ? 2 : 1);
+        give(PlanItem{in.n_chk_tiles + whole + i, kb0, kb1, kind, s, S > 1 ? i : -1},
+             static_cast<double>(kb1 - kb0) / in.num_kb + ovh);
+      }
+    }
+  };
   for (int t = 0; t < in.n_chk_tiles; ++t)
     give(PlanItem{t, 0, in.num_kb, 0, 0, -1}, in.chk_col_cost[static_cast<size_t>(t / in.tiles_m)]);
-  for (int d = 0; d < whole; ++d) give(PlanItem{in.n_chk_tiles + d, 0, in.num_kb, 0, 0, -1}, 1.0);
-  for (int s = 0; s < S; ++s) {
-    const int kb0 = static_cast<int>(static_cast<long long>(in.num_kb) * s / S);
-    const int kb1 = static_cast<int>(static_cast<long long>(in.num_kb) * (s + 1) / S);
-    for (int i = 0; i < H; ++i) {
-      const int kind = (S == 1) ? 0 : (s == S - 1 ? 2 : 1);
-      give(PlanItem{in.n_chk_tiles + whole + i, kb0, kb1, kind, s, S > 1 ? i : -1},
-           static_cast<double>(kb1 - kb0) / in.num_kb + (S > 1 ? in.slice_overhead : 0.0));
-    }
+  if (head_first) {
+    give_split();
+    give_whole();
+  } else {
+    give_whole();
+    give_split();
   }
   if (out) {
     out->units = in.units;
@@ -105,7 +120,8 @@ inline double schedule(const PlanInput &in, int H, int S, Plan *out) {
 inline Plan build_plan(const PlanInput &in) {
   using plan_detail::schedule;
   int bestH = 0, bestS = 1;
-  double best = schedule(in, 0, 1, nullptr);
+  bool best_head = false;
+  double best = schedule(in, 0, 1, false, nullptr);
   const int P = in.units, T = in.n_data_tiles;
   if (in.max_slices > 1 && T > 0) {
     const int hs[] = {T % P, T % P + P, P / 2, P, (3 * P) / 2, 2 * P, T};
@@ -117,18 +133,21 @@ inline Plan build_plan(const PlanInput &in) {
         if (in.force_slices > 1 && S != in.force_slices) continue;
         if (static_cast<size_t>(H) * (S - 1) * in.slab_bytes > (static_cast<size_t>(256) << 20)) break;
         if (static_cast<size_t>(H) * (S - 1) * 8 * sizeof(int) > 65536) break;  // flag area
-        const double t = schedule(in, H, S, nullptr);
-        const bool forced_first = in.force_slices > 1 && bestS == 1;
-        if (t < best * 0.985 || forced_first) {  // a split must buy at least 1.5 %
-          best = t;
-          bestH = H;
-          bestS = S;
+        for (int head = 0; head < 2; ++head) {
+          const double t = schedule(in, H, S, head != 0, nullptr);
+          const bool forced_first = in.force_slices > 1 && bestS == 1;
+          if (t < best * 0.985 || forced_first) {  // a split must buy at least 1.5 %
+            best = t;
+            bestH = H;
+            bestS = S;
+            best_head = head != 0;
+          }
         }
       }
     }
   }
   Plan p;
-  schedule(in, bestH, bestS, &p);
+  schedule(in, bestH, bestS, best_head, &p);
   return p;
 }
 
