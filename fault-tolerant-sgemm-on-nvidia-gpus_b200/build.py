@@ -26,7 +26,7 @@ def _stale(target: Path, sources) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> None:
     lib_src = [CSRC / "ftsgemm.cu"]
-    lib_dep = lib_src + [CSRC / "ftsgemm_kernel.cuh", CSRC / "ptx.cuh", ROOT / "include" / "ftsgemm.h"]
+    lib_dep = lib_src + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [ROOT / "include" / "ftsgemm.h"]
     if force or _stale(LIB, lib_dep):
         cmd = [NVCC, *ARCH, *COMMON, "-shared", "-Xptxas", "-v", *map(str, lib_src), "-o", str(LIB), "-lcublas"]
         out = subprocess.run(cmd, capture_output=True, text=True)

@@ -80,7 +80,8 @@ inline double schedule(const PlanInput &in, int H, int S, bool head_first, Plan 
     for (int d = 0; d < whole; ++d) give(PlanItem{in.n_chk_tiles + d, 0, in.num_kb, 0, 0, -1}, 1.0);
   };
   auto give_split = [&]() {
-    const double ovh = S > 1 ? in.slice_overhead * (head_first ? 0.35 : 1.0) : 0.0;
+    // the fold-in is hidden only if a full wave of whole tiles follows the split items
+    const double ovh = S > 1 ? in.slice_overhead * ((head_first && whole >= in.units) ? 0.35 : 1.0) : 0.0;
     for (int s = 0; s < S; ++s) {
       const int kb0 = static_cast<int>(static_cast<long long>(in.num_kb) * s / S);
       const int kb1 = static_cast<int>(static_cast<long long>(in.num_kb) * (s + 1) / S);
