@@ -166,7 +166,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--size", type=int, default=4096)
@@ -264,12 +264,13 @@ def main():
 
     # ---- dominant kernel alone (checksum panel reused -> no encode launch), same event method
     reset_c()
-    k_ms = timed(lambda: ft.run(args.id, M, N, K, dA, dB, dC, alpha, beta, opts_reuse), steps) / steps
+    k_steps = min(steps, 100)
+    k_ms = timed(lambda: ft.run(args.id, M, N, K, dA, dB, dC, alpha, beta, opts_reuse), k_steps) / k_steps
     # ---- comparators on the same buffers: cuBLAS-TF32 (the bar), own non-FT kernel, non-fused baseline, cuBLAS FP32
     comp = {}
     plain_id = {31: 21, 32: 22}.get(args.id, args.id - 10)
-    for name, kid, reps in (("cublas_tf32", 7, steps), ("plain", plain_id, steps), ("cublas_fp32", 0, max(3, steps // 4)),
-                            ("abft_baseline_tf32", 30, 2), ("abft_baseline", 10, 2)):
+    for name, kid, reps in (("cublas_tf32", 7, min(steps, 100)), ("plain", plain_id, min(steps, 100)),
+                            ("cublas_fp32", 0, 5), ("abft_baseline_tf32", 30, 2), ("abft_baseline", 10, 2)):
         reset_c()
         o = pkg.make_opts(stream=stream, baseline_host_sync=True)
         for _ in range(2):

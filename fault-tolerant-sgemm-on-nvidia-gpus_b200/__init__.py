@@ -81,6 +81,7 @@ EXPORTED_SYMBOLS = [
     "ftsgemm_create", "ftsgemm_destroy", "ftsgemm_abi_version", "ftsgemm_error_string", "ftsgemm_last_cuda_error",
     "ftsgemm_default_opts", "ftsgemm_kernel_table", "ftsgemm_kernel_lookup", "ftsgemm_run", "ftsgemm_get_stats",
     "ftsgemm_run_host", "ftsgemm_baseline", "ftsgemm_verify", "ftsgemm_debug_set", "ftsgemm_debug_schedule",
+    "ftsgemm_verify_bad_count",
 ]
 
 _lib = None
@@ -118,6 +119,8 @@ def lib():
         L.ftsgemm_baseline.argtypes = [vp, ip, ip, ip, vp, vp, vp, fp, fp, ip, C.POINTER(Opts), vp]
         L.ftsgemm_verify.argtypes = [vp, vp, vp, ip, ip, C.POINTER(C.c_longlong), C.POINTER(C.c_double), vp]
         L.ftsgemm_debug_set.argtypes = [C.c_char_p, C.c_longlong]
+        L.ftsgemm_verify_bad_count.argtypes = [vp]
+        L.ftsgemm_verify_bad_count.restype = C.c_longlong
         L.ftsgemm_debug_schedule.argtypes = [ip, ip, ip, ip, ip, C.POINTER(C.c_int), C.POINTER(C.c_int), ip]
         _lib = L
     return _lib
