@@ -105,6 +105,11 @@ struct ftsgemm_handle_s {
     bool uploaded = false;
   };
   std::map<std::array<long long, 6>, CachedPlan> plans;  // key: kernel id, M, N, K, units, forced slices
+  cudaStream_t enc_stream = nullptr;   // the encode pre-pass runs here, concurrently with the GEMM kernel
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int *d_enc_done = nullptr;    // {done epoch, block counter}
+  int enc_epoch = 0;
+  int chk_epoch = 0;
   float *d_sk = nullptr;        // split-K partial tiles + flags
   size_t sk_bytes = 0;
   int sk_epoch = 0;
@@ -233,6 +238,13 @@ PlanInput make_plan_input(int num_sms, int CG, int BN, int K, const KernelParams
   in.max_slices = (force == 0 || (p.tiles_c > 0 && force <= 1)) ? 1 : 8;
   in.force_slices = force > 1 ? static_cast<int>(force) : 0;
   in.slab_bytes = static_cast<size_t>(CG) * kBM * BN * sizeof(float);
+  // concurrent encode: checksum items cannot start before the pre-pass has streamed B once (~2.5 TB/s while it shares
+  // the machine with the GEMM); one tile-time is num_kb k-blocks of ~512 cycles at ~1.5 GHz
+  in.chk_release = 0.0;
+  if (p.tiles_c > 0 && dbg("enc_overlap", 1) != 0) {
+    const double enc_us = 4.0 * static_cast<double>(p.N) * K / 2.5e6 + 4.0;
+    in.chk_release = enc_us / (in.num_kb * 512.0 / 1500.0);
+  }
   return in;
 }
 
@@ -329,26 +341,56 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     if (rc) return rc;
     if (h->d_chk != chk_before) h->chk_for_b = nullptr;  // reallocated: the cached encode is gone
     const size_t out_floats = static_cast<size_t>(M) * p.n_chk_cols;
-    rc = ensure_buf(h, &h->d_chk_out, &h->chk_out_bytes, (out_floats + n_slabs) * sizeof(float));
+    const size_t n_flags = static_cast<size_t>(n_slabs) * p.tiles_c;
+    const float *out_before = h->d_chk_out;
+    rc = ensure_buf(h, &h->d_chk_out, &h->chk_out_bytes, 65536 + out_floats * sizeof(float));
     if (rc) return rc;
-    p.chk_out = h->d_chk_out;
-    p.chk_flags = reinterpret_cast<int *>(h->d_chk_out + out_floats);
+    if (n_flags * sizeof(int) > 65536) return FTSGEMM_ERR_UNSUPPORTED;
+    p.chk_flags = reinterpret_cast<int *>(h->d_chk_out);  // fixed location: stale flags never equal a new epoch
+    p.chk_out = h->d_chk_out + 65536 / sizeof(float);
+    if (h->d_chk_out != out_before || h->chk_epoch > (1 << 30)) {
+      FT_CUDA(h, cudaMemsetAsync(p.chk_flags, 0, 65536, stream));
+      h->chk_epoch = 0;
+    }
+    p.chk_epoch = ++h->chk_epoch;
+    p.dbg_flags = static_cast<int>(dbg("ft_dbg", 0)) & 1;
     const bool reuse = o.reuse_b_checksums && h->chk_for_b == dB && h->chk_n == N && h->chk_k == K && h->chk_bn == BN;
+    p.enc_done = nullptr;
     if (!reuse) {
       const int J = BN >= 128 ? BN / 128 : 0;  // float4 loads per lane and k-row (0: narrow tile, scalar path)
       const int kw = kEncLoads / (J > 0 ? J : 1);
-      dim3 grid(p.tiles_n, (K + kEncWarps * kw - 1) / (kEncWarps * kw));
+      const int k_groups = (K + kEncWarps * kw - 1) / (kEncWarps * kw);
       const int rounding = static_cast<int>(dbg("enc_rounding", 0));
+      const bool overlap = dbg("enc_overlap", 1) != 0;
+      cudaStream_t es = stream;
+      int grid = p.tiles_n * k_groups;
+      int *done = nullptr;
+      int epoch = 0;
+      if (overlap) {
+        // Fork: the pre-pass runs on the handle's own stream, concurrently with the GEMM kernel launched below.  Its
+        // persistent grid (ONE block of 256 threads x <= 64 registers per SM, no shared memory) fits next to the
+        // resident GEMM CTA (256 x 168 registers, 226 KB) whichever kernel the hardware places first, and it never
+        // waits for the GEMM, so there is no circular wait; the GEMM's checksum items spin (with a trap watchdog) on
+        // the completion flag.
+        FT_CUDA(h, cudaEventRecord(h->ev_fork, stream));
+        FT_CUDA(h, cudaStreamWaitEvent(h->enc_stream, h->ev_fork, 0));
+        es = h->enc_stream;
+        if (grid > h->num_sms) grid = h->num_sms;
+        done = h->d_enc_done;
+        epoch = ++h->enc_epoch;
+        if (h->enc_epoch > (1 << 30)) h->enc_epoch = 0;
+        p.enc_done = done;
+        p.enc_epoch = epoch;
+      }
       if (J == 2)
-        encode_b_kernel<2><<<grid, kEncWarps * 32, 0, stream>>>(dB, N, K, N, BN, h->d_chk, chk_ld, rounding, p.chk_flags, n_slabs);
+        encode_b_kernel<2><<<grid, kEncWarps * 32, 0, es>>>(dB, N, K, N, BN, h->d_chk, chk_ld, rounding, p.tiles_n, k_groups, done, epoch);
       else if (J == 1)
-        encode_b_kernel<1><<<grid, kEncWarps * 32, 0, stream>>>(dB, N, K, N, BN, h->d_chk, chk_ld, rounding, p.chk_flags, n_slabs);
+        encode_b_kernel<1><<<grid, kEncWarps * 32, 0, es>>>(dB, N, K, N, BN, h->d_chk, chk_ld, rounding, p.tiles_n, k_groups, done, epoch);
       else
-        encode_b_kernel<0><<<grid, kEncWarps * 32, 0, stream>>>(dB, N, K, N, BN, h->d_chk, chk_ld, rounding, p.chk_flags, n_slabs);
+        encode_b_kernel<0><<<grid, kEncWarps * 32, 0, es>>>(dB, N, K, N, BN, h->d_chk, chk_ld, rounding, p.tiles_n, k_groups, done, epoch);
       FT_CUDA(h, cudaGetLastError());
+      if (overlap) FT_CUDA(h, cudaEventRecord(h->ev_join, h->enc_stream));
       h->chk_for_b = dB; h->chk_n = N; h->chk_k = K; h->chk_bn = BN;
-    } else {
-      FT_CUDA(h, cudaMemsetAsync(p.chk_flags, 0, n_slabs * sizeof(int), stream));
     }
     p.chk_box_bytes = BN / CG * kBK * static_cast<int>(sizeof(float));
     if (allow3d) {
@@ -412,10 +454,11 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     p.sk_epoch = ++h->sk_epoch;
   }
   h->last_stream = stream;
+  int lrc = FTSGEMM_ERR_UNSUPPORTED;
 #define FT_DISPATCH(bn, cg)                                                          \
   if (BN == bn && CG == cg)                                                          \
-    return ft ? launch_tc<bn, true, cg>(h, tmA, tmB, tmC, p, units, stream)          \
-              : launch_tc<bn, false, cg>(h, tmA, tmB, tmC, p, units, stream);
+    lrc = ft ? launch_tc<bn, true, cg>(h, tmA, tmB, tmC, p, units, stream)           \
+             : launch_tc<bn, false, cg>(h, tmA, tmB, tmC, p, units, stream);
   FT_DISPATCH(32, 1)
   FT_DISPATCH(64, 1)
   FT_DISPATCH(128, 1)
@@ -423,7 +466,9 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
   FT_DISPATCH(128, 2)
   FT_DISPATCH(256, 2)
 #undef FT_DISPATCH
-  return FTSGEMM_ERR_UNSUPPORTED;
+  // join: later work on the caller's stream (the next call's encode, a change of B) is ordered after the pre-pass
+  if (p.enc_done != nullptr) FT_CUDA(h, cudaStreamWaitEvent(stream, h->ev_join, 0));
+  return lrc;
 }
 
 int run_cublas(ftsgemm_handle_t h, bool tf32, int M, int N, int K, const float *dA, const float *dB, float *dC,
@@ -578,6 +623,14 @@ int ftsgemm_create(ftsgemm_handle_t *out) {
     delete h;
     return FTSGEMM_ERR_CUBLAS;
   }
+  if (cudaStreamCreateWithFlags(&h->enc_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaMalloc(&h->d_enc_done, 2 * sizeof(int)) != cudaSuccess ||
+      cudaMemset(h->d_enc_done, 0, 2 * sizeof(int)) != cudaSuccess) {
+    ftsgemm_destroy(h);
+    return FTSGEMM_ERR_CUDA;
+  }
   if (cudaMalloc(&h->d_stats, sizeof(DeviceStats)) != cudaSuccess ||
       cudaMemset(h->d_stats, 0, sizeof(DeviceStats)) != cudaSuccess ||
       cudaMalloc(&h->d_verify, 4 * sizeof(double)) != cudaSuccess) {
@@ -596,6 +649,10 @@ int ftsgemm_destroy(ftsgemm_handle_t h) {
   cudaFree(h->d_chk);
   cudaFree(h->d_chk_out);
   cudaFree(h->d_sk);
+  cudaFree(h->d_enc_done);
+  if (h->enc_stream) cudaStreamDestroy(h->enc_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   for (auto &kv : h->plans) {
     cudaFree(kv.second.d_items);
     cudaFree(kv.second.d_off);

@@ -95,7 +95,10 @@ struct KernelParams {
                         // sized to the checksum columns that exist, so checksum items load less than data tiles)
   int n_chk_cols;       // tiles_n * kChkPerTile
   float *chk_out;       // M x n_chk_cols, column-major (ld = M): expected checksums r1/r2 (hi, lo each)
-  int *chk_flags;       // one counter per 32-row slab; == tiles_c once that slab's checksums are published
+  int *chk_flags;       // [slab * tiles_c + c] = chk_epoch once checksum tile-column c of that 32-row slab is published
+  int chk_epoch;
+  const int *enc_done;  // != nullptr: the encode pre-pass runs CONCURRENTLY on another stream; *enc_done == enc_epoch
+  int enc_epoch;        //             once the checksum vectors are complete (only checksum items wait for it)
   float tau_abs, tau_rel;
   int detect_only;
   int inject_mode;
@@ -303,12 +306,14 @@ __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr
   }
   // ---- expected checksums published by the checksum tile-columns (wait for this 32-row slab's flag) ----
   {
-    const int *flag = p.chk_flags + (m0_cta >> 5) + q;
+    const int *flag = p.chk_flags + ((m0_cta >> 5) + q) * p.tiles_c;
     if (lane == 0) {
-      unsigned spins = 0;
-      while (ld_acquire(flag) < p.tiles_c) {
-        __nanosleep(64);
-        if (++spins > (1u << 24)) __trap();
+      for (int c = 0; c < p.tiles_c; ++c) {
+        unsigned spins = 0;
+        while (ld_acquire(flag + c) != p.chk_epoch) {
+          __nanosleep(64);
+          if (++spins > (1u << 24)) __trap();
+        }
       }
     }
     __syncwarp();
@@ -555,6 +560,18 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int nb0 = (b_is_chk ? tc.n_blk * chk_cols_per_tile(BN) : tc.n_blk * BN) +
                       static_cast<int>(cta_rank) * (n_eff / CG);  // this CTA's share of B rows
       const CUtensorMap *tmb = b_is_chk ? &tmChk : &tmB;
+      if (FT && b_is_chk && p.enc_done != nullptr) {
+        // the encode pre-pass may still be running on its own stream: checksum items (and only they) wait for it
+        if (lane == 0) {
+          unsigned spins = 0;
+          while (ld_acquire(p.enc_done) != p.enc_epoch) {
+            __nanosleep(128);
+            if (++spins > (1u << 23)) __trap();
+          }
+        }
+        __syncwarp();
+        ptx::fence_proxy_async();
+      }
       // The loop body is specialised OUTSIDE the k loop: with 3-D tensor maps a stage is exactly two TMA instructions
       // (predicated-off TMA instructions still cost issue time on the single producer thread).
       const bool all3d = (p.tma3d & 1) && (p.tma3d & (b_is_chk ? 4 : 2));
@@ -739,7 +756,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         store_tile<BN>(taddr, p.chk_out + m, m < p.M, n0, n_hi, p.M, 1.0f, 0.0f, -1, 0.0f);
         __threadfence();
         __syncwarp();
-        if (lane == 0) atomicAdd(p.chk_flags + (m0_cta >> 5) + q, 1);
+        if (lane == 0) atomicExch(p.chk_flags + ((m0_cta >> 5) + q) * p.tiles_c + tc.n_blk, p.chk_epoch);
       } else {
         int fix_col = -1;
         float fix_val = 0.0f;
@@ -803,17 +820,19 @@ constexpr int kEncLoads = 8;  // 16-byte loads in flight per lane
 // magnitude -- and only the 32-way cross-lane reduction runs in FP64 (10 DADD per row).  All kEncLoads loads of a lane
 // are issued before the first is consumed; 4 blocks (32 warps) are resident per SM.  The kernel also clears the checksum
 // slab flags of the GEMM launch that follows it in the stream (one memset launch less).
+// done != nullptr: the kernel is launched with a 1-D persistent grid (a few blocks per SM at most, so that it fits next
+// to the resident GEMM CTAs) on its own stream; the last block to finish publishes *done = epoch.
 template <int J>
 __global__ void __launch_bounds__(kEncWarps * 32, 4)
 encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, float *__restrict__ chk, int chk_ld,
-                int rounding, int *__restrict__ flags, int n_flags) {
+                int rounding, int tiles_n, int k_groups, int *__restrict__ done, int epoch) {
   constexpr int KW = kEncLoads / (J > 0 ? J : 1);
-  if (flags != nullptr && blockIdx.x == 0 && blockIdx.y == 0)
-    for (int i = threadIdx.x; i < n_flags; i += blockDim.x) flags[i] = 0;
-  const int t = blockIdx.x;
-  const int n0 = t * BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kbase = (blockIdx.y * kEncWarps + warp) * KW;
+  const int total = tiles_n * k_groups;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+  const int t = item % tiles_n;        // tile fastest: concurrently running blocks read neighbouring columns
+  const int n0 = t * BN;
+  const int kbase = ((item / tiles_n) * kEncWarps + warp) * KW;
   float e[KW], w[KW];
 #pragma unroll
   for (int u = 0; u < KW; ++u) e[u] = w[u] = 0.0f;
@@ -869,6 +888,19 @@ encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, floa
       split2_tf32(dw, wh, wl);
       const float val = lane == 0 ? eh : lane == 1 ? el : lane == 2 ? wh : wl;
       chk[static_cast<size_t>(k) * chk_ld + t * kChkPerTile + lane] = val;
+    }
+  }
+  }  // item loop
+  if (done != nullptr) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int prev = atomicAdd(done + 1, 1);
+      if (prev == static_cast<int>(gridDim.x) - 1) {
+        done[1] = 0;
+        __threadfence();
+        atomicExch(done, epoch);
+      }
     }
   }
 }

@@ -44,6 +44,7 @@ struct PlanInput {
   int num_kb;           // k-blocks per tile
   int tiles_m;          // checksum tile t belongs to checksum tile-column t / tiles_m
   std::vector<double> chk_col_cost;  // tile-times of one tile of each checksum tile-column (narrowed UMMA N / BN)
+  double chk_release = 0.0;          // tile-times before checksum items can start (encode pre-pass running concurrently)
   double slice_overhead;// tile-times added to every split item (partial-sum round trip)
   int max_slices;       // 1 disables the tail
   int force_slices;     // > 1: use exactly this S on the best H (tests)
@@ -66,9 +67,10 @@ inline double schedule(const PlanInput &in, int H, int S, bool head_first, Plan 
   std::vector<std::vector<PlanItem>> lists;
   if (out) lists.resize(in.units);
   double makespan = 0.0;
-  auto give = [&](const PlanItem &it, double cost) {
+  auto give = [&](const PlanItem &it, double cost, double release = 0.0) {
     LU lu = pq.top();
     pq.pop();
+    if (lu.first < release) lu.first = release;  // the unit idles until the item's input exists
     lu.first += cost;
     if (lu.first > makespan) makespan = lu.first;
     if (out) lists[lu.second].push_back(it);
@@ -93,7 +95,7 @@ inline double schedule(const PlanInput &in, int H, int S, bool head_first, Plan 
     }
   };
   for (int t = 0; t < in.n_chk_tiles; ++t)
-    give(PlanItem{t, 0, in.num_kb, 0, 0, -1}, in.chk_col_cost[static_cast<size_t>(t / in.tiles_m)]);
+    give(PlanItem{t, 0, in.num_kb, 0, 0, -1}, in.chk_col_cost[static_cast<size_t>(t / in.tiles_m)], in.chk_release);
   if (head_first) {
     give_split();
     give_whole();

@@ -98,6 +98,36 @@ def test_ft_equals_plain_bitwise_when_fault_free(cuda, ft, dev):
         assert np.abs(a - b).max() < 1e-4 * np.abs(a).max()
 
 
+def test_encode_overlap_and_serial_paths_agree(cuda, ft, dev):
+    """The encode pre-pass normally runs concurrently with the GEMM kernel on the handle's own stream (checksum items wait
+    on a flag); the serial in-stream path and the cached-checksum path must give bit-identical results and verdicts."""
+    rng = np.random.default_rng(5)
+    M, N, K = 1024, 1280, 768
+    A, B = _rand(rng, M * K), _rand(rng, N * K)
+    C0 = rng.standard_normal(M * N).astype(np.float32)
+    faults = [{"row": 77, "col": 300, "xor": 1 << 29}, {"row": 900, "col": 1279, "add": -55.0}]
+    outs = []
+    for overlap in (1, 0):
+        try:
+            ft.debug_set("enc_overlap", overlap)
+            dev.stats()
+            for rep in range(3):  # back-to-back launches reuse the flags / epochs
+                got = _run(cuda, dev, 31, M, N, K, A, B, C0, 1.0, -1.5, opts=ft.make_opts(faults=faults))
+            st = dev.stats()
+            assert st["detected"] == 6 and st["corrected"] == 6 and st["uncorrectable"] == 0
+            outs.append(got)
+        finally:
+            ft.debug_set("enc_overlap", -1)
+    assert np.array_equal(outs[0], outs[1])
+    dA, dB = cuda.from_numpy(A).cuda(), cuda.from_numpy(B).cuda()
+    dC = cuda.from_numpy(C0.copy()).cuda()
+    dev.run(31, M, N, K, dA, dB, dC, 1.0, -1.5, ft.make_opts(faults=faults))
+    dC2 = cuda.from_numpy(C0.copy()).cuda()
+    dev.run(31, M, N, K, dA, dB, dC2, 1.0, -1.5, ft.make_opts(faults=faults, reuse_b_checksums=True))
+    cuda.cuda.synchronize()
+    assert cuda.equal(dC, dC2) and np.array_equal(dC.cpu().numpy(), outs[0])
+
+
 @pytest.mark.parametrize("slices", [2, 3, 5])
 def test_split_k_head_forced(cuda, ft, dev, oracle, slices):
     """Force the split-K head (contributor dump + finisher fold-in through TMEM) on shapes where the planner would not
