@@ -241,7 +241,7 @@ PlanInput make_plan_input(int num_sms, int CG, int BN, int K, const KernelParams
   // concurrent encode: checksum items cannot start before the pre-pass has streamed B once (~2.5 TB/s while it shares
   // the machine with the GEMM); one tile-time is num_kb k-blocks of ~512 cycles at ~1.5 GHz
   in.chk_release = 0.0;
-  if (p.tiles_c > 0 && dbg("enc_overlap", 1) != 0) {
+  if (p.tiles_c > 0 && dbg("enc_overlap", 0) != 0) {
     const double enc_us = 4.0 * static_cast<double>(p.N) * K / 2.5e6 + 4.0;
     in.chk_release = enc_us / (in.num_kb * 512.0 / 1500.0);
   }
@@ -361,7 +361,10 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
       const int kw = kEncLoads / (J > 0 ? J : 1);
       const int k_groups = (K + kEncWarps * kw - 1) / (kEncWarps * kw);
       const int rounding = static_cast<int>(dbg("enc_rounding", 0));
-      const bool overlap = dbg("enc_overlap", 1) != 0;
+      // Experimental (off by default): measured on B200 the concurrent pre-pass is correct but ~9 % SLOWER end to end
+      // (622 vs 685 TFLOP/s at 4096^3, 702 vs 767 at 8192^3): it steals issue slots / L2 bandwidth from the GEMM, runs 2-3x
+      // longer than alone, and the cross-stream fork/join costs more than the ~18 us it hides.  Kept for tests.
+      const bool overlap = dbg("enc_overlap", 0) != 0;
       cudaStream_t es = stream;
       int grid = p.tiles_n * k_groups;
       int *done = nullptr;
