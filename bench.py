@@ -160,10 +160,33 @@ def run_reference_arm(args):
            "cpu_baseline": {"value": round(gf, 4), "unit": "GFLOPS", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": round(gf, 4), "unit": "GFLOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    _emit(out)
+
+
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: anything libraries print there (NCCL's version banner under torchrun) goes to
+    stderr instead."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, line)
+    else:
+        os.write(_JSON_FD, line)
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=500)
@@ -354,7 +377,7 @@ def main():
                 ms = timed(lambda: ft.run(kid, s, s, s, bA, bB, bC, alpha, beta, opts), reps) / reps
                 row += f"{2.0 * s ** 3 / ms / 1e6:8.0f}|"
             sys.stderr.write(row + "\n")
-    print(json.dumps(out))
+    _emit(out)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -81,7 +81,7 @@ EXPORTED_SYMBOLS = [
     "ftsgemm_create", "ftsgemm_destroy", "ftsgemm_abi_version", "ftsgemm_error_string", "ftsgemm_last_cuda_error",
     "ftsgemm_default_opts", "ftsgemm_kernel_table", "ftsgemm_kernel_lookup", "ftsgemm_run", "ftsgemm_get_stats",
     "ftsgemm_run_host", "ftsgemm_baseline", "ftsgemm_verify", "ftsgemm_debug_set", "ftsgemm_debug_schedule",
-    "ftsgemm_verify_bad_count",
+    "ftsgemm_verify_bad_count", "ftsgemm_debug_trace",
 ]
 
 _lib = None
@@ -122,6 +122,7 @@ def lib():
         L.ftsgemm_verify_bad_count.argtypes = [vp]
         L.ftsgemm_verify_bad_count.restype = C.c_longlong
         L.ftsgemm_debug_schedule.argtypes = [ip, ip, ip, ip, ip, C.POINTER(C.c_int), C.POINTER(C.c_int), ip]
+        L.ftsgemm_debug_trace.argtypes = [vp, C.POINTER(C.c_ulonglong), ip]
         _lib = L
     return _lib
 
@@ -246,6 +247,28 @@ class FtSgemm:
         s = Stats()
         self._run_checked(lib().ftsgemm_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def debug_trace(self):
+        """Timeline of the last launch made under debug_set("trace", 1): list (per unit) of item dicts, times in ns."""
+        cap = 160 * 512
+        buf = (C.c_ulonglong * cap)()
+        n = lib().ftsgemm_debug_trace(self._h, buf, cap)
+        if n < 0:
+            self._run_checked(n)
+        keys = ("prod_start", "prod_end", "mma_start", "mma_end", "acc_done", "check_done", "epi_end")
+        out = []
+        for u in range(n):
+            items = []
+            for i in range(64):
+                r = buf[(u * 64 + i) * 8:(u * 64 + i) * 8 + 8]
+                if r[4] == 0:
+                    break
+                d = dict(zip(keys, r[:7]))
+                d["tile"] = r[7] & 0xFFFFFF
+                d["kind"] = r[7] >> 24
+                items.append(d)
+            out.append(items)
+        return out
 
     # verify_matrix (utils/utils.cu:61-77) on device buffers
     def verify(self, d_ref, d_x, M: int, N: int, stream=None):

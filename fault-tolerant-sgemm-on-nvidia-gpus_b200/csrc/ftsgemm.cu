@@ -113,6 +113,8 @@ struct ftsgemm_handle_s {
   float *d_sk = nullptr;        // split-K partial tiles + flags
   size_t sk_bytes = 0;
   int sk_epoch = 0;
+  unsigned long long *d_trace = nullptr;  // debug timeline (ftsgemm_debug_trace), allocated on first use
+  int trace_units = 0;
   float *d_stage[3] = {nullptr, nullptr, nullptr};  // run_host staging A, B, C
   size_t stage_bytes[3] = {0, 0, 0};
   double *d_verify = nullptr;   // {first_bad (as long long), num, den}
@@ -456,6 +458,18 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     }
     p.sk_epoch = ++h->sk_epoch;
   }
+  if (dbg("trace", 0) != 0) {
+    const int cap = 64;
+    if (h->d_trace == nullptr || h->trace_units < units) {
+      if (h->d_trace) FT_CUDA(h, cudaFree(h->d_trace));
+      h->d_trace = nullptr;
+      FT_CUDA(h, cudaMalloc(&h->d_trace, static_cast<size_t>(units) * cap * 8 * sizeof(unsigned long long)));
+      h->trace_units = units;
+    }
+    FT_CUDA(h, cudaMemsetAsync(h->d_trace, 0, static_cast<size_t>(units) * cap * 8 * sizeof(unsigned long long), stream));
+    p.trace = h->d_trace;
+    p.trace_cap = cap;
+  }
   h->last_stream = stream;
   int lrc = FTSGEMM_ERR_UNSUPPORTED;
 #define FT_DISPATCH(bn, cg)                                                          \
@@ -594,6 +608,16 @@ int ftsgemm_debug_schedule(int kernel_id, int M, int N, int K, int num_sms, int 
   return n;
 }
 
+int ftsgemm_debug_trace(ftsgemm_handle_t h, unsigned long long *out, int cap_u64) {
+  if (!h || !out) return FTSGEMM_ERR_INVALID_ARG;
+  if (!h->d_trace) return 0;
+  const int n = h->trace_units * 64 * 8;
+  if (cap_u64 < n) return FTSGEMM_ERR_INVALID_ARG;
+  FT_CUDA(h, cudaDeviceSynchronize());
+  FT_CUDA(h, cudaMemcpy(out, h->d_trace, static_cast<size_t>(n) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return h->trace_units;
+}
+
 int ftsgemm_debug_set(const char *key, long long value) {
   if (!key) return FTSGEMM_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(g_dbg_mu);
@@ -652,6 +676,7 @@ int ftsgemm_destroy(ftsgemm_handle_t h) {
   cudaFree(h->d_chk);
   cudaFree(h->d_chk_out);
   cudaFree(h->d_sk);
+  cudaFree(h->d_trace);
   cudaFree(h->d_enc_done);
   if (h->enc_stream) cudaStreamDestroy(h->enc_stream);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);

@@ -107,7 +107,20 @@ struct KernelParams {
   int n_faults;
   DeviceFault faults[kMaxFaults];
   DeviceStats *stats;
+  // debug timeline (ftsgemm_debug_trace): per unit and item 8 x u64 = %globaltimer ns at {producer start, producer end,
+  // MMA start, MMA issue end, epilogue start (accumulator complete), after check/fold, epilogue end}, tile | kind << 24
+  unsigned long long *trace;
+  int trace_cap;        // items recorded per unit
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_put(const KernelParams &p, int unit, int item, int slot, unsigned long long v) {
+  if (p.trace != nullptr && item < p.trace_cap) p.trace[(static_cast<size_t>(unit) * p.trace_cap + item) * 8 + slot] = v;
+}
 
 template <int BN, bool FT, int CG>
 struct TileCfg {
@@ -552,7 +565,9 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t phase = 0;
     SegIter it(p, unit);
     Segment sg;
+    int item_idx = -1;
     while (it.next(sg)) {
+      ++item_idx;
       const TileCoord tc = decode_tile(p, sg.tile);
       const int m0 = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;        // this CTA's 128 rows of A
       const bool b_is_chk = FT && tc.is_chk;
@@ -572,6 +587,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
         ptx::fence_proxy_async();
       }
+      if (p.trace != nullptr && is_leader && lane == 0) trace_put(p, unit, item_idx, 0, globaltimer_ns());
       // The loop body is specialised OUTSIDE the k loop: with 3-D tensor maps a stage is exactly two TMA instructions
       // (predicated-off TMA instructions still cost issue time on the single producer thread).
       const bool all3d = (p.tma3d & 1) && (p.tma3d & (b_is_chk ? 4 : 2));
@@ -653,6 +669,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       }
+      if (p.trace != nullptr && is_leader && lane == 0) trace_put(p, unit, item_idx, 1, globaltimer_ns());
     }
   } else if (warp == 1 && is_leader) {
     // ===================================================================== MMA issuer (leader CTA only)
@@ -668,7 +685,9 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t acc_phase = 0;
     SegIter it(p, unit);
     Segment sg;
+    int item_idx = -1;
     while (it.next(sg)) {
+      ++item_idx;
       uint32_t idesc_t = idesc;
       if (FT) {
         const TileCoord tc = decode_tile(p, sg.tile);
@@ -676,6 +695,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       ptx::tc_fence_after();
+      if (p.trace != nullptr && lane == 0) trace_put(p, unit, item_idx, 2, globaltimer_ns());
       const uint32_t d_tmem = tmem_base + acc * BN;
       // Lean issue loop: a single thread runs dependent integer chains at ~1 instruction per 4-6 cycles, and four UMMAs
       // (one k-block) take only ~512 cycles, so the 64-bit descriptors are NOT rebuilt per UMMA: the high word
@@ -711,6 +731,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           phase ^= 1u;
         }
       }
+      if (p.trace != nullptr && lane == 0) trace_put(p, unit, item_idx, 3, globaltimer_ns());
       if (kAccStages == 2) {
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
@@ -728,7 +749,10 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     SegIter it(p, unit);
     Segment sg;
     const size_t ws_slab = static_cast<size_t>(kBM) * BN;  // floats per (unit, CTA) partial tile
+    int item_idx = -1;
+    const bool tracer = p.trace != nullptr && is_leader && q == 0 && lane == 0;
     while (it.next(sg)) {
+      ++item_idx;
       const TileCoord tc = decode_tile(p, sg.tile);
       const int m0_cta = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;
       const int n0 = (FT && tc.is_chk) ? tc.n_blk * chk_cols_per_tile(BN) : tc.n_blk * BN;
@@ -736,6 +760,10 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      if (tracer) {
+        trace_put(p, unit, item_idx, 4, globaltimer_ns());
+        trace_put(p, unit, item_idx, 7, static_cast<unsigned long long>(sg.tile) | (static_cast<unsigned long long>(sg.kind) << 24));
+      }
 
       if (sg.kind == 1) {
         // split-K contributor: park the raw partial sums of this slab for the unit that finishes the tile
@@ -761,11 +789,13 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int fix_col = -1;
         float fix_val = 0.0f;
         if (FT && !(p.dbg_flags & 1)) abft_check<BN>(p, taddr, q, lane, m, m0_cta, n0, tc.n_blk, fix_col, fix_val);
+        if (tracer) trace_put(p, unit, item_idx, 5, globaltimer_ns());
         store_tile<BN>(taddr, p.C + m, m < p.M, n0, p.N, p.ldc, p.alpha, p.beta, fix_col, fix_val);
       }
       // release this accumulator stage back to the MMA warp (of the leader CTA)
       ptx::tc_fence_before();
       __syncwarp();
+      if (tracer) trace_put(p, unit, item_idx, 6, globaltimer_ns());
       if (lane == 0) {
         if (CG == 2) ptx::mbar_arrive_cluster(tempty_leader + 8u * acc);
         else ptx::mbar_arrive(tempty_bar(acc));

@@ -174,6 +174,10 @@ int ftsgemm_debug_set(const char *key, long long value);
  * rows of 9 ints {unit, tile, is_chk, m_blk, n_blk, kb_begin, kb_end, kind(0 whole,1 contributor,2 finisher), slice};
  * hdr[7] = {units, num_tiles, n_chk_tiles, sk_tiles, num_kb, cta_group, sk_slices}.  Needs no GPU. */
 int ftsgemm_debug_schedule(int kernel_id, int M, int N, int K, int num_sms, int *hdr, int *rows, int cap);
+/* Device timeline of the last tensor-core launch made with ftsgemm_debug_set("trace", 1): per work unit 64 items x 8
+ * u64 = %globaltimer ns {producer start, producer end, MMA start, MMA issue end, accumulator complete, check done,
+ * epilogue end, tile | kind << 24}.  Returns the number of units (out must hold units * 512 u64), 0 if none. */
+int ftsgemm_debug_trace(ftsgemm_handle_t h, unsigned long long *out, int cap_u64);
 
 #ifdef __cplusplus
 }
