@@ -267,6 +267,9 @@ class FtSgemm:
                 d["tile"] = r[7] & 0xFFFFFF
                 d["kind"] = r[7] >> 24
                 items.append(d)
+            if items:
+                items[0]["enc_end"] = buf[(u * 64 + 63) * 8]  # helper warps finished their share of the in-kernel encode
+                items[0]["enc_start"] = buf[(u * 64 + 63) * 8 + 1]
             out.append(items)
         return out
 

@@ -105,10 +105,8 @@ struct ftsgemm_handle_s {
     bool uploaded = false;
   };
   std::map<std::array<long long, 6>, CachedPlan> plans;  // key: kernel id, M, N, K, units, forced slices
-  cudaStream_t enc_stream = nullptr;   // the encode pre-pass runs here, concurrently with the GEMM kernel
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int *d_enc_done = nullptr;    // {done epoch, block counter}
-  int enc_epoch = 0;
+  int *d_enc_count = nullptr;   // helper warps that have finished their share of the in-kernel encode (monotonic)
+  int enc_total = 0;            // host mirror of the value the counter reaches after the last launch
   int chk_epoch = 0;
   float *d_sk = nullptr;        // split-K partial tiles + flags
   size_t sk_bytes = 0;
@@ -210,9 +208,14 @@ int launch_tc(ftsgemm_handle_t h, const CUtensorMap &tmA, const CUtensorMap &tmB
 }
 
 // Planner input for one launch (tile grid already set by plan_tiles).
+// Measured on B200 (device timeline, profiles/r01_trace_*): a checksum tile's main loop takes 0.57-0.58 of a data tile's
+// whatever its UMMA N (it is bound by the A-operand feed, L2 -> shared memory), one k-block of a 256x256 CTA-pair tile
+// takes ~0.33 us, an item costs ~1.5 us of pipeline fill + drain, and a parked accumulator is back in the next owner's
+// tensor memory ~8 us after the piece's last UMMA.
 template <int BNv, int CGv>
 void chk_costs(const KernelParams &p, std::vector<double> *out) {
-  for (int c = 0; c < p.tiles_c; ++c) out->push_back(static_cast<double>(chk_tile_width<BNv, CGv>(p, c)) / BNv);
+  for (int c = 0; c < p.tiles_c; ++c)
+    out->push_back(std::max(0.58, static_cast<double>(chk_tile_width<BNv, CGv>(p, c)) / BNv));
 }
 
 PlanInput make_plan_input(int num_sms, int CG, int BN, int K, const KernelParams &p) {
@@ -229,23 +232,24 @@ PlanInput make_plan_input(int num_sms, int CG, int BN, int K, const KernelParams
   else if (BN == 128) chk_costs<128, 2>(p, &in.chk_col_cost);
   else if (CG == 1) chk_costs<256, 1>(p, &in.chk_col_cost);
   else chk_costs<256, 2>(p, &in.chk_col_cost);
-  // measured on B200: a split item costs ~10 us extra (partial-sum round trip through L2, latency-bound), i.e.
-  // ~15k SM cycles, whatever K is; expressed in tile-times (one k-block = 4 UMMAs of ~128 cycles)
-  in.slice_overhead = static_cast<double>(dbg("slice_overhead_cycles", 15000)) / (static_cast<double>(in.num_kb) * 512.0);
-  const long long force = dbg("splitk", -2);  // -2 auto, 0 off, s > 1: force s slices
-  // ABFT tiles are never K-split: the tensor core's FP32 accumulation has a small systematic (truncation-like) bias that
-  // is the same for a data row and its checksum as long as both accumulate over the same k sequence; restarting the data
-  // accumulation at a slice boundary breaks that cancellation (measured: fault-free residual 7.6e-7 -> 5.3e-6 of sum|acc|
-  // at K = 8192, profiles/r01_probe8_residual_vs_splitk.jsonl), which would eat the detection margin.
-  in.max_slices = (force == 0 || (p.tiles_c > 0 && force <= 1)) ? 1 : 8;
+  const double tile_us = in.num_kb * 0.333 * (static_cast<double>(BN) * CG / 512.0 < 0.25 ? 0.25 : static_cast<double>(BN) * CG / 512.0);
+  in.item_overhead = static_cast<double>(dbg("item_overhead_ns", 1500)) * 1e-3 / tile_us;
+  in.park_latency = static_cast<double>(dbg("park_latency_ns", 8000)) * 1e-3 / tile_us;
+  in.seed_overhead = static_cast<double>(dbg("seed_overhead_ns", 2000)) * 1e-3 / tile_us;
+  const long long force = dbg("splitk", -2);  // -2 auto, 0 off, s > 1: force s equal pieces
+  in.max_slices = force == 0 ? 1 : 2;
   in.force_slices = force > 1 ? static_cast<int>(force) : 0;
   in.slab_bytes = static_cast<size_t>(CG) * kBM * BN * sizeof(float);
-  // concurrent encode: checksum items cannot start before the pre-pass has streamed B once (~2.5 TB/s while it shares
-  // the machine with the GEMM); one tile-time is num_kb k-blocks of ~512 cycles at ~1.5 GHz
+  // operands larger than ~3/4 of the 126 MB L2: keep the units in k-lockstep (plan.h)
+  const long long lock = dbg("lockstep", -2);
+  in.lockstep = lock >= 0 ? static_cast<int>(lock)
+                          : (4.0 * K * (static_cast<double>(p.M) + p.N) > 96.0 * 1024 * 1024 ? 1 : 0);
+  // in-kernel encode: checksum items cannot start before the helper warps have streamed B once (~3 TB/s in the
+  // background of the first main loops)
   in.chk_release = 0.0;
-  if (p.tiles_c > 0 && dbg("enc_overlap", 0) != 0) {
-    const double enc_us = 4.0 * static_cast<double>(p.N) * K / 2.5e6 + 4.0;
-    in.chk_release = enc_us / (in.num_kb * 512.0 / 1500.0);
+  if (p.tiles_c > 0 && dbg("enc_mode", 1) == 0) {
+    const double enc_us = 4.0 * static_cast<double>(p.N) * K / 3.0e6 + 3.0;
+    in.chk_release = enc_us / tile_us;
   }
   return in;
 }
@@ -316,6 +320,8 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
 
   CUtensorMap tmA, tmB, tmC;
   const bool allow3d = dbg("tma3d", 1) != 0;
+  bool need_encode = false;
+  int chk_ld_v = 0;
   int rc;
   if (allow3d && M % kAtomMN == 0) {
     rc = make_tmap_3d(h, &tmA, dA, M, K, M, kBM / kAtomMN);
@@ -334,7 +340,7 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
   tmC = tmB;
   if (ft) {
     // checksum vectors of B: 8 columns per N-tile, appended to B as extra tile-columns of the same GEMM
-    p.dbg_flags = static_cast<int>(dbg("ft_dbg", 0)) & 1;
+    p.dbg_flags = static_cast<int>(dbg("ft_dbg", 0)) & 5;
     const int chk_ld = (p.n_chk_cols + kAtomMN - 1) / kAtomMN * kAtomMN;  // padded so the 3-D TMA view is exact; pad
                                                                           // columns are never stored (n_chk_cols mask)
     const int n_slabs = p.tiles_m * CG * (kBM / 32);
@@ -355,48 +361,22 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
       h->chk_epoch = 0;
     }
     p.chk_epoch = ++h->chk_epoch;
-    p.dbg_flags = static_cast<int>(dbg("ft_dbg", 0)) & 1;
+    p.dbg_flags = static_cast<int>(dbg("ft_dbg", 0)) & 5;
     const bool reuse = o.reuse_b_checksums && h->chk_for_b == dB && h->chk_n == N && h->chk_k == K && h->chk_bn == BN;
-    p.enc_done = nullptr;
-    if (!reuse) {
-      const int J = BN >= 128 ? BN / 128 : 0;  // float4 loads per lane and k-row (0: narrow tile, scalar path)
-      const int kw = kEncLoads / (J > 0 ? J : 1);
-      const int k_groups = (K + kEncWarps * kw - 1) / (kEncWarps * kw);
+    need_encode = !reuse;
+    chk_ld_v = chk_ld;
+    if (need_encode && dbg("enc_mode", 1) != 0) {
+      // stand-alone pre-pass in the caller's stream (the in-kernel encode is the default, see below)
       const int rounding = static_cast<int>(dbg("enc_rounding", 0));
-      // Experimental (off by default): measured on B200 the concurrent pre-pass is correct but ~9 % SLOWER end to end
-      // (622 vs 685 TFLOP/s at 4096^3, 702 vs 767 at 8192^3): it steals issue slots / L2 bandwidth from the GEMM, runs 2-3x
-      // longer than alone, and the cross-stream fork/join costs more than the ~18 us it hides.  Kept for tests.
-      const bool overlap = dbg("enc_overlap", 0) != 0;
-      cudaStream_t es = stream;
-      int grid = p.tiles_n * k_groups;
-      int *done = nullptr;
-      int epoch = 0;
-      if (overlap) {
-        // Fork: the pre-pass runs on the handle's own stream, concurrently with the GEMM kernel launched below.  Its
-        // persistent grid (ONE block of 256 threads x <= 64 registers per SM, no shared memory) fits next to the
-        // resident GEMM CTA (256 x 168 registers, 226 KB) whichever kernel the hardware places first, and it never
-        // waits for the GEMM, so there is no circular wait; the GEMM's checksum items spin (with a trap watchdog) on
-        // the completion flag.
-        FT_CUDA(h, cudaEventRecord(h->ev_fork, stream));
-        FT_CUDA(h, cudaStreamWaitEvent(h->enc_stream, h->ev_fork, 0));
-        es = h->enc_stream;
-        if (grid > h->num_sms) grid = h->num_sms;
-        done = h->d_enc_done;
-        epoch = ++h->enc_epoch;
-        if (h->enc_epoch > (1 << 30)) h->enc_epoch = 0;
-        p.enc_done = done;
-        p.enc_epoch = epoch;
-      }
-      if (J == 2)
-        encode_b_kernel<2><<<grid, kEncWarps * 32, 0, es>>>(dB, N, K, N, BN, h->d_chk, chk_ld, rounding, p.tiles_n, k_groups, done, epoch);
-      else if (J == 1)
-        encode_b_kernel<1><<<grid, kEncWarps * 32, 0, es>>>(dB, N, K, N, BN, h->d_chk, chk_ld, rounding, p.tiles_n, k_groups, done, epoch);
-      else
-        encode_b_kernel<0><<<grid, kEncWarps * 32, 0, es>>>(dB, N, K, N, BN, h->d_chk, chk_ld, rounding, p.tiles_n, k_groups, done, epoch);
+      const int grid = 4 * h->num_sms;
+#define FT_ENC(bn) \
+  if (BN == bn) encode_b_kernel<bn><<<grid, kEncWarps * 32, 0, stream>>>(dB, N, K, N, h->d_chk, chk_ld, rounding, p.tiles_n);
+      FT_ENC(32) FT_ENC(64) FT_ENC(128) FT_ENC(256)
+#undef FT_ENC
       FT_CUDA(h, cudaGetLastError());
-      if (overlap) FT_CUDA(h, cudaEventRecord(h->ev_join, h->enc_stream));
-      h->chk_for_b = dB; h->chk_n = N; h->chk_k = K; h->chk_bn = BN;
+      need_encode = false;
     }
+    if (!reuse) { h->chk_for_b = dB; h->chk_n = N; h->chk_k = K; h->chk_bn = BN; }
     p.chk_box_bytes = BN / CG * kBK * static_cast<int>(sizeof(float));
     if (allow3d) {
       // the checksum operand's box only spans the atoms that exist (e.g. 128 of 256 columns at N = 8192), so a
@@ -458,6 +438,25 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     }
     p.sk_epoch = ++h->sk_epoch;
   }
+  if (ft && dbg("enc_mode", 1) == 0) {
+    // In-kernel encode: the helper warps of every CTA stream their share of B while the first main loops run; checksum
+    // items wait until all of them have reported (monotonic counter, so a launch that reuses the vectors waits for
+    // nothing new).
+    if (h->enc_total > (1 << 30)) {
+      FT_CUDA(h, cudaMemsetAsync(h->d_enc_count, 0, sizeof(int), stream));
+      h->enc_total = 0;
+    }
+    p.enc_count = h->d_enc_count;
+    if (need_encode) {
+      p.enc_b = dB;
+      p.enc_ldb = N;
+      p.enc_out = h->d_chk;
+      p.enc_ld = chk_ld_v;
+      p.enc_rounding = static_cast<int>(dbg("enc_rounding", 0));
+      h->enc_total += units * CG * 4;
+    }
+    p.enc_target = h->enc_total;
+  }
   if (dbg("trace", 0) != 0) {
     const int cap = 64;
     if (h->d_trace == nullptr || h->trace_units < units) {
@@ -483,8 +482,6 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
   FT_DISPATCH(128, 2)
   FT_DISPATCH(256, 2)
 #undef FT_DISPATCH
-  // join: later work on the caller's stream (the next call's encode, a change of B) is ordered after the pre-pass
-  if (p.enc_done != nullptr) FT_CUDA(h, cudaStreamWaitEvent(stream, h->ev_join, 0));
   return lrc;
 }
 
@@ -585,6 +582,7 @@ int ftsgemm_debug_schedule(int kernel_id, int M, int N, int K, int num_sms, int 
   if (!v || v->info.engine != 1 || M <= 0 || N <= 0 || K <= 0 || num_sms <= 0) return FTSGEMM_ERR_INVALID_ARG;
   KernelParams p;
   memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
   plan_tiles(M, N, v->bn, v->cg, v->info.fault_tolerant != 0, &p);
   const PlanInput pin = make_plan_input(num_sms, v->cg, v->bn, K, p);
   const Plan plan = build_plan(pin);
@@ -650,11 +648,8 @@ int ftsgemm_create(ftsgemm_handle_t *out) {
     delete h;
     return FTSGEMM_ERR_CUBLAS;
   }
-  if (cudaStreamCreateWithFlags(&h->enc_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
-      cudaMalloc(&h->d_enc_done, 2 * sizeof(int)) != cudaSuccess ||
-      cudaMemset(h->d_enc_done, 0, 2 * sizeof(int)) != cudaSuccess) {
+  if (cudaMalloc(&h->d_enc_count, sizeof(int)) != cudaSuccess ||
+      cudaMemset(h->d_enc_count, 0, sizeof(int)) != cudaSuccess) {
     ftsgemm_destroy(h);
     return FTSGEMM_ERR_CUDA;
   }
@@ -677,10 +672,7 @@ int ftsgemm_destroy(ftsgemm_handle_t h) {
   cudaFree(h->d_chk_out);
   cudaFree(h->d_sk);
   cudaFree(h->d_trace);
-  cudaFree(h->d_enc_done);
-  if (h->enc_stream) cudaStreamDestroy(h->enc_stream);
-  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  cudaFree(h->d_enc_count);
   for (auto &kv : h->plans) {
     cudaFree(kv.second.d_items);
     cudaFree(kv.second.d_off);

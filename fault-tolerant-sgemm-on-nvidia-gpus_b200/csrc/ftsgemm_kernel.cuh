@@ -16,10 +16,13 @@
 //                             TMEM, two accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1
 //   warp 2   TMEM allocator
 //   warps 4-7 epilogue      : tcgen05.ld (lane = row), per-row ABFT detect / locate / correct, C = alpha*acc + beta*C
+//   warps 8-11 helpers      : (a) ENCODE of B in the background of the first tiles' main loops (the SM's LSU and issue
+//                             slots are idle while one thread feeds the tensor core), (b) seeding tensor memory with the
+//                             parked accumulator of the previous K-piece of a cut tile (plan.h)
 //
 // ABFT scheme.  With b~ = the TF32 value the tensor core actually consumes and J_t the columns
 // of N-tile t:
-//   encode    (pre-pass encode_b_kernel; reference ENCODE ft_sgemm_huge.cuh:150-168)
+//   encode    (helper warps of this kernel, or the pre-pass encode_b_kernel; reference ENCODE ft_sgemm_huge.cuh:150-168)
 //             e_t[k] = sum_{n in J_t} b~[n,k]      w_t[k] = sum_{n in J_t} (n-n0+1) b~[n,k]     (2-way TF32 split each)
 //   checksum GEMM (reference CHECKSUM-GEMV :171-213): the 4 checksum vectors of every N-tile are appended to B as extra
 //             "rows", i.e. the SAME kernel computes extra tile-columns  R = A * [e_t, w_t]^T  first (FP32 accumulate in
@@ -44,7 +47,7 @@ constexpr int kBM = 128;          // rows per CTA (UMMA M = 128 * CG)
 constexpr int kBK = 32;           // K extent of one shared-memory stage (4 UMMA k-steps of 8)
 constexpr int kAtomMN = 32;       // floats per 128-byte swizzle row
 constexpr int kChkPerTile = 4;    // checksum columns per N-tile: e hi/lo, w hi/lo (2 x 11-bit TF32 terms = 2^-22 relative)
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;     // 12 warps: producer, MMA, TMEM alloc, idle, 4 epilogue, 4 helpers
 constexpr int kMaxFaults = 8;
 constexpr int kMaxEvents = 16;
 
@@ -80,14 +83,16 @@ struct KernelParams {
   int dbg_flags;        // experiments only: bit 0 = skip the epilogue ABFT check of data tiles
   // Work plan (built on the host, plan.h): unit u executes items plan[plan_off[u] .. plan_off[u+1]) in order.
   //   item.x = tile (decode order: checksum tiles first), item.y = kb_begin | kb_end << 16,
-  //   item.z = kind (0 whole tile, 1 split-K contributor, 2 split-K finisher) | slice << 8, item.w = index among split tiles
-  // The last sk_tiles data tiles are cut into sk_slices k-slices each ("split-K tail") so that the list scheduler can
-  // level the units' finishing times; contributors park raw partial sums, the finisher folds them in (through TMEM).
+  //   item.z = kind (0 whole tile, 1 first piece, 3 middle piece, 2 last piece of a cut tile) | piece << 8,
+  //   item.w = index among the cut tiles
+  // The last sk_tiles data tiles are cut along K into up to sk_slices pieces so that the list scheduler can level the
+  // units' finishing times.  Piece p parks its raw accumulator; piece p+1 loads it into tensor memory BEFORE its first
+  // UMMA ("seed"), so a cut tile accumulates in exactly the k order of an uncut one (bit-identical).
   const int4 *plan;
   const int *plan_off;
   int sk_tiles, sk_slices;
-  float *sk_ws;         // per (slice < sk_slices-1, split tile, CTA of the group): one raw 128 x BN accumulator tile
-  int *sk_flags;        // [((slice*sk_tiles + split tile)*CG + cta_rank)*4 + quadrant] = sk_epoch once written
+  float *sk_ws;         // per (piece < sk_slices-1, cut tile, CTA of the group): one raw 128 x BN accumulator tile
+  int *sk_flags;        // [((piece*sk_tiles + cut tile)*CG + cta_rank)*4 + quadrant] = sk_epoch once written
   int sk_epoch;
   // fault tolerance: checksum tile-columns
   int tiles_c;          // number of BN-wide checksum tile-columns (0 when FT is off)
@@ -97,8 +102,14 @@ struct KernelParams {
   float *chk_out;       // M x n_chk_cols, column-major (ld = M): expected checksums r1/r2 (hi, lo each)
   int *chk_flags;       // [slab * tiles_c + c] = chk_epoch once checksum tile-column c of that 32-row slab is published
   int chk_epoch;
-  const int *enc_done;  // != nullptr: the encode pre-pass runs CONCURRENTLY on another stream; *enc_done == enc_epoch
-  int enc_epoch;        //             once the checksum vectors are complete (only checksum items wait for it)
+  // in-kernel encode (helper warps): B -> enc_out[k][enc_ld] (= the checksum operand the tmChk tensor map reads)
+  const float *enc_b;   // != nullptr: this launch encodes B itself
+  int enc_ldb;
+  float *enc_out;
+  int enc_ld;
+  int enc_rounding;
+  int *enc_count;       // != nullptr: every helper warp adds 1 when its share is written; checksum items wait until
+  int enc_target;       //             the counter has reached enc_target (a later launch that reuses B waits for nothing new)
   float tau_abs, tau_rel;
   int detect_only;
   int inject_mode;
@@ -113,14 +124,14 @@ struct KernelParams {
   int trace_cap;        // items recorded per unit
 };
 
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
+__device__ __forceinline__ unsigned long long globaltimer_ns() { return ptx::globaltimer(); }
 __device__ __forceinline__ void trace_put(const KernelParams &p, int unit, int item, int slot, unsigned long long v) {
   if (p.trace != nullptr && item < p.trace_cap) p.trace[(static_cast<size_t>(unit) * p.trace_cap + item) * 8 + slot] = v;
 }
+
+#ifndef FTSGEMM_MAX_STAGES
+#define FTSGEMM_MAX_STAGES 8
+#endif
 
 template <int BN, bool FT, int CG>
 struct TileCfg {
@@ -134,10 +145,11 @@ struct TileCfg {
   static constexpr int kTmemNeeded = kAccStages * BN;
   static constexpr int kTmemCols = kTmemNeeded <= 32 ? 32 : kTmemNeeded <= 64 ? 64 : kTmemNeeded <= 128 ? 128
                                    : kTmemNeeded <= 256 ? 256 : 512;
-  static constexpr int kMaxSmem = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*barriers*/;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kMaxSmem = 227 * 1024 - 1024 /*alignment slack*/ - kBarBytes;
   static constexpr int kStagesFit = kMaxSmem / kStageBytes;
-  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kStages = kStagesFit > FTSGEMM_MAX_STAGES ? FTSGEMM_MAX_STAGES : kStagesFit;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kBarBytes;
 };
 
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
@@ -234,18 +246,13 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
 // ------------------------------------------------------------------------------------------------------------
 template <int BN>
 __device__ __forceinline__ void store_tile(uint32_t taddr, float *crow, bool row_ok, int n0, int n_limit, int ldc,
-                                           float alpha, float beta, int fix_col, float fix_val) {
+                                           float alpha, float beta) {
   const bool full_n = (n0 + BN <= n_limit);
 #pragma unroll 1
   for (int c = 0; c < BN / 32; ++c) {
     uint32_t v[32];
     ptx::tmem_ld_x32(taddr + c * 32, v);
     ptx::tmem_wait_ld();
-    if (fix_col >= 0 && (fix_col >> 5) == c) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i == (fix_col & 31)) v[i] = f2u(fix_val);
-    }
     const int nb = n0 + c * 32;
     if (!row_ok) continue;
     if (full_n) {
@@ -322,10 +329,10 @@ __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr
     const int *flag = p.chk_flags + ((m0_cta >> 5) + q) * p.tiles_c;
     if (lane == 0) {
       for (int c = 0; c < p.tiles_c; ++c) {
-        unsigned spins = 0;
+        ptx::Watchdog wd;
         while (ld_acquire(flag + c) != p.chk_epoch) {
           __nanosleep(64);
-          if (++spins > (1u << 24)) __trap();
+          wd.tick();
         }
       }
     }
@@ -454,9 +461,8 @@ __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Split-K fix-up (epilogue warps, lane = row).  A contributor dumps its raw accumulator slab; a finisher adds the
-// slabs of every unit that worked on the earlier k-blocks of its tile back INTO tensor memory, so that the ABFT
-// check and the store pass that follow see the complete sum.
+// Cut tiles (plan.h).  Epilogue warps (lane = row) of a non-final piece park the raw accumulator slab; helper warps of
+// the unit that owns the next piece load it back INTO tensor memory before that piece's first UMMA.
 // ------------------------------------------------------------------------------------------------------------
 template <int BN>
 __device__ __forceinline__ void sk_dump_partial(const KernelParams &p, uint32_t taddr, float *ws, int *flag, int lane) {
@@ -473,26 +479,135 @@ __device__ __forceinline__ void sk_dump_partial(const KernelParams &p, uint32_t 
   if (lane == 0) atomicExch(flag, p.sk_epoch);
 }
 
+// seed: the previous piece's parked accumulator goes back into tensor memory before this piece's first UMMA
 template <int BN>
-__device__ __forceinline__ void sk_add_partial(const KernelParams &p, uint32_t taddr, const float *ws, const int *flag,
-                                               int lane) {
+__device__ __forceinline__ void sk_seed(const KernelParams &p, uint32_t taddr, const float *ws, const int *flag, int lane) {
   if (lane == 0) {
-    unsigned spins = 0;
+    ptx::Watchdog wd;
     while (ld_acquire(flag) != p.sk_epoch) {
       __nanosleep(64);
-      if (++spins > (1u << 24)) __trap();
+      wd.tick();
     }
   }
   __syncwarp();
 #pragma unroll 1
   for (int c = 0; c < BN / 32; ++c) {
     uint32_t v[32];
-    ptx::tmem_ld_x32(taddr + c * 32, v);
-    ptx::tmem_wait_ld();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = f2u(u2f(v[i]) + __ldcg(ws + (c * 32 + i) * kBM));
+    for (int i = 0; i < 32; ++i) v[i] = f2u(__ldcg(ws + (c * 32 + i) * kBM));
     ptx::tmem_st_x32(taddr + c * 32, v);
-    ptx::tmem_wait_st();
+  }
+  ptx::tmem_wait_st();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// ENCODE of B (reference: ft_sgemm_huge.cuh:150-168, done there per CTA and per k-step with shuffles; here once per
+// GEMM and per BN-wide column block -- a CUDA-core re-read of every shared-memory stage does not fit next to a
+// tensor-core main loop).
+//   chk[k][t*4 + 0..1] = (hi, lo) TF32 split of  e = sum_{n in block t} tf32(B[n,k])
+//   chk[k][t*4 + 2..3] = (hi, lo) TF32 split of  w = sum_{n in block t} (n - n0 + 1) * tf32(B[n,k])
+// Each lane sums its <= 8 elements of a row in plain FP32 -- TF32 inputs have 11-bit significands and (j+1)*b is an
+// exact 20-bit product, so these short sums are exact unless the elements differ by > 2^10 in magnitude -- the 32-way
+// cross-lane reduction runs in FP64 as a transposing butterfly (NV values per lane -> one per lane: NV-1 + log steps
+// instead of 5*NV shuffles), and the two TF32 terms carry each checksum to ~2^-22 relative.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_bits(float x, int rounding) {
+  uint32_t u = __float_as_uint(x);
+  if (rounding == 1) u += 0x1000u;  // round-to-nearest (ties away), like cvt.rna.tf32.f32
+  if (rounding != 2) u &= 0xFFFFE000u;
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ void split2_tf32(double x, float &h, float &l) {
+  h = tf32_bits(static_cast<float>(x), 0);
+  l = tf32_bits(static_cast<float>(x - static_cast<double>(h)), 0);  // x - h is exact in FP64
+}
+
+// v[0..CNT) per lane -> after all steps v[0] of lane L is the 32-lane total of value idx(L)
+template <int CNT, int O>
+struct TransposeReduce {
+  static __device__ __forceinline__ void run(double *v, int lane, int &idx) {
+    if constexpr (O > 0) {
+      if constexpr (CNT > 1) {
+        constexpr int H = CNT / 2;
+        const bool up = (lane & O) != 0;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+          const double send = up ? v[i] : v[i + H];
+          const double keep = up ? v[i + H] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+        }
+        if (up) idx += H;
+        TransposeReduce<H, O / 2>::run(v, lane, idx);
+      } else {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], O);
+        TransposeReduce<1, O / 2>::run(v, lane, idx);
+      }
+    }
+  }
+};
+
+// One warp encodes items (column block t, KR consecutive k-rows), item = gw, gw + nw, ...; t fastest, so that warps
+// running side by side read neighbouring 1 KiB segments of the same rows of B.
+template <int BN>
+__device__ __forceinline__ void encode_b_warp(const float *__restrict__ B, int N, int K, int ldb, float *__restrict__ chk,
+                                              int chk_ld, int rounding, int tiles_n, int gw, int nw, int lane) {
+  constexpr int J = BN >= 128 ? BN / 128 : 0;   // float4 loads per lane and k-row
+  constexpr int KR = (J == 2) ? 8 : 16;         // k-rows per item: 16 float4 (J = 2, 1) in flight per lane
+  constexpr int NV = 2 * KR;
+  const int k_items = (K + KR - 1) / KR;
+  const int total = tiles_n * k_items;
+  for (int item = gw; item < total; item += nw) {
+    const int t = item % tiles_n;
+    const int n0 = t * BN;
+    const int k0 = (item / tiles_n) * KR;
+    double v[NV];
+    if (J > 0 && n0 + BN <= N && k0 + KR <= K) {  // full block: 16-byte loads (ldb % 4 == 0, n0 % 4 == 0)
+      float4 x[KR][J > 0 ? J : 1];
+#pragma unroll
+      for (int u = 0; u < KR; ++u)
+#pragma unroll
+        for (int jj = 0; jj < J; ++jj)
+          x[u][jj] = __ldg(reinterpret_cast<const float4 *>(B + static_cast<size_t>(k0 + u) * ldb + n0) + lane + 32 * jj);
+#pragma unroll
+      for (int u = 0; u < KR; ++u) {
+        float e = 0.0f, w = 0.0f;
+#pragma unroll
+        for (int jj = 0; jj < J; ++jj) {
+          const float wj = static_cast<float>(4 * (lane + 32 * jj) + 1);
+          const float b0 = tf32_bits(x[u][jj].x, rounding), b1 = tf32_bits(x[u][jj].y, rounding),
+                      b2 = tf32_bits(x[u][jj].z, rounding), b3 = tf32_bits(x[u][jj].w, rounding);
+          e += (b0 + b1) + (b2 + b3);
+          w += (b0 * wj + b1 * (wj + 1.0f)) + (b2 * (wj + 2.0f) + b3 * (wj + 3.0f));
+        }
+        v[2 * u] = static_cast<double>(e);
+        v[2 * u + 1] = static_cast<double>(w);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < KR; ++u) {
+        float e = 0.0f, w = 0.0f;
+        const int k = k0 + u;
+        if (k < K) {
+          for (int j = lane; j < BN; j += 32) {
+            if (n0 + j < N) {
+              const float b = tf32_bits(__ldg(B + static_cast<size_t>(k) * ldb + n0 + j), rounding);
+              e += b;
+              w += b * static_cast<float>(j + 1);
+            }
+          }
+        }
+        v[2 * u] = static_cast<double>(e);
+        v[2 * u + 1] = static_cast<double>(w);
+      }
+    }
+    int idx = 0;
+    TransposeReduce<NV, 16>::run(v, lane, idx);
+    const int k = k0 + (idx >> 1);
+    if ((lane & (32 / NV - 1)) == 0 && k < K) {
+      float h, l;
+      split2_tf32(v[0], h, l);
+      *reinterpret_cast<float2 *>(chk + static_cast<size_t>(k) * chk_ld + t * kChkPerTile + (idx & 1) * 2) = make_float2(h, l);
+    }
   }
 }
 
@@ -516,7 +631,11 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  auto seeded_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 4 + a); };  // leader: TMEM stage a holds the seed
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 6);
+  // number of (epilogue warp, item) pairs this CTA has finished: the helper warps' view of which accumulator stages
+  // are drained (a counter, not an mbarrier: the helpers may be many items behind while they encode B)
+  const uint32_t epi_count = tmem_slot + 8u;
   volatile uint32_t *tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
@@ -539,7 +658,9 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
       ptx::mbar_init(tempty_bar(a), 4 * CG);  // one arrive per epilogue warp of every CTA in the group
+      ptx::mbar_init(seeded_bar(a), 4 * CG);  // one arrive per helper warp of every CTA in the group
     }
+    ptx::st_shared_u32(epi_count, 0u);
     ptx::fence_mbar_init();
   }
   if (CG == 2) ptx::cluster_sync_all();  // peer barriers must be initialised before any remote arrive / 2-CTA alloc
@@ -566,6 +687,17 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     SegIter it(p, unit);
     Segment sg;
     int item_idx = -1;
+    if (FT && (p.dbg_flags & 4) && p.enc_count != nullptr) {
+      // experiment: "foreground" encode -- no main loop starts before the whole encode is done
+      if (lane == 0) {
+        ptx::Watchdog wd;
+        while (ld_acquire(p.enc_count) - p.enc_target < 0) {
+          __nanosleep(128);
+          wd.tick();
+        }
+      }
+      __syncwarp();
+    }
     while (it.next(sg)) {
       ++item_idx;
       const TileCoord tc = decode_tile(p, sg.tile);
@@ -575,17 +707,17 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int nb0 = (b_is_chk ? tc.n_blk * chk_cols_per_tile(BN) : tc.n_blk * BN) +
                       static_cast<int>(cta_rank) * (n_eff / CG);  // this CTA's share of B rows
       const CUtensorMap *tmb = b_is_chk ? &tmChk : &tmB;
-      if (FT && b_is_chk && p.enc_done != nullptr) {
-        // the encode pre-pass may still be running on its own stream: checksum items (and only they) wait for it
+      if (FT && b_is_chk && p.enc_count != nullptr) {
+        // the checksum vectors are being written by the helper warps of all CTAs: checksum items (and only they) wait
         if (lane == 0) {
-          unsigned spins = 0;
-          while (ld_acquire(p.enc_done) != p.enc_epoch) {
+          ptx::Watchdog wd;
+          while (ld_acquire(p.enc_count) - p.enc_target < 0) {
             __nanosleep(128);
-            if (++spins > (1u << 23)) __trap();
+            wd.tick();
           }
         }
         __syncwarp();
-        ptx::fence_proxy_async();
+        ptx::fence_proxy_async();  // generic-proxy writes (st.global) -> async-proxy reads (TMA)
       }
       if (p.trace != nullptr && is_leader && lane == 0) trace_put(p, unit, item_idx, 0, globaltimer_ns());
       // The loop body is specialised OUTSIDE the k loop: with 3-D tensor maps a stage is exactly two TMA instructions
@@ -683,6 +815,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t seed_phase = 0;  // bit a: parity of seeded_bar(a)
     SegIter it(p, unit);
     Segment sg;
     int item_idx = -1;
@@ -700,7 +833,13 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // Lean issue loop: a single thread runs dependent integer chains at ~1 instruction per 4-6 cycles, and four UMMAs
       // (one k-block) take only ~512 cycles, so the 64-bit descriptors are NOT rebuilt per UMMA: the high word
       // (SBO, version, layout) and LBO are constant, only the 14-bit start-address field advances (+64 = 1024 B).
-      uint32_t first = 1u;  // the first UMMA of a segment overwrites the accumulator
+      uint32_t first = 1u;  // the first UMMA of a tile overwrites the accumulator ...
+      if (sg.kind >= 2) {   // ... unless the helper warps seeded it with the previous piece's parked sums
+        ptx::mbar_wait(seeded_bar(acc), (seed_phase >> acc) & 1u);
+        seed_phase ^= 1u << acc;
+        ptx::tc_fence_after();
+        first = 0u;
+      }
       for (int kb = sg.kb_begin; kb < sg.kb_end; ++kb) {
         ptx::mbar_wait(full_bar(stage), phase);
         ptx::tc_fence_after();
@@ -739,7 +878,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         acc_phase ^= 1u;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ===================================================================== epilogue (4 warps per CTA, lane = row)
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;
@@ -765,23 +904,18 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         trace_put(p, unit, item_idx, 7, static_cast<unsigned long long>(sg.tile) | (static_cast<unsigned long long>(sg.kind) << 24));
       }
 
-      if (sg.kind == 1) {
-        // split-K contributor: park the raw partial sums of this slab for the unit that finishes the tile
+      const bool parks = (sg.kind & 1) != 0;  // first / middle piece of a cut tile
+      if (parks) {
+        // park the raw sums of this piece for the unit that owns the next one
         const int slot = (sg.slice * p.sk_tiles + sg.split_idx) * CG + static_cast<int>(cta_rank);
         sk_dump_partial<BN>(p, taddr, p.sk_ws + slot * ws_slab + row, p.sk_flags + slot * 4 + q, lane);
-      } else if (sg.kind == 2) {
-        // split-K finisher: fold in the earlier k-slices of this tile
-        for (int sl = 0; sl < p.sk_slices - 1; ++sl) {
-          const int slot = (sl * p.sk_tiles + sg.split_idx) * CG + static_cast<int>(cta_rank);
-          sk_add_partial<BN>(p, taddr, p.sk_ws + slot * ws_slab + row, p.sk_flags + slot * 4 + q, lane);
-        }
       }
-      if (sg.kind == 1) {
+      if (parks) {
         // nothing to store yet
       } else if (FT && tc.is_chk) {
         // checksum tile-column: publish R = A * [e, w]^T for these 128 rows, then raise the slab flag
         const int n_hi = min(p.n_chk_cols, n0 + chk_cols_per_tile(BN));  // columns beyond belong to the next item
-        store_tile<BN>(taddr, p.chk_out + m, m < p.M, n0, n_hi, p.M, 1.0f, 0.0f, -1, 0.0f);
+        store_tile<BN>(taddr, p.chk_out + m, m < p.M, n0, n_hi, p.M, 1.0f, 0.0f);
         __threadfence();
         __syncwarp();
         if (lane == 0) atomicExch(p.chk_flags + ((m0_cta >> 5) + q) * p.tiles_c + tc.n_blk, p.chk_epoch);
@@ -790,7 +924,24 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float fix_val = 0.0f;
         if (FT && !(p.dbg_flags & 1)) abft_check<BN>(p, taddr, q, lane, m, m0_cta, n0, tc.n_blk, fix_col, fix_val);
         if (tracer) trace_put(p, unit, item_idx, 5, globaltimer_ns());
-        store_tile<BN>(taddr, p.C + m, m < p.M, n0, p.N, p.ldc, p.alpha, p.beta, fix_col, fix_val);
+        if (FT) {
+          // rare: write the recomputed elements back into the accumulator (one lane = one row at a time, like the
+          // injection path), so that the store pass stays free of per-element patching (a dynamically indexed patch of the
+          // register tile had pushed it into local memory: 6.6 us instead of 3.6 us per tile)
+          unsigned fix_mask = __ballot_sync(0xffffffffu, fix_col >= 0);
+          while (fix_mask != 0u) {
+            const int src = __ffs(fix_mask) - 1;
+            fix_mask &= fix_mask - 1u;
+            const int col = __shfl_sync(0xffffffffu, fix_col, src);
+            const float val = __shfl_sync(0xffffffffu, fix_val, src);
+            uint32_t x = ptx::tmem_ld_x1(taddr + col);
+            ptx::tmem_wait_ld();
+            if (lane == src) x = f2u(val);
+            ptx::tmem_st_x1(taddr + col, x);
+            ptx::tmem_wait_st();
+          }
+        }
+        store_tile<BN>(taddr, p.C + m, m < p.M, n0, p.N, p.ldc, p.alpha, p.beta);
       }
       // release this accumulator stage back to the MMA warp (of the leader CTA)
       ptx::tc_fence_before();
@@ -799,12 +950,60 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (lane == 0) {
         if (CG == 2) ptx::mbar_arrive_cluster(tempty_leader + 8u * acc);
         else ptx::mbar_arrive(tempty_bar(acc));
+        ptx::red_release_shared_add(epi_count, 1u);
       }
       if (kAccStages == 2) {
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       } else {
         acc_phase ^= 1u;
+      }
+    }
+  }
+
+  else if (warp >= 8) {
+    // ===================================================================== helper warps (TMEM lane quadrant = warp & 3)
+    const int q = warp & 3;
+    if (FT && p.enc_b != nullptr) {
+      if (p.trace != nullptr && is_leader && q == 0 && lane == 0) trace_put(p, unit, p.trace_cap - 1, 1, globaltimer_ns());
+      encode_b_warp<BN>(p.enc_b, p.N, p.K, p.enc_ldb, p.enc_out, p.enc_ld, p.enc_rounding, p.tiles_n,
+                        static_cast<int>(blockIdx.x) * 4 + q, static_cast<int>(gridDim.x) * 4, lane);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicAdd(p.enc_count, 1);
+      if (p.trace != nullptr && is_leader && q == 0 && lane == 0) trace_put(p, unit, p.trace_cap - 1, 0, globaltimer_ns());
+    }
+    if (p.sk_tiles > 0) {
+      const uint32_t seeded_leader = (CG == 2) ? ptx::mapa(seeded_bar(0), 0) : seeded_bar(0);
+      const size_t ws_slab = static_cast<size_t>(kBM) * BN;
+      int acc = 0;
+      int item_idx = -1;
+      SegIter it(p, unit);
+      Segment sg;
+      while (it.next(sg)) {
+        ++item_idx;
+        if (sg.kind >= 2) {
+          // the accumulator stage must have been drained by this CTA's four epilogue warps (item_idx - 2 and before)
+          if (item_idx >= 2) {
+            const uint32_t need = 4u * static_cast<uint32_t>(item_idx - 1);
+            ptx::Watchdog wd;
+            while (ptx::ld_acquire_shared_u32(epi_count) < need) {
+              __nanosleep(64);
+              wd.tick();
+            }
+          }
+          ptx::tc_fence_after();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+          const int slot = ((sg.slice - 1) * p.sk_tiles + sg.split_idx) * CG + static_cast<int>(cta_rank);
+          sk_seed<BN>(p, taddr, p.sk_ws + slot * ws_slab + q * 32 + lane, p.sk_flags + slot * 4 + q, lane);
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2) ptx::mbar_arrive_cluster(seeded_leader + 8u * acc);
+            else ptx::mbar_arrive(seeded_bar(acc));
+          }
+        }
+        acc ^= 1;
       }
     }
   }
@@ -821,118 +1020,17 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Encode pre-pass (reference: ft_sgemm_huge.cuh:150-168 ENCODE of B, done there per CTA and per k-step with
-// shuffles; here once per GEMM and per BN-wide column block, because a CUDA-core re-read of every shared-memory
-// stage does not fit next to a tensor-core main loop -- DESIGN.md section 3).
-//   chk[k][t*4 + 0..1] = (hi, lo) TF32 split of  e = sum_{n in block t} tf32(B[n,k])
-//   chk[k][t*4 + 2..3] = (hi, lo) TF32 split of  w = sum_{n in block t} (n - n0 + 1) * tf32(B[n,k])
-// Sums are accumulated as FP32 hi+lo pairs (error-free transformations), so the three TF32 terms carry the checksum
-// to ~2^-22 relative (enough: its contribution to the residual is < 3 % of the measured floor).
+// Stand-alone encode pre-pass (same per-warp routine as the in-kernel helpers): used when the caller asks for it
+// (debug knob enc_mode = 1) -- the A/B partner of the in-kernel encode.
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float tf32_bits(float x, int rounding) {
-  uint32_t u = __float_as_uint(x);
-  if (rounding == 1) u += 0x1000u;  // round-to-nearest (ties away), like cvt.rna.tf32.f32
-  if (rounding != 2) u &= 0xFFFFE000u;
-  return __uint_as_float(u);
-}
-__device__ __forceinline__ void split2_tf32(double x, float &h, float &l) {
-  h = tf32_bits(static_cast<float>(x), 0);
-  l = tf32_bits(static_cast<float>(x - static_cast<double>(h)), 0);  // x - h is exact in FP64
-}
-
 constexpr int kEncWarps = 8;
-constexpr int kEncLoads = 8;  // 16-byte loads in flight per lane
 
-// grid = (tiles_n, ceil(K / (8 warps * KW))), KW = kEncLoads / J k-rows per warp, J = BN/128 float4 per lane and row.
-// Arithmetic budget matters here (the first versions were instruction-bound at ~2.5 TB/s: FP64 or double-float work
-// on every element):  each lane sums its <= 8 elements of a row in plain FP32 -- TF32 inputs have 11-bit significands
-// and (j+1)*b is an exact 20-bit product, so these short sums are exact unless the elements differ by > 2^10 in
-// magnitude -- and only the 32-way cross-lane reduction runs in FP64 (10 DADD per row).  All kEncLoads loads of a lane
-// are issued before the first is consumed; 4 blocks (32 warps) are resident per SM.  The kernel also clears the checksum
-// slab flags of the GEMM launch that follows it in the stream (one memset launch less).
-// done != nullptr: the kernel is launched with a 1-D persistent grid (a few blocks per SM at most, so that it fits next
-// to the resident GEMM CTAs) on its own stream; the last block to finish publishes *done = epoch.
-template <int J>
-__global__ void __launch_bounds__(kEncWarps * 32, 4)
-encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, int BN, float *__restrict__ chk, int chk_ld,
-                int rounding, int tiles_n, int k_groups, int *__restrict__ done, int epoch) {
-  constexpr int KW = kEncLoads / (J > 0 ? J : 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total = tiles_n * k_groups;
-  for (int item = blockIdx.x; item < total; item += gridDim.x) {
-  const int t = item % tiles_n;        // tile fastest: concurrently running blocks read neighbouring columns
-  const int n0 = t * BN;
-  const int kbase = ((item / tiles_n) * kEncWarps + warp) * KW;
-  float e[KW], w[KW];
-#pragma unroll
-  for (int u = 0; u < KW; ++u) e[u] = w[u] = 0.0f;
-  if (J > 0 && n0 + BN <= N) {  // full tile of 128*J columns: 16-byte loads (ldb % 4 == 0, n0 % 4 == 0)
-    float4 v[KW][J > 0 ? J : 1];
-#pragma unroll
-    for (int u = 0; u < KW; ++u) {
-      const int k = kbase + u;
-#pragma unroll
-      for (int jj = 0; jj < J; ++jj)
-        v[u][jj] = (k < K) ? __ldg(reinterpret_cast<const float4 *>(B + static_cast<size_t>(k) * ldb + n0) + lane + 32 * jj)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int u = 0; u < KW; ++u) {
-#pragma unroll
-      for (int jj = 0; jj < J; ++jj) {
-        const float wj = static_cast<float>(4 * (lane + 32 * jj) + 1);
-        const float b0 = tf32_bits(v[u][jj].x, rounding), b1 = tf32_bits(v[u][jj].y, rounding),
-                    b2 = tf32_bits(v[u][jj].z, rounding), b3 = tf32_bits(v[u][jj].w, rounding);
-        e[u] += (b0 + b1) + (b2 + b3);
-        w[u] += (b0 * wj + b1 * (wj + 1.0f)) + (b2 * (wj + 2.0f) + b3 * (wj + 3.0f));
-      }
-    }
-  } else {
-    for (int j = lane; j < BN; j += 32) {
-      const int n = n0 + j;
-      if (n < N) {
-#pragma unroll
-        for (int u = 0; u < KW; ++u) {
-          const int k = kbase + u;
-          if (k < K) {
-            const float b = tf32_bits(__ldg(B + static_cast<size_t>(k) * ldb + n), rounding);
-            e[u] += b;
-            w[u] += b * static_cast<float>(j + 1);
-          }
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int u = 0; u < KW; ++u) {
-    double de = static_cast<double>(e[u]), dw = static_cast<double>(w[u]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      de += __shfl_xor_sync(0xffffffffu, de, o);
-      dw += __shfl_xor_sync(0xffffffffu, dw, o);
-    }
-    const int k = kbase + u;
-    if (k < K && lane < kChkPerTile) {  // every lane holds the totals; lane i writes column i of the 4-float block
-      float eh, el, wh, wl;
-      split2_tf32(de, eh, el);
-      split2_tf32(dw, wh, wl);
-      const float val = lane == 0 ? eh : lane == 1 ? el : lane == 2 ? wh : wl;
-      chk[static_cast<size_t>(k) * chk_ld + t * kChkPerTile + lane] = val;
-    }
-  }
-  }  // item loop
-  if (done != nullptr) {
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const int prev = atomicAdd(done + 1, 1);
-      if (prev == static_cast<int>(gridDim.x) - 1) {
-        done[1] = 0;
-        __threadfence();
-        atomicExch(done, epoch);
-      }
-    }
-  }
+template <int BN>
+__global__ void __launch_bounds__(kEncWarps * 32, 2)
+encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, float *__restrict__ chk, int chk_ld, int rounding,
+                int tiles_n) {
+  encode_b_warp<BN>(B, N, K, ldb, chk, chk_ld, rounding, tiles_n, blockIdx.x * kEncWarps + (threadIdx.x >> 5),
+                    gridDim.x * kEncWarps, threadIdx.x & 31);
 }
 
 }  // namespace ftsgemm

@@ -49,21 +49,46 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin on try_wait.  FTSGEMM_WATCHDOG (default on) turns a protocol bug into a trap instead of a hung GPU:
-// ~2^26 failed polls (each try_wait already blocks for a HW-defined interval) is seconds, far beyond any legal wait.
+// Spin on try_wait.  FTSGEMM_WATCHDOG (default on) turns a protocol bug into a trap instead of a hung GPU: any wait
+// longer than kWatchdogNs of wall time (%globaltimer; far beyond any legal wait) traps.  The clock is only read on the
+// slow path (every 1024 failed polls).
 #ifndef FTSGEMM_WATCHDOG
 #define FTSGEMM_WATCHDOG 1
 #endif
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-#if FTSGEMM_WATCHDOG
+constexpr unsigned long long kWatchdogNs = 1500ull * 1000 * 1000;
+__device__ __forceinline__ unsigned long long globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct Watchdog {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
-  }
-#else
-  while (!mbar_try_wait(bar, parity)) {
-  }
+  unsigned long long t0 = 0;
+  __device__ __forceinline__ void tick() {
+#if FTSGEMM_WATCHDOG
+    if ((++spins & 1023u) == 0u) {
+      const unsigned long long t = globaltimer();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > kWatchdogNs) __trap();
+    }
 #endif
+  }
+};
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  Watchdog wd;
+  while (!mbar_try_wait(bar, parity)) wd.tick();
+}
+
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_shared_add(uint32_t addr, uint32_t v) {
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
 }
 
 // Orders preceding generic-proxy memory operations (e.g. an acquire load that observed another kernel's writes) before
@@ -80,6 +105,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm,
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+// plain (non-tensor) bulk copy global -> shared, completion counted in bytes on an mbarrier; 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float ld_shared_f1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(

@@ -34,10 +34,14 @@ def trace_case(pkg, kid, n, dbg=None, tag="", reuse=False, m=None, k=None):
     B = (rng.integers(-9, 10, n * k) * 0.1).astype(np.float32)
     dA, dB, dC = cu.DevBuf.from_numpy(A), cu.DevBuf.from_numpy(B), cu.DevBuf(4 * m * n)
     dC.zero()
-    for key, v in (dbg or {}).items():
+    dbg = dict(dbg or {})
+    big_tau = dbg.pop("bigtau", 0)
+    for key, v in dbg.items():
         pkg.debug_set(key, v)
     ft = pkg.FtSgemm()
     opts = pkg.make_opts(reuse_b_checksums=1) if reuse else None
+    if big_tau:
+        opts = pkg.make_opts(tau_abs=1e30)
     for _ in range(3):
         ft.run(kid, m, n, k, dA, dB, dC, 1.0, 0.0, opts)
     cu.sync()
@@ -77,6 +81,13 @@ def trace_case(pkg, kid, n, dbg=None, tag="", reuse=False, m=None, k=None):
            "unit_end_us": {"min": round(min(unit_end) / 1e3, 2), "p50": round(float(np.median(unit_end)) / 1e3, 2),
                            "max": round(max(unit_end) / 1e3, 2)},
            "first_data_epilogue_start_us": round(min(it["acc_done"] for u in tr for it in u if it["tile"] >= n_chk) / 1e3 - t0 / 1e3, 2),
+           "encode_end_us": (lambda e: None if not e else {"min": round(min(e) / 1e3, 2), "max": round(max(e) / 1e3, 2)})(
+               [u[0]["enc_end"] - t0 for u in tr if u and u[0].get("enc_end")]),
+           "encode_dur_us": (lambda e: None if not e else {"min": round(min(e) / 1e3, 2), "max": round(max(e) / 1e3, 2),
+                                                              "mean": round(sum(e) / len(e) / 1e3, 2)})(
+               [u[0]["enc_end"] - u[0]["enc_start"] for u in tr if u and u[0].get("enc_end")]),
+           "encode_all_done_after_first_start_us": (lambda a, b: None if not a else round((max(a) - min(b)) / 1e3, 2))(
+               [u[0]["enc_end"] for u in tr if u and u[0].get("enc_end")], [u[0]["enc_start"] for u in tr if u and u[0].get("enc_start")]),
            "chk_items_end_us": [round((it["epi_end"] - t0) / 1e3, 1) for u in tr for it in u if it["tile"] < n_chk][:40]}
     raw = [[{kk: (vv - t0 if kk not in ("tile", "kind") and vv else vv) for kk, vv in it.items()} for it in u] for u in tr]
     name = f"trace_{kid}_{n}{('_' + tag) if tag else ''}.json"

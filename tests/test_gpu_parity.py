@@ -78,46 +78,46 @@ def test_reference_inputs_vs_golden_and_oracle(cuda, ft, dev, oracle, n, name):
 
 
 def test_ft_equals_plain_bitwise_when_fault_free(cuda, ft, dev):
-    """With the same K decomposition (split-K head off) the ABFT kernel must not perturb a single bit of a fault-free
-    product; with the head on, FT and plain may slice K differently, so they agree to FP32 accumulation order only."""
+    """The ABFT kernel must not perturb a single bit of a fault-free product -- whatever the planner cuts: a cut tile is
+    a seeded chain that accumulates in exactly the k order of an uncut tile."""
     rng = np.random.default_rng(3)
     M, N, K = 512, 768, 640
     A, B = _rand(rng, M * K), _rand(rng, N * K)
     C0 = np.zeros(M * N, np.float32)
-    try:
-        ft.debug_set("splitk", 0)
-        for name in ("medium", "huge", "wide", "giant"):
-            a = _run(cuda, dev, ft.SGEMM_IDS[name], M, N, K, A, B, C0)
-            b = _run(cuda, dev, ft.ABFT_IDS[name], M, N, K, A, B, C0)
-            assert np.array_equal(a, b), name
-    finally:
-        ft.debug_set("splitk", -1)
-    for name in ("huge", "giant"):
-        a = _run(cuda, dev, ft.SGEMM_IDS[name], M, N, K, A, B, C0)
-        b = _run(cuda, dev, ft.ABFT_IDS[name], M, N, K, A, B, C0)
-        assert np.abs(a - b).max() < 1e-4 * np.abs(a).max()
+    ref = {}
+    for splitk in (0, -1, 2, 3):
+        try:
+            ft.debug_set("splitk", splitk)
+            for name in ("medium", "huge", "wide", "giant"):
+                a = _run(cuda, dev, ft.SGEMM_IDS[name], M, N, K, A, B, C0)
+                b = _run(cuda, dev, ft.ABFT_IDS[name], M, N, K, A, B, C0)
+                assert np.array_equal(a, b), (name, splitk)
+                assert np.array_equal(ref.setdefault(name, a), a), (name, splitk)
+        finally:
+            ft.debug_set("splitk", -1)
 
 
-def test_encode_overlap_and_serial_paths_agree(cuda, ft, dev):
-    """The encode pre-pass normally runs concurrently with the GEMM kernel on the handle's own stream (checksum items wait
-    on a flag); the serial in-stream path and the cached-checksum path must give bit-identical results and verdicts."""
+def test_encode_in_kernel_and_prepass_agree(cuda, ft, dev):
+    """The checksum vectors of B are normally encoded by the GEMM kernel's own helper warps in the background of the first
+    main loops (checksum items wait on a counter); the stand-alone pre-pass kernel and the cached-checksum path must give
+    bit-identical results and verdicts."""
     rng = np.random.default_rng(5)
     M, N, K = 1024, 1280, 768
     A, B = _rand(rng, M * K), _rand(rng, N * K)
     C0 = rng.standard_normal(M * N).astype(np.float32)
     faults = [{"row": 77, "col": 300, "xor": 1 << 29}, {"row": 900, "col": 1279, "add": -55.0}]
     outs = []
-    for overlap in (1, 0):
+    for mode in (0, 1):
         try:
-            ft.debug_set("enc_overlap", overlap)
+            ft.debug_set("enc_mode", mode)
             dev.stats()
-            for rep in range(3):  # back-to-back launches reuse the flags / epochs
+            for rep in range(3):  # back-to-back launches reuse the flags / epochs / counters
                 got = _run(cuda, dev, 31, M, N, K, A, B, C0, 1.0, -1.5, opts=ft.make_opts(faults=faults))
             st = dev.stats()
             assert st["detected"] == 6 and st["corrected"] == 6 and st["uncorrectable"] == 0
             outs.append(got)
         finally:
-            ft.debug_set("enc_overlap", -1)
+            ft.debug_set("enc_mode", -1)
     assert np.array_equal(outs[0], outs[1])
     dA, dB = cuda.from_numpy(A).cuda(), cuda.from_numpy(B).cuda()
     dC = cuda.from_numpy(C0.copy()).cuda()
@@ -126,12 +126,28 @@ def test_encode_overlap_and_serial_paths_agree(cuda, ft, dev):
     dev.run(31, M, N, K, dA, dB, dC2, 1.0, -1.5, ft.make_opts(faults=faults, reuse_b_checksums=True))
     cuda.cuda.synchronize()
     assert cuda.equal(dC, dC2) and np.array_equal(dC.cpu().numpy(), outs[0])
+    # ragged N / K tail and the narrow-tile (scalar) encode path against the pre-pass, all FT tile widths
+    M2, N2, K2 = 260, 388, 72
+    A2, B2 = _rand(rng, M2 * K2), _rand(rng, N2 * K2)
+    C2 = np.zeros(M2 * N2, np.float32)
+    for kid in (11, 12, 16, 15, 31, 32):
+        res = []
+        for mode in (0, 1):
+            try:
+                ft.debug_set("enc_mode", mode)
+                dev.stats()
+                res.append(_run(cuda, dev, kid, M2, N2, K2, A2, B2, C2, 1.0, 0.0, opts=ft.make_opts(selftest=(10000.0, 17, 5))))
+                st = dev.stats()
+                assert st["detected"] == st["corrected"] > 0 and st["uncorrectable"] == 0, (kid, mode, st)
+            finally:
+                ft.debug_set("enc_mode", -1)
+        assert np.array_equal(res[0], res[1]), kid
 
 
 @pytest.mark.parametrize("slices", [2, 3, 5])
 def test_split_k_head_forced(cuda, ft, dev, oracle, slices):
-    """Force the split-K head (contributor dump + finisher fold-in through TMEM) on shapes where the planner would not
-    pick it, with and without ABFT + injected faults."""
+    """Force cut tiles (pieces park their accumulator, the next piece seeds tensor memory with it) on shapes where the
+    planner would not cut, with and without ABFT + injected faults."""
     rng = np.random.default_rng(slices)
     M, N, K = 768, 1024, 1600
     A, B = _rand(rng, M * K), _rand(rng, N * K)
