@@ -259,10 +259,10 @@ class FtSgemm:
         out = []
         for u in range(n):
             items = []
-            for i in range(64):
+            for i in range(63):
                 r = buf[(u * 64 + i) * 8:(u * 64 + i) * 8 + 8]
-                if r[4] == 0:
-                    break
+                if r[4] == 0:  # unused slot, or an encoder item (it has no accumulator / epilogue)
+                    continue
                 d = dict(zip(keys, r[:7]))
                 d["tile"] = r[7] & 0xFFFFFF
                 d["kind"] = r[7] >> 24

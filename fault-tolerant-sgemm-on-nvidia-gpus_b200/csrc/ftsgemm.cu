@@ -107,6 +107,9 @@ struct ftsgemm_handle_s {
   std::map<std::array<long long, 6>, CachedPlan> plans;  // key: kernel id, M, N, K, units, forced slices
   int *d_enc_count = nullptr;   // helper warps that have finished their share of the in-kernel encode (monotonic)
   int enc_total = 0;            // host mirror of the value the counter reaches after the last launch
+  int *d_enc_prog = nullptr;    // encoder items: per k-chunk progress counters (monotonic per shape)
+  int enc_prog_cap = 0, enc_prog_value = 0;
+  std::array<long long, 4> enc_prog_shape = {0, 0, 0, 0};
   int chk_epoch = 0;
   float *d_sk = nullptr;        // split-K partial tiles + flags
   size_t sk_bytes = 0;
@@ -218,7 +221,22 @@ void chk_costs(const KernelParams &p, std::vector<double> *out) {
     out->push_back(std::max(0.58, static_cast<double>(chk_tile_width<BNv, CGv>(p, c)) / BNv));
 }
 
-PlanInput make_plan_input(int num_sms, int CG, int BN, int K, const KernelParams &p) {
+// How the checksum vectors of B are produced (debug knob enc_mode; -2 = automatic):
+//   2  encoder items inside the GEMM kernel: one unit per tile-column streams B through its shared-memory ring and its
+//      helper + epilogue warps reduce it (needs the 3-D tensor map of B, i.e. N % 32 == 0).  One launch per GEMM, but
+//      the items run while every SM is fetching cold operands and get 1/148 of the HBM bandwidth each: ~1.2 tile-times
+//      per item, the same cost as the pre-pass (715 vs 709 TFLOP/s at 4096^3, 781 vs 785 at 8192^3)
+//   1  stand-alone pre-pass kernel in front of the GEMM (10.7 us per step at 4096^3 in a loop: 5.6 %)   [default]
+//   0  helper warps read their share of B from global memory in the background (measured 3-8x slower: they cannot keep
+//      enough bytes in flight next to the main loop)
+int encode_mode(int N) {
+  const long long m = dbg("enc_mode", -2);
+  const bool items_ok = N % kAtomMN == 0 && dbg("enc_rounding", 0) == 0;  // (the rounding experiment only exists in modes 0/1)
+  if (m >= 0 && m <= 2 && !(m == 2 && !items_ok)) return static_cast<int>(m);
+  return 1;
+}
+
+PlanInput make_plan_input(int num_sms, int CG, int BN, int K, const KernelParams &p, bool encode_items) {
   PlanInput in;
   long long units = dbg("grid", 0);
   in.units = units > 0 ? static_cast<int>(units) : num_sms / CG;
@@ -244,11 +262,16 @@ PlanInput make_plan_input(int num_sms, int CG, int BN, int K, const KernelParams
   const long long lock = dbg("lockstep", -2);
   in.lockstep = lock >= 0 ? static_cast<int>(lock)
                           : (4.0 * K * (static_cast<double>(p.M) + p.N) > 96.0 * 1024 * 1024 ? 1 : 0);
-  // in-kernel encode: checksum items cannot start before the helper warps have streamed B once (~3 TB/s in the
-  // background of the first main loops)
   in.chk_release = 0.0;
-  if (p.tiles_c > 0 && dbg("enc_mode", 1) == 0) {
-    const double enc_us = 4.0 * static_cast<double>(p.N) * K / 3.0e6 + 3.0;
+  if (p.tiles_c > 0 && encode_items) {
+    // one encoder item per tile-column of B; the checksum tiles follow them k-chunk by k-chunk, so they can start almost
+    // at once but cannot finish before the encoders do
+    in.n_enc_items = p.tiles_n;
+    in.enc_cost = static_cast<double>(dbg("enc_cost_permille", 1200)) * 1e-3;
+    in.chk_release = std::max(0.0, in.enc_cost - in.chk_col_cost[0]) + 0.05;
+  } else if (p.tiles_c > 0 && encode_mode(p.N) == 0) {
+    // helper warps stream B from global memory in the background (~1 TB/s next to the main loops)
+    const double enc_us = 4.0 * static_cast<double>(p.N) * K / 1.0e6 + 3.0;
     in.chk_release = enc_us / tile_us;
   }
   return in;
@@ -321,7 +344,7 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
   CUtensorMap tmA, tmB, tmC;
   const bool allow3d = dbg("tma3d", 1) != 0;
   bool need_encode = false;
-  int chk_ld_v = 0;
+  int chk_ld_v = 0, enc_mode_v = 1;
   int rc;
   if (allow3d && M % kAtomMN == 0) {
     rc = make_tmap_3d(h, &tmA, dA, M, K, M, kBM / kAtomMN);
@@ -365,8 +388,9 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     const bool reuse = o.reuse_b_checksums && h->chk_for_b == dB && h->chk_n == N && h->chk_k == K && h->chk_bn == BN;
     need_encode = !reuse;
     chk_ld_v = chk_ld;
-    if (need_encode && dbg("enc_mode", 1) != 0) {
-      // stand-alone pre-pass in the caller's stream (the in-kernel encode is the default, see below)
+    enc_mode_v = encode_mode(N);
+    if (need_encode && enc_mode_v == 1) {
+      // stand-alone pre-pass in the caller's stream
       const int rounding = static_cast<int>(dbg("enc_rounding", 0));
       const int grid = 4 * h->num_sms;
 #define FT_ENC(bn) \
@@ -395,8 +419,10 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     if (rc) return rc;
   }
   // ---- work plan (plan.h), cached per shape on the handle
-  const PlanInput pin = make_plan_input(h->num_sms, CG, BN, K, p);
-  const std::array<long long, 6> key = {v.info.id, M, N, K, pin.units, pin.force_slices * 16 + pin.max_slices};
+  const bool encode_items = ft && need_encode && enc_mode_v == 2;
+  const PlanInput pin = make_plan_input(h->num_sms, CG, BN, K, p, encode_items);
+  const std::array<long long, 6> key = {v.info.id, M, N, K, pin.units,
+                                        pin.force_slices * 16 + pin.max_slices + (encode_items ? 1024 : 0) + pin.lockstep * 2048};
   ftsgemm_handle_s::CachedPlan &cp = h->plans[key];
   if (!cp.uploaded) {
     if (h->plans.size() > 64) {  // bound the cache: drop everything but this entry
@@ -438,7 +464,37 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     }
     p.sk_epoch = ++h->sk_epoch;
   }
-  if (ft && dbg("enc_mode", 1) == 0) {
+  if (encode_items) {
+    // Encoder items: per launch every helper warp of every encoder unit adds 1 to each k-chunk counter; the counters
+    // are monotonic while the shape stays the same and are cleared when it changes.
+    const int n_chunks = ((K + kBK - 1) / kBK + 31) / 32;
+    int workers = 4;
+    if (BN == 32) workers = TileCfg<32, true, 1>::kEncWorkers;
+    else if (BN == 64) workers = TileCfg<64, true, 1>::kEncWorkers;
+    else if (BN == 128) workers = CG == 1 ? TileCfg<128, true, 1>::kEncWorkers : TileCfg<128, true, 2>::kEncWorkers;
+    else workers = CG == 1 ? TileCfg<256, true, 1>::kEncWorkers : TileCfg<256, true, 2>::kEncWorkers;
+    const int inc = workers * CG * p.tiles_n;  // every ENCODE worker warp reports every k-chunk once
+    const std::array<long long, 4> shape = {N, K, BN, CG};
+    if (h->d_enc_prog == nullptr || h->enc_prog_cap < n_chunks) {
+      if (h->d_enc_prog) FT_CUDA(h, cudaFree(h->d_enc_prog));
+      h->d_enc_prog = nullptr;
+      FT_CUDA(h, cudaMalloc(&h->d_enc_prog, static_cast<size_t>(n_chunks) * sizeof(int)));
+      h->enc_prog_cap = n_chunks;
+      h->enc_prog_shape = {0, 0, 0, 0};
+    }
+    if (h->enc_prog_shape != shape || h->enc_prog_value > (1 << 30) - inc) {
+      FT_CUDA(h, cudaMemsetAsync(h->d_enc_prog, 0, static_cast<size_t>(h->enc_prog_cap) * sizeof(int), stream));
+      h->enc_prog_shape = shape;
+      h->enc_prog_value = 0;
+    }
+    h->enc_prog_value += inc;
+    p.enc_prog = h->d_enc_prog;
+    p.enc_prog_target = h->enc_prog_value;
+    p.enc_out = h->d_chk;
+    p.enc_ld = chk_ld_v;
+    p.enc_rounding = static_cast<int>(dbg("enc_rounding", 0));
+  }
+  if (ft && enc_mode_v == 0) {
     // In-kernel encode: the helper warps of every CTA stream their share of B while the first main loops run; checksum
     // items wait until all of them have reported (monotonic counter, so a launch that reuses the vectors waits for
     // nothing new).
@@ -584,7 +640,8 @@ int ftsgemm_debug_schedule(int kernel_id, int M, int N, int K, int num_sms, int 
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
   plan_tiles(M, N, v->bn, v->cg, v->info.fault_tolerant != 0, &p);
-  const PlanInput pin = make_plan_input(num_sms, v->cg, v->bn, K, p);
+  const bool encode_items = v->info.fault_tolerant != 0 && encode_mode(N) == 2 && p.tiles_c > 0;
+  const PlanInput pin = make_plan_input(num_sms, v->cg, v->bn, K, p, encode_items);
   const Plan plan = build_plan(pin);
   if (hdr) {
     hdr[0] = plan.units; hdr[1] = pin.n_chk_tiles + pin.n_data_tiles; hdr[2] = pin.n_chk_tiles; hdr[3] = plan.sk_tiles;
@@ -595,7 +652,9 @@ int ftsgemm_debug_schedule(int kernel_id, int M, int N, int K, int num_sms, int 
     for (int i = plan.offsets[u]; i < plan.offsets[u + 1]; ++i) {
       const PlanItem &it = plan.items[i];
       if (rows && n < cap) {
-        const TileCoord tc = decode_tile(p, it.tile);
+        TileCoord tc;
+        if (it.kind == 4) { tc.is_chk = false; tc.m_blk = -1; tc.n_blk = it.tile; }
+        else tc = decode_tile(p, it.tile);
         int *r = rows + 9 * n;
         r[0] = u; r[1] = it.tile; r[2] = tc.is_chk ? 1 : 0; r[3] = tc.m_blk; r[4] = tc.n_blk;
         r[5] = it.kb_begin; r[6] = it.kb_end; r[7] = it.kind; r[8] = it.slice;
@@ -673,6 +732,7 @@ int ftsgemm_destroy(ftsgemm_handle_t h) {
   cudaFree(h->d_sk);
   cudaFree(h->d_trace);
   cudaFree(h->d_enc_count);
+  cudaFree(h->d_enc_prog);
   for (auto &kv : h->plans) {
     cudaFree(kv.second.d_items);
     cudaFree(kv.second.d_off);

@@ -83,7 +83,8 @@ struct KernelParams {
   int dbg_flags;        // experiments only: bit 0 = skip the epilogue ABFT check of data tiles
   // Work plan (built on the host, plan.h): unit u executes items plan[plan_off[u] .. plan_off[u+1]) in order.
   //   item.x = tile (decode order: checksum tiles first), item.y = kb_begin | kb_end << 16,
-  //   item.z = kind (0 whole tile, 1 first piece, 3 middle piece, 2 last piece of a cut tile) | piece << 8,
+  //   item.z = kind (0 whole tile, 1 first piece, 3 middle piece, 2 last piece of a cut tile, 4 encoder item:
+  //            tile = tile-column of B, no accumulator) | piece << 8,
   //   item.w = index among the cut tiles
   // The last sk_tiles data tiles are cut along K into up to sk_slices pieces so that the list scheduler can level the
   // units' finishing times.  Piece p parks its raw accumulator; piece p+1 loads it into tensor memory BEFORE its first
@@ -110,6 +111,12 @@ struct KernelParams {
   int enc_rounding;
   int *enc_count;       // != nullptr: every helper warp adds 1 when its share is written; checksum items wait until
   int enc_target;       //             the counter has reached enc_target (a later launch that reuses B waits for nothing new)
+  // encoder items (kind 4, always a prefix of a unit's list): the unit streams B[tile-column] through the shared-memory
+  // ring and its helper warps write the checksum vectors; every helper warp adds 1 to enc_prog[c] when its share of the
+  // k-blocks [32c, 32c+32) of the tile-column is done, checksum items wait for enc_prog[c] >= enc_prog_target before
+  // k-block 32c
+  int *enc_prog;
+  int enc_prog_target;
   float tau_abs, tau_rel;
   int detect_only;
   int inject_mode;
@@ -150,6 +157,10 @@ struct TileCfg {
   static constexpr int kStagesFit = kMaxSmem / kStageBytes;
   static constexpr int kStages = kStagesFit > FTSGEMM_MAX_STAGES ? FTSGEMM_MAX_STAGES : kStagesFit;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kBarBytes;
+  // ENCODE workers of an encoder item (helper warps first, then epilogue warps): each owns every kEncWorkers-th ring slot.
+  // A worker's parity wait on a stage is only unambiguous if its previous slot is not older than the stage's previous
+  // use, i.e. kEncWorkers <= kStages (8 workers on a 7-stage ring read unfilled stages: measured as a hang).
+  static constexpr int kEncWorkers = kStages < 8 ? kStages : 8;
 };
 
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
@@ -211,7 +222,7 @@ __host__ __device__ __forceinline__ int chk_tile_width(const KernelParams &p, in
 // ------------------------------------------------------------------------------------------------------------
 struct Segment {
   int tile, kb_begin, kb_end;
-  int kind;   // 0 whole tile, 1 contributor, 2 finisher
+  int kind;   // 0 whole tile, 1 first piece, 3 middle piece, 2 last piece, 4 encoder item
   int slice;
   int split_idx;
 };
@@ -611,6 +622,51 @@ __device__ __forceinline__ void encode_b_warp(const float *__restrict__ B, int N
   }
 }
 
+// ENCODE from shared memory (encoder items).  One ring stage holds B[n0 .. n0+BN) x 32 k-rows exactly as the UMMA
+// operand layout has it: [atom = 32 n][k][32 floats], 128-byte rows whose four 32-byte granules are XOR-ed with (k & 3)
+// (SWIZZLE_128B with 32-byte atoms).  One call reduces k-rows 8g .. 8g+7 of a stage: every lane sums float4 pieces of
+// a row, the 32-lane totals are formed by the transposing butterfly, and lane 2i writes the (hi, lo) TF32 pair of value
+// i (e and w of 8 rows) to the checksum operand.  A helper warp owns whole stages (every 4th slot of the ring), so the
+// four warps work on four stages at once and nothing but the stage's own barriers synchronises them.
+template <int BN>
+__device__ __forceinline__ void encode_stage_rows(uint32_t stage_base, int g, int lane, int kb, int K, int t,
+                                                  float *__restrict__ chk, int chk_ld) {
+  // Instruction budget matters: one warp has ~2.5k cycles per 32 KiB stage.  Per float4: 4 mask operations (the
+  // truncation the tensor core applies), s = sum of the four, t = b1 + 2 b2 + 3 b3, e += s, w += w0 * s + t.
+  double v[16];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int kr = g * 8 + u;
+    float e = 0.0f, w = 0.0f;
+#pragma unroll
+    for (int idx0 = 0; idx0 < BN / 4; idx0 += 32) {
+      const int idx = idx0 + lane;  // float4 index within the k-row (over all atoms)
+      if (BN / 4 >= 32 || idx < BN / 4) {
+        const int atom = idx >> 3, c4 = idx & 7;
+        const float4 x = ptx::ld_shared_f4(stage_base + atom * (kBK * 128) + kr * 128 + c4 * 16);
+        const int granule = (c4 >> 1) ^ (kr & 3);
+        const float w0 = static_cast<float>(atom * 32 + granule * 8 + (c4 & 1) * 4 + 1);
+        const float b0 = u2f(f2u(x.x) & 0xFFFFE000u), b1 = u2f(f2u(x.y) & 0xFFFFE000u),
+                    b2 = u2f(f2u(x.z) & 0xFFFFE000u), b3 = u2f(f2u(x.w) & 0xFFFFE000u);
+        const float s4 = (b0 + b1) + (b2 + b3);
+        const float t4 = fmaf(3.0f, b3, fmaf(2.0f, b2, b1));
+        e += s4;
+        w += fmaf(w0, s4, t4);
+      }
+    }
+    v[2 * u] = static_cast<double>(e);
+    v[2 * u + 1] = static_cast<double>(w);
+  }
+  int idx = 0;
+  TransposeReduce<16, 16>::run(v, lane, idx);
+  const int k = kb * kBK + g * 8 + (idx >> 1);
+  if ((lane & 1) == 0 && k < K) {
+    float h, l;
+    split2_tf32(v[0], h, l);
+    *reinterpret_cast<float2 *>(chk + static_cast<size_t>(k) * chk_ld + t * kChkPerTile + (idx & 1) * 2) = make_float2(h, l);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // The kernel.
 // ------------------------------------------------------------------------------------------------------------
@@ -632,7 +688,9 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   auto seeded_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 4 + a); };  // leader: TMEM stage a holds the seed
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 6);
+  // peer CTA only: the leader has consumed its last encoder slot (see the producer)
+  const uint32_t pair_bar = bar_base + 8u * (2 * kStages + 6);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 7);
   // number of (epilogue warp, item) pairs this CTA has finished: the helper warps' view of which accumulator stages
   // are drained (a counter, not an mbarrier: the helpers may be many items behind while they encode B)
   const uint32_t epi_count = tmem_slot + 8u;
@@ -661,6 +719,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ptx::mbar_init(seeded_bar(a), 4 * CG);  // one arrive per helper warp of every CTA in the group
     }
     ptx::st_shared_u32(epi_count, 0u);
+    ptx::mbar_init(pair_bar, 1);
     ptx::fence_mbar_init();
   }
   if (CG == 2) ptx::cluster_sync_all();  // peer barriers must be initialised before any remote arrive / 2-CTA alloc
@@ -679,6 +738,52 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // ENCODE workers (encoder items, kind 4): the four helper warps and the four epilogue warps (idle until the first
+  // accumulator is complete) share the ring slots of the encoder prefix, worker w8 taking slots w8, w8 + 8, ...
+  constexpr int kEncWorkers = Cfg::kEncWorkers;
+  auto encoder_prefix = [&](int w8) {
+    if (w8 >= kEncWorkers) return;
+    int base = 0;   // ring slots consumed by earlier encoder items
+    int n_enc = 0;
+    SegIter it(p, unit);
+    Segment sg;
+    if (p.trace != nullptr && is_leader && w8 == 0 && lane == 0) trace_put(p, unit, p.trace_cap - 1, 1, globaltimer_ns());
+    while (it.next(sg) && sg.kind == 4) {
+      ++n_enc;
+      const int slots = (sg.kb_end + CG - 1) / CG;
+      const int n_chunks = (sg.kb_end + 31) >> 5;
+      int signalled = 0;  // chunks this warp has reported
+      for (int j = w8; j < slots; j += kEncWorkers) {
+        const int abs_slot = base + j;
+        const int stage = abs_slot % kStages;
+        ptx::mbar_wait(full_bar(stage), static_cast<uint32_t>(abs_slot / kStages) & 1u);
+        const int kb = j * CG + static_cast<int>(cta_rank);
+#pragma unroll 1
+        for (int g = 0; g < kBK / 8; ++g)
+          encode_stage_rows<BN>(smem_base + stage * Cfg::kStageBytes, g, lane, kb, p.K, sg.tile, p.enc_out, p.enc_ld);
+        __syncwarp();  // every lane has read the stage
+        if (lane == 0) ptx::mbar_arrive(empty_bar(stage));
+        // report k-chunk c (32 k-blocks) once this warp's last slot of it is written
+        const int c = (j * CG) >> 5;
+        if (j + kEncWorkers >= slots || (((j + kEncWorkers) * CG) >> 5) != c) {
+          __threadfence();
+          __syncwarp();
+          if (lane == 0)
+            for (int cc = signalled; cc <= c; ++cc) atomicAdd(p.enc_prog + cc, 1);  // (chunks without a slot of this warp too)
+          signalled = c + 1;
+        }
+      }
+      if (lane == 0)
+        for (int c = signalled; c < n_chunks; ++c) atomicAdd(p.enc_prog + c, 1);  // short tail: chunks without a slot
+      base += slots;
+      if (p.trace != nullptr && is_leader && w8 == 0 && lane == 0) trace_put(p, unit, p.trace_cap - 1, 0, globaltimer_ns());
+    }
+    if (n_enc > 0 && is_leader) {
+      ptx::named_bar_sync(2, 32 * (kEncWorkers + 1));  // workers + the UMMA warp: releases the UMMA warp (see there) ...
+      if (CG == 2 && w8 == 0 && lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(pair_bar, 1));  // ... and the peer's producer
+    }
+  };
+
   if (warp == 0) {
     // ===================================================================== TMA producer (every CTA)
     // warp-uniform loop, one elected lane issues the TMA instructions (see ptx::elect_one)
@@ -687,6 +792,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     SegIter it(p, unit);
     Segment sg;
     int item_idx = -1;
+    bool enc_prefix = false;
     if (FT && (p.dbg_flags & 4) && p.enc_count != nullptr) {
       // experiment: "foreground" encode -- no main loop starts before the whole encode is done
       if (lane == 0) {
@@ -700,6 +806,40 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     while (it.next(sg)) {
       ++item_idx;
+      if (FT && sg.kind == 4) {
+        // encoder item: this CTA streams k-blocks j*CG + rank of tile-column sg.tile of B through the ring (whole BN
+        // rows per stage, no A, no UMMA); its helper warps consume the stages.  Every CTA of the group takes the same
+        // number of slots (a slot past the end of K is zero-filled by TMA), so the rings stay in step.
+        const int b_atom0 = sg.tile * (BN / kAtomMN);
+        const int slots = (sg.kb_end + CG - 1) / CG;
+        for (int j = 0; j < slots; ++j) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sA = smem_base + stage * Cfg::kStageBytes;
+          const int k0 = (j * CG + static_cast<int>(cta_rank)) * kBK;
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(full_bar(stage), static_cast<uint32_t>(CG * Cfg::kBBytes));
+            if (CG == 2) ptx::mbar_arrive(full_bar(stage));  // the barrier counts CG arrivals (normally the peer's)
+#pragma unroll
+            for (int i = 0; i < CG; ++i)
+              ptx::tma_load_3d(sA + i * Cfg::kBBytes, &tmB, full_bar(stage), 0, k0, b_atom0 + i * (Cfg::kBNLocal / kAtomMN));
+          }
+          __syncwarp();
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        enc_prefix = true;
+        continue;
+      }
+      if (FT && CG == 2 && enc_prefix && !is_leader) {
+        // In ordinary items this CTA's loads are credited to the LEADER's full barriers.  During the encoder slots both
+        // CTAs run their own barriers at their own pace, so the peer must not touch the leader's barriers before the
+        // leader's helpers have consumed the leader's last encoder slot (measured: without this the pair desynchronised
+        // at K = 8192).
+        ptx::mbar_wait(pair_bar, 0u);
+        enc_prefix = false;
+      }
       const TileCoord tc = decode_tile(p, sg.tile);
       const int m0 = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;        // this CTA's 128 rows of A
       const bool b_is_chk = FT && tc.is_chk;
@@ -730,6 +870,18 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t stage_tx = b_is_chk ? static_cast<uint32_t>(Cfg::kABytes + p.chk_box_bytes)
                                            : static_cast<uint32_t>(Cfg::kStageBytes);
         for (int kb = sg.kb_begin; kb < sg.kb_end; ++kb) {
+          if (FT && b_is_chk && p.enc_prog != nullptr && (kb & 31) == 0) {
+            // the checksum vectors of k-blocks [kb, kb + 32) come from the encoder items running on other units
+            if (lane == 0) {
+              ptx::Watchdog wd;
+              while (ld_acquire(p.enc_prog + (kb >> 5)) - p.enc_prog_target < 0) {
+                __nanosleep(64);
+                wd.tick();
+              }
+            }
+            __syncwarp();
+            ptx::fence_proxy_async();  // generic-proxy writes (st.global) -> async-proxy reads (TMA)
+          }
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sA = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sB = sA + Cfg::kABytes;
@@ -759,6 +911,17 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         else fast_loop(&tmB);
       } else {
         for (int kb = sg.kb_begin; kb < sg.kb_end; ++kb) {
+          if (FT && b_is_chk && p.enc_prog != nullptr && (kb & 31) == 0) {
+            if (lane == 0) {
+              ptx::Watchdog wd;
+              while (ld_acquire(p.enc_prog + (kb >> 5)) - p.enc_prog_target < 0) {
+                __nanosleep(64);
+                wd.tick();
+              }
+            }
+            __syncwarp();
+            ptx::fence_proxy_async();
+          }
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sA = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sB = sA + Cfg::kABytes;
@@ -816,11 +979,25 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t seed_phase = 0;  // bit a: parity of seeded_bar(a)
+    bool enc_pending = false;
     SegIter it(p, unit);
     Segment sg;
     int item_idx = -1;
     while (it.next(sg)) {
       ++item_idx;
+      if (FT && sg.kind == 4) {  // encoder item: no UMMA, but the ring moved on by the same number of slots
+        const int adv = stage + (sg.kb_end + CG - 1) / CG;
+        if ((adv / kStages) & 1) phase ^= 1u;
+        stage = adv % kStages;
+        enc_pending = true;
+        continue;
+      }
+      if (FT && enc_pending) {
+        // A parity wait is only unambiguous within one phase of the barrier: this warp took no part in the encoder
+        // slots, so it must not look at a full barrier before the helper warps have consumed the last of them.
+        ptx::named_bar_sync(2, 32 * (Cfg::kEncWorkers + 1));
+        enc_pending = false;
+      }
       uint32_t idesc_t = idesc;
       if (FT) {
         const TileCoord tc = decode_tile(p, sg.tile);
@@ -878,6 +1055,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         acc_phase ^= 1u;
       }
     }
+    if (FT && enc_pending) ptx::named_bar_sync(2, 32 * (Cfg::kEncWorkers + 1));  // a unit with encoder items only
   } else if (warp >= 4 && warp < 8) {
     // ===================================================================== epilogue (4 warps per CTA, lane = row)
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
@@ -890,8 +1068,10 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const size_t ws_slab = static_cast<size_t>(kBM) * BN;  // floats per (unit, CTA) partial tile
     int item_idx = -1;
     const bool tracer = p.trace != nullptr && is_leader && q == 0 && lane == 0;
+    if (FT && p.enc_prog != nullptr) encoder_prefix(4 + q);
     while (it.next(sg)) {
       ++item_idx;
+      if (FT && sg.kind == 4) continue;  // encoder items have no accumulator
       const TileCoord tc = decode_tile(p, sg.tile);
       const int m0_cta = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;
       const int n0 = (FT && tc.is_chk) ? tc.n_blk * chk_cols_per_tile(BN) : tc.n_blk * BN;
@@ -964,7 +1144,8 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   else if (warp >= 8) {
     // ===================================================================== helper warps (TMEM lane quadrant = warp & 3)
     const int q = warp & 3;
-    if (FT && p.enc_b != nullptr) {
+    if (FT && p.enc_prog != nullptr) encoder_prefix(q);
+    if (FT && p.enc_b != nullptr && p.enc_count != nullptr) {
       if (p.trace != nullptr && is_leader && q == 0 && lane == 0) trace_put(p, unit, p.trace_cap - 1, 1, globaltimer_ns());
       encode_b_warp<BN>(p.enc_b, p.N, p.K, p.enc_ldb, p.enc_out, p.enc_ld, p.enc_rounding, p.tiles_n,
                         static_cast<int>(blockIdx.x) * 4 + q, static_cast<int>(gridDim.x) * 4, lane);
@@ -981,6 +1162,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       SegIter it(p, unit);
       Segment sg;
       while (it.next(sg)) {
+        if (FT && sg.kind == 4) continue;  // no accumulator
         ++item_idx;
         if (sg.kind >= 2) {
           // the accumulator stage must have been drained by this CTA's four epilogue warps (item_idx - 2 and before)

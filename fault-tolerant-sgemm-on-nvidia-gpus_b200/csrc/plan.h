@@ -13,8 +13,10 @@
 // as in the checksum tile-columns.  (Adding independently accumulated partial sums, the usual split-K, raised the
 // fault-free ABFT residual 6x, profiles/r01_probe8_residual_vs_splitk.jsonl.)
 //
-// Global item order:  [early first pieces][checksum tiles][whole data tiles, raster order][late first pieces]
-//                     [2nd pieces][3rd pieces]...
+// Global item order:  [encoder items][early first pieces][checksum tiles][whole data tiles, raster order]
+//                     [late first pieces][2nd pieces][3rd pieces]...
+//   * encoder items (ABFT, one per tile-column of B) produce the checksum vectors the checksum tiles consume; they wait
+//     for nothing and must be a prefix of their unit's list (the helper warps consume the ring from its initial state);
 //   * early first pieces run at the very start: their epilogue only parks the accumulator (no checksum needed); made as
 //     long as a checksum item they keep all units in step (the units that share A / B panels then stream the same k range);
 //   * late first pieces and all later pieces run at the end, longest first, and level the finishing times.
@@ -29,9 +31,10 @@
 namespace ftsgemm {
 
 struct PlanItem {
-  int tile;        // decode order: checksum tiles first, then data tiles
+  int tile;        // decode order: checksum tiles first, then data tiles (encoder items: the tile-column of B)
   int kb_begin, kb_end;
-  int kind;        // 0 whole tile, 1 first piece (park), 3 middle piece (seed + park), 2 last piece (seed + finish)
+  int kind;        // 0 whole tile, 1 first piece (park), 3 middle piece (seed + park), 2 last piece (seed + finish),
+                   // 4 encoder item (streams a tile-column of B through shared memory and writes its checksum vectors)
   int slice;       // piece index within its tile
   int split_idx;   // index among the cut tiles (workspace slot), -1 otherwise
 };
@@ -53,6 +56,8 @@ struct PlanInput {
   int tiles_m;          // checksum tile t belongs to checksum tile-column t / tiles_m
   std::vector<double> chk_col_cost;  // tile-times of one tile of each checksum tile-column
   double chk_release = 0.0;          // tile-times before checksum items can start (in-kernel encode of B)
+  int n_enc_items = 0;               // encoder items (one per tile-column of B), first in every unit's list
+  double enc_cost = 0.0;             // tile-times of one encoder item
   double item_overhead = 0.0;        // tile-times per item (pipeline fill + drain)
   double park_latency = 0.0;         // tile-times between the end of a piece's main loop and its successor's start
   double seed_overhead = 0.0;        // extra tile-times of a seeded piece (its accumulator stage is loaded before the first UMMA)
@@ -128,6 +133,7 @@ inline double schedule(const PlanInput &in, const Cut &c, Plan *out) {
                             len + (p > 0 ? in.seed_overhead : 0.0), ready[i], false);
     ready[i] = end + in.park_latency;
   };
+  for (int t = 0; t < in.n_enc_items; ++t) give(PlanItem{t, 0, in.num_kb, 4, 0, -1}, in.enc_cost, 0.0, false);
   for (int i = 0; i < c.He; ++i) piece(i, 0);
   for (int t = 0; t < in.n_chk_tiles; ++t)
     give(PlanItem{t, 0, in.num_kb, 0, 0, -1}, in.chk_col_cost[static_cast<size_t>(t / in.tiles_m)], in.chk_release, false);

@@ -50,9 +50,11 @@ enum {
   FTSGEMM_ID_ABFT_BASELINE = 10,
   FTSGEMM_ID_ABFT_SMALL = 11, FTSGEMM_ID_ABFT_MEDIUM = 12, FTSGEMM_ID_ABFT_LARGE = 13,
   FTSGEMM_ID_ABFT_TALL = 14, FTSGEMM_ID_ABFT_WIDE = 15, FTSGEMM_ID_ABFT_HUGE = 16,
-  FTSGEMM_ID_SGEMM_GIANT = 21,       /* 128 x 256 tile, plain  (B200 extra) */
+  FTSGEMM_ID_SGEMM_GIANT = 21,       /* 256 x 256 tile on a CTA pair (cta_group::2), plain  (B200 extra) */
+  FTSGEMM_ID_SGEMM_PAIR128 = 22,     /* 256 x 128 tile on a CTA pair, plain  (B200 extra) */
   FTSGEMM_ID_ABFT_BASELINE_TF32 = 30,/* non-fused baseline with TF32 tensor-op math */
-  FTSGEMM_ID_ABFT_GIANT = 31         /* 128 x 256 tile, fused ABFT (B200 extra) */
+  FTSGEMM_ID_ABFT_GIANT = 31,        /* 256 x 256 CTA-pair tile, fused ABFT: the bench configuration (B200 extra) */
+  FTSGEMM_ID_ABFT_PAIR128 = 32       /* 256 x 128 CTA-pair tile, fused ABFT (B200 extra) */
 };
 
 typedef struct ftsgemm_handle_s *ftsgemm_handle_t;
@@ -95,7 +97,8 @@ typedef struct ftsgemm_opts {
    * (ft_sgemm_huge.cuh:50). */
   float tau_abs, tau_rel;
   int detect_only;       /* 1: count detections but do not correct */
-  int reuse_b_checksums; /* 1: B is unchanged since the previous FT call on this handle -> skip the encode pass */
+  int reuse_b_checksums; /* 1: B is unchanged since the previous FT call on this handle -> reuse its checksum vectors
+                            (no encoder items in this launch) */
   int baseline_host_sync;/* id 10/30: 1 = host-synchronise between stages like the reference
                             (baseline_ft_sgemm.cuh:7,19,26,30); 0 = stream-ordered */
 } ftsgemm_opts;

@@ -98,16 +98,17 @@ def test_ft_equals_plain_bitwise_when_fault_free(cuda, ft, dev):
 
 
 def test_encode_in_kernel_and_prepass_agree(cuda, ft, dev):
-    """The checksum vectors of B are normally encoded by the GEMM kernel's own helper warps in the background of the first
-    main loops (checksum items wait on a counter); the stand-alone pre-pass kernel and the cached-checksum path must give
-    bit-identical results and verdicts."""
+    """The checksum vectors of B are normally produced inside the GEMM kernel by encoder items (a unit streams a
+    tile-column of B through its shared-memory ring, the helper warps reduce it, checksum items follow k-chunk by
+    k-chunk); the stand-alone pre-pass kernel (mode 1), the background global-memory encode (mode 0) and the
+    cached-checksum path must give bit-identical results and verdicts."""
     rng = np.random.default_rng(5)
     M, N, K = 1024, 1280, 768
     A, B = _rand(rng, M * K), _rand(rng, N * K)
     C0 = rng.standard_normal(M * N).astype(np.float32)
     faults = [{"row": 77, "col": 300, "xor": 1 << 29}, {"row": 900, "col": 1279, "add": -55.0}]
     outs = []
-    for mode in (0, 1):
+    for mode in (2, 1, 0):
         try:
             ft.debug_set("enc_mode", mode)
             dev.stats()
@@ -118,7 +119,7 @@ def test_encode_in_kernel_and_prepass_agree(cuda, ft, dev):
             outs.append(got)
         finally:
             ft.debug_set("enc_mode", -1)
-    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
     dA, dB = cuda.from_numpy(A).cuda(), cuda.from_numpy(B).cuda()
     dC = cuda.from_numpy(C0.copy()).cuda()
     dev.run(31, M, N, K, dA, dB, dC, 1.0, -1.5, ft.make_opts(faults=faults))
@@ -132,7 +133,7 @@ def test_encode_in_kernel_and_prepass_agree(cuda, ft, dev):
     C2 = np.zeros(M2 * N2, np.float32)
     for kid in (11, 12, 16, 15, 31, 32):
         res = []
-        for mode in (0, 1):
+        for mode in (2, 1, 0):
             try:
                 ft.debug_set("enc_mode", mode)
                 dev.stats()
@@ -141,7 +142,7 @@ def test_encode_in_kernel_and_prepass_agree(cuda, ft, dev):
                 assert st["detected"] == st["corrected"] > 0 and st["uncorrectable"] == 0, (kid, mode, st)
             finally:
                 ft.debug_set("enc_mode", -1)
-        assert np.array_equal(res[0], res[1]), kid
+        assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2]), kid
 
 
 @pytest.mark.parametrize("slices", [2, 3, 5])
