@@ -64,9 +64,14 @@ def _simulate(hdr, segs, acc_stages):
                                    (1536, 2560, 1000), (256, 256, 64), (128, 4096, 32), (5120, 384, 4096),
                                    (16384, 16384, 1024), (32768, 1024, 256)])
 @pytest.mark.parametrize("num_sms", [148, 16, 6])
-def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms):
+@pytest.mark.parametrize("enc_mode", [1, 2])  # pre-pass kernel | encoder items inside the GEMM kernel
+def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms, enc_mode):
     M, N, K = shape
-    hdr, segs = ft.debug_schedule(kid, M, N, K, num_sms)
+    try:
+        ft.debug_set("enc_mode", enc_mode)
+        hdr, segs = ft.debug_schedule(kid, M, N, K, num_sms)
+    finally:
+        ft.debug_set("enc_mode", -1)
     units, num_kb, H, S = hdr["units"], hdr["num_kb"], hdr["sk_tiles"], hdr["sk_slices"]
     assert hdr["num_kb"] == -(-K // 32)
     first_cut = hdr["num_tiles"] - H
@@ -81,7 +86,7 @@ def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms):
         cover.setdefault(s["tile"], []).append((s["kb_begin"], s["kb_end"], s["kind"], s["slice"]))
         if s["kind"] != 0:
             assert s["tile"] >= first_cut and not s["is_chk"]
-    if kid in (11, 12, 16, 15, 31, 32) and N % 32 == 0:
+    if kid in (11, 12, 16, 15, 31, 32) and N % 32 == 0 and enc_mode == 2:
         assert sorted(enc_cols) == list(range(-(-N // TILE_N[kid])))
     else:
         assert not enc_cols
