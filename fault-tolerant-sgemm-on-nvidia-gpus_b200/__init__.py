@@ -270,6 +270,7 @@ class FtSgemm:
             if items:
                 items[0]["enc_end"] = buf[(u * 64 + 63) * 8]  # helper warps finished their share of the in-kernel encode
                 items[0]["enc_start"] = buf[(u * 64 + 63) * 8 + 1]
+                items[0]["enc_worker0"] = (buf[(u * 64 + 63) * 8 + 2], buf[(u * 64 + 63) * 8 + 3], buf[(u * 64 + 63) * 8 + 5])
             out.append(items)
         return out
 

@@ -221,22 +221,39 @@ void chk_costs(const KernelParams &p, std::vector<double> *out) {
     out->push_back(std::max(0.58, static_cast<double>(chk_tile_width<BNv, CGv>(p, c)) / BNv));
 }
 
-// How the checksum vectors of B are produced (debug knob enc_mode; -2 = automatic):
-//   2  encoder items inside the GEMM kernel: one unit per tile-column streams B through its shared-memory ring and its
-//      helper + epilogue warps reduce it (needs the 3-D tensor map of B, i.e. N % 32 == 0).  One launch per GEMM, but
-//      the items run while every SM is fetching cold operands and get 1/148 of the HBM bandwidth each: ~1.2 tile-times
-//      per item, the same cost as the pre-pass (715 vs 709 TFLOP/s at 4096^3, 781 vs 785 at 8192^3)
-//   1  stand-alone pre-pass kernel in front of the GEMM (10.7 us per step at 4096^3 in a loop: 5.6 %)   [default]
-//   0  helper warps read their share of B from global memory in the background (measured 3-8x slower: they cannot keep
-//      enough bytes in flight next to the main loop)
-int encode_mode(int N) {
+// How the checksum vectors of B are produced (debug knob enc_mode; default 1).  Four variants were built and measured
+// (profiles/r01_probe12_*, r01_probe14_*, r01_trace_*); whichever way the 4*N*K bytes of B are summed it costs about the
+// same machine time, so the simplest one is the default:
+//   1  stand-alone pre-pass kernel in front of the GEMM: 10.7 us per step at 4096^3 in a loop (5.6 %), ~45 us at 8192^3
+//      (3 %); B is left in L2 for the GEMM's first wave                                                    [default]
+//   3  encoder TILES: the first data tile of every tile-column also reduces its own B stages from shared memory -- no
+//      extra HBM / L2 traffic, one launch per GEMM.  The two ENCODE workers of a k-block (one per CTA, 16 k-rows each, the
+//      other CTA's half read through distributed shared memory) need ~1.9 us per stage, and a stage is only refilled
+//      after that, so an encoder tile's main loop runs at 0.55 instead of 0.33 us per k-block (77 vs 42 us at 4096^3):
+//      695 vs 691 TFLOP/s at 4096^3, 755 vs 770 at 8192^3
+//   2  encoder ITEMS: one unit per tile-column streams B through its shared-memory ring (no UMMA) and reduces it.  The
+//      items run while every SM is fetching cold operands and get 1/148 of the HBM bandwidth each: ~1.2 tile-times per
+//      item (715 vs 709 TFLOP/s at 4096^3, 781 vs 785 at 8192^3)
+//   0  helper warps read their share of B from global memory in the background (3-8x slower: they cannot keep enough
+//      bytes in flight next to the main loop)
+// Modes 2 / 3 need the 3-D tensor map of B (N % 32 == 0); mode 3 also needs spare units for the checksum items.
+int encode_mode(int N, int tiles_n, int units) {
   const long long m = dbg("enc_mode", -2);
   const bool items_ok = N % kAtomMN == 0 && dbg("enc_rounding", 0) == 0;  // (the rounding experiment only exists in modes 0/1)
-  if (m >= 0 && m <= 2 && !(m == 2 && !items_ok)) return static_cast<int>(m);
+  const bool tiles_ok = items_ok && 2 * tiles_n <= units;
+  if (m == 3) return tiles_ok ? 3 : 1;
+  if (m == 2) return items_ok ? 2 : 1;
+  if (m == 0) return 0;
   return 1;
 }
 
-PlanInput make_plan_input(int num_sms, int CG, int BN, int K, const KernelParams &p, bool encode_items) {
+// raster index (among the data tiles) of tile (m_blk = 0, n_blk = t): inverse of decode_tile
+int encoder_tile_index(const KernelParams &p, int t) {
+  const int g = t / p.group_n;
+  return g * p.group_n * p.tiles_m + (t - g * p.group_n);
+}
+
+PlanInput make_plan_input(int num_sms, int CG, int BN, int K, const KernelParams &p, int enc_plan /* 0 none, 2 items, 3 tiles */) {
   PlanInput in;
   long long units = dbg("grid", 0);
   in.units = units > 0 ? static_cast<int>(units) : num_sms / CG;
@@ -263,13 +280,18 @@ PlanInput make_plan_input(int num_sms, int CG, int BN, int K, const KernelParams
   in.lockstep = lock >= 0 ? static_cast<int>(lock)
                           : (4.0 * K * (static_cast<double>(p.M) + p.N) > 96.0 * 1024 * 1024 ? 1 : 0);
   in.chk_release = 0.0;
-  if (p.tiles_c > 0 && encode_items) {
-    // one encoder item per tile-column of B; the checksum tiles follow them k-chunk by k-chunk, so they can start almost
-    // at once but cannot finish before the encoders do
+  if (p.tiles_c > 0 && enc_plan == 3) {
+    // the first data tile of every tile-column encodes it; the checksum tiles follow the encoders k-chunk by k-chunk:
+    // started 0.45 tile-times in they never catch up with them (0.45 + 0.58 f >= f)
+    for (int t = 0; t < p.tiles_n; ++t) in.enc_tiles.push_back(encoder_tile_index(p, t));
+    in.enc_tile_cost = static_cast<double>(dbg("enc_tile_cost_permille", 1850)) * 1e-3;
+    in.chk_release = std::max(0.0, in.enc_tile_cost - in.chk_col_cost[0]) + 0.02;
+  } else if (p.tiles_c > 0 && enc_plan == 2) {
+    // one encoder item per tile-column of B; the checksum tiles follow them k-chunk by k-chunk
     in.n_enc_items = p.tiles_n;
     in.enc_cost = static_cast<double>(dbg("enc_cost_permille", 1200)) * 1e-3;
     in.chk_release = std::max(0.0, in.enc_cost - in.chk_col_cost[0]) + 0.05;
-  } else if (p.tiles_c > 0 && encode_mode(p.N) == 0) {
+  } else if (p.tiles_c > 0 && dbg("enc_mode", -2) == 0) {
     // helper warps stream B from global memory in the background (~1 TB/s next to the main loops)
     const double enc_us = 4.0 * static_cast<double>(p.N) * K / 1.0e6 + 3.0;
     in.chk_release = enc_us / tile_us;
@@ -388,7 +410,7 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     const bool reuse = o.reuse_b_checksums && h->chk_for_b == dB && h->chk_n == N && h->chk_k == K && h->chk_bn == BN;
     need_encode = !reuse;
     chk_ld_v = chk_ld;
-    enc_mode_v = encode_mode(N);
+    enc_mode_v = encode_mode(N, p.tiles_n, static_cast<int>(dbg("grid", 0) > 0 ? dbg("grid", 0) : h->num_sms / CG));
     if (need_encode && enc_mode_v == 1) {
       // stand-alone pre-pass in the caller's stream
       const int rounding = static_cast<int>(dbg("enc_rounding", 0));
@@ -419,10 +441,11 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     if (rc) return rc;
   }
   // ---- work plan (plan.h), cached per shape on the handle
-  const bool encode_items = ft && need_encode && enc_mode_v == 2;
-  const PlanInput pin = make_plan_input(h->num_sms, CG, BN, K, p, encode_items);
+  const int enc_plan = (ft && need_encode && enc_mode_v >= 2) ? enc_mode_v : 0;
+  const bool encode_items = enc_plan != 0;
+  const PlanInput pin = make_plan_input(h->num_sms, CG, BN, K, p, enc_plan);
   const std::array<long long, 6> key = {v.info.id, M, N, K, pin.units,
-                                        pin.force_slices * 16 + pin.max_slices + (encode_items ? 1024 : 0) + pin.lockstep * 2048};
+                                        pin.force_slices * 16 + pin.max_slices + enc_plan * 1024 + pin.lockstep * 8192};
   ftsgemm_handle_s::CachedPlan &cp = h->plans[key];
   if (!cp.uploaded) {
     if (h->plans.size() > 64) {  // bound the cache: drop everything but this entry
@@ -473,8 +496,9 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     else if (BN == 64) workers = TileCfg<64, true, 1>::kEncWorkers;
     else if (BN == 128) workers = CG == 1 ? TileCfg<128, true, 1>::kEncWorkers : TileCfg<128, true, 2>::kEncWorkers;
     else workers = CG == 1 ? TileCfg<256, true, 1>::kEncWorkers : TileCfg<256, true, 2>::kEncWorkers;
-    const int inc = workers * CG * p.tiles_n;  // every ENCODE worker warp reports every k-chunk once
-    const std::array<long long, 4> shape = {N, K, BN, CG};
+    // every ENCODE worker warp of every CTA of the group reports every k-chunk once
+    const int inc = workers * CG * p.tiles_n;
+    const std::array<long long, 4> shape = {N, K, BN, CG * 8 + enc_plan};
     if (h->d_enc_prog == nullptr || h->enc_prog_cap < n_chunks) {
       if (h->d_enc_prog) FT_CUDA(h, cudaFree(h->d_enc_prog));
       h->d_enc_prog = nullptr;
@@ -640,8 +664,10 @@ int ftsgemm_debug_schedule(int kernel_id, int M, int N, int K, int num_sms, int 
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
   plan_tiles(M, N, v->bn, v->cg, v->info.fault_tolerant != 0, &p);
-  const bool encode_items = v->info.fault_tolerant != 0 && encode_mode(N) == 2 && p.tiles_c > 0;
-  const PlanInput pin = make_plan_input(num_sms, v->cg, v->bn, K, p, encode_items);
+  const long long gunits = dbg("grid", 0);
+  const int em = encode_mode(N, p.tiles_n, static_cast<int>(gunits > 0 ? gunits : num_sms / v->cg));
+  const int enc_plan = (v->info.fault_tolerant != 0 && em >= 2 && p.tiles_c > 0) ? em : 0;
+  const PlanInput pin = make_plan_input(num_sms, v->cg, v->bn, K, p, enc_plan);
   const Plan plan = build_plan(pin);
   if (hdr) {
     hdr[0] = plan.units; hdr[1] = pin.n_chk_tiles + pin.n_data_tiles; hdr[2] = pin.n_chk_tiles; hdr[3] = plan.sk_tiles;

@@ -84,7 +84,8 @@ struct KernelParams {
   // Work plan (built on the host, plan.h): unit u executes items plan[plan_off[u] .. plan_off[u+1]) in order.
   //   item.x = tile (decode order: checksum tiles first), item.y = kb_begin | kb_end << 16,
   //   item.z = kind (0 whole tile, 1 first piece, 3 middle piece, 2 last piece of a cut tile, 4 encoder item:
-  //            tile = tile-column of B, no accumulator) | piece << 8,
+  //            tile = tile-column of B, no accumulator, 5 encoder tile: a whole data tile whose B stages are also
+  //            reduced to the checksum vectors of its tile-column) | piece << 8,
   //   item.w = index among the cut tiles
   // The last sk_tiles data tiles are cut along K into up to sk_slices pieces so that the list scheduler can level the
   // units' finishing times.  Piece p parks its raw accumulator; piece p+1 loads it into tensor memory BEFORE its first
@@ -222,7 +223,7 @@ __host__ __device__ __forceinline__ int chk_tile_width(const KernelParams &p, in
 // ------------------------------------------------------------------------------------------------------------
 struct Segment {
   int tile, kb_begin, kb_end;
-  int kind;   // 0 whole tile, 1 first piece, 3 middle piece, 2 last piece, 4 encoder item
+  int kind;   // 0 whole tile, 1 first piece, 3 middle piece, 2 last piece, 4 encoder item, 5 encoder tile
   int slice;
   int split_idx;
 };
@@ -534,24 +535,24 @@ __device__ __forceinline__ void split2_tf32(double x, float &h, float &l) {
 }
 
 // v[0..CNT) per lane -> after all steps v[0] of lane L is the 32-lane total of value idx(L)
-template <int CNT, int O>
+template <typename T, int CNT, int O>
 struct TransposeReduce {
-  static __device__ __forceinline__ void run(double *v, int lane, int &idx) {
+  static __device__ __forceinline__ void run(T *v, int lane, int &idx) {
     if constexpr (O > 0) {
       if constexpr (CNT > 1) {
         constexpr int H = CNT / 2;
         const bool up = (lane & O) != 0;
 #pragma unroll
         for (int i = 0; i < H; ++i) {
-          const double send = up ? v[i] : v[i + H];
-          const double keep = up ? v[i + H] : v[i];
+          const T send = up ? v[i] : v[i + H];
+          const T keep = up ? v[i + H] : v[i];
           v[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
         }
         if (up) idx += H;
-        TransposeReduce<H, O / 2>::run(v, lane, idx);
+        TransposeReduce<T, H, O / 2>::run(v, lane, idx);
       } else {
         v[0] += __shfl_xor_sync(0xffffffffu, v[0], O);
-        TransposeReduce<1, O / 2>::run(v, lane, idx);
+        TransposeReduce<T, 1, O / 2>::run(v, lane, idx);
       }
     }
   }
@@ -612,7 +613,7 @@ __device__ __forceinline__ void encode_b_warp(const float *__restrict__ B, int N
       }
     }
     int idx = 0;
-    TransposeReduce<NV, 16>::run(v, lane, idx);
+    TransposeReduce<double, NV, 16>::run(v, lane, idx);
     const int k = k0 + (idx >> 1);
     if ((lane & (32 / NV - 1)) == 0 && k < K) {
       float h, l;
@@ -628,22 +629,37 @@ __device__ __forceinline__ void encode_b_warp(const float *__restrict__ B, int N
 // a row, the 32-lane totals are formed by the transposing butterfly, and lane 2i writes the (hi, lo) TF32 pair of value
 // i (e and w of 8 rows) to the checksum operand.  A helper warp owns whole stages (every 4th slot of the ring), so the
 // four warps work on four stages at once and nothing but the stage's own barriers synchronises them.
-template <int BN>
-__device__ __forceinline__ void encode_stage_rows(uint32_t stage_base, int g, int lane, int kb, int K, int t,
-                                                  float *__restrict__ chk, int chk_ld) {
-  // Instruction budget matters: one warp has ~2.5k cycles per 32 KiB stage.  Per float4: 4 mask operations (the
-  // truncation the tensor core applies), s = sum of the four, t = b1 + 2 b2 + 3 b3, e += s, w += w0 * s + t.
-  double v[16];
+// LOCAL_ATOMS = atoms of the row held by this CTA starting at local_base (all BN/32 for an encoder item; BN/32/CG for
+// an encoder tile of a CTA pair, whose other half sits in the peer CTA's stage and is read through distributed shared
+// memory at peer_base).  One call reduces k-rows 16h .. 16h+15 of the stage.
+//
+// Instruction budget: an ENCODE worker has to finish a 32 KiB stage in ~2.3 us (7 workers, one k-block per 0.33 us of
+// main loop); the first version (8 rows per call, FP64 butterfly) needed 2.7 us from local and 5.5 us with the
+// distributed-shared-memory half (device timeline, worker 0: 104 us of work for 19 k-blocks) and tripled the main loop
+// of its tile.  Per float4: 4 mask operations (the truncation the tensor core applies), s = sum of the four,
+// t = b1 + 2 b2 + 3 b3, e += s, w += w0 * s + t; the lane partials (8 TF32 values, exact in FP32) of 16 rows x (e, w)
+// are reduced over the 32 lanes by one FP32 transposing butterfly (31 exchange steps, <= 5 roundings of 2^-24 per total:
+// far below the 2^-22 the (hi, lo) TF32 pair keeps) and every lane writes one pair.
+template <int BN, int LOCAL_ATOMS>
+__device__ __forceinline__ void encode_stage_rows(uint32_t local_base, uint32_t peer_base, int first_atom, int h, int lane,
+                                                  int kb, int K, int t, float *__restrict__ chk, int chk_ld) {
+  // atoms [first_atom, first_atom + LOCAL_ATOMS) of the row are at local_base, the others at peer_base (the other CTA)
+  const int peer_first = first_atom == 0 ? LOCAL_ATOMS : 0;
+  float v[32];
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const int kr = g * 8 + u;
+  for (int u = 0; u < 16; ++u) {
+    const int kr = h * 16 + u;
     float e = 0.0f, w = 0.0f;
 #pragma unroll
     for (int idx0 = 0; idx0 < BN / 4; idx0 += 32) {
       const int idx = idx0 + lane;  // float4 index within the k-row (over all atoms)
       if (BN / 4 >= 32 || idx < BN / 4) {
         const int atom = idx >> 3, c4 = idx & 7;
-        const float4 x = ptx::ld_shared_f4(stage_base + atom * (kBK * 128) + kr * 128 + c4 * 16);
+        float4 x;
+        if (LOCAL_ATOMS >= BN / 32 || (atom >= first_atom && atom < first_atom + LOCAL_ATOMS))
+          x = ptx::ld_shared_f4(local_base + (atom - first_atom) * (kBK * 128) + kr * 128 + c4 * 16);
+        else
+          x = ptx::ld_dsmem_f4(peer_base + (atom - peer_first) * (kBK * 128) + kr * 128 + c4 * 16);
         const int granule = (c4 >> 1) ^ (kr & 3);
         const float w0 = static_cast<float>(atom * 32 + granule * 8 + (c4 & 1) * 4 + 1);
         const float b0 = u2f(f2u(x.x) & 0xFFFFE000u), b1 = u2f(f2u(x.y) & 0xFFFFE000u),
@@ -654,16 +670,16 @@ __device__ __forceinline__ void encode_stage_rows(uint32_t stage_base, int g, in
         w += fmaf(w0, s4, t4);
       }
     }
-    v[2 * u] = static_cast<double>(e);
-    v[2 * u + 1] = static_cast<double>(w);
+    v[2 * u] = e;
+    v[2 * u + 1] = w;
   }
   int idx = 0;
-  TransposeReduce<16, 16>::run(v, lane, idx);
-  const int k = kb * kBK + g * 8 + (idx >> 1);
-  if ((lane & 1) == 0 && k < K) {
-    float h, l;
-    split2_tf32(v[0], h, l);
-    *reinterpret_cast<float2 *>(chk + static_cast<size_t>(k) * chk_ld + t * kChkPerTile + (idx & 1) * 2) = make_float2(h, l);
+  TransposeReduce<float, 32, 16>::run(v, lane, idx);
+  const int k = kb * kBK + h * 16 + (idx >> 1);
+  if (k < K) {
+    const float hi = u2f(f2u(v[0]) & 0xFFFFE000u);
+    const float lo = u2f(f2u(v[0] - hi) & 0xFFFFE000u);  // v - hi is exact
+    *reinterpret_cast<float2 *>(chk + static_cast<size_t>(k) * chk_ld + t * kChkPerTile + (idx & 1) * 2) = make_float2(hi, lo);
   }
 }
 
@@ -694,6 +710,8 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // number of (epilogue warp, item) pairs this CTA has finished: the helper warps' view of which accumulator stages
   // are drained (a counter, not an mbarrier: the helpers may be many items behind while they encode B)
   const uint32_t epi_count = tmem_slot + 8u;
+  // peer CTA: worker w's "the leader saw k-block j complete" hand-off (the pair's TMA bytes are credited to the leader)
+  auto pfull_bar = [&](int w) { return epi_count + 8u + 8u * w; };
   volatile uint32_t *tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
@@ -711,7 +729,10 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(full_bar(s), CG);   // leader's own arrive.expect_tx (+ the peer's remote arrive)
-      ptx::mbar_init(empty_bar(s), 1);   // one tcgen05.commit (multicast to both CTAs when CG = 2)
+      // one tcgen05.commit (multicast to both CTAs when CG = 2); with ABFT two more arrivals say that nobody else still
+      // reads the stage: the two ENCODE workers of an encoder tile's k-block (one per CTA; a CTA pair's workers read both
+      // halves), or the producer itself right after filling it
+      ptx::mbar_init(empty_bar(s), FT ? 3 : 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
@@ -720,6 +741,8 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     ptx::st_shared_u32(epi_count, 0u);
     ptx::mbar_init(pair_bar, 1);
+    if (FT)
+      for (int w = 0; w < Cfg::kEncWorkers; ++w) ptx::mbar_init(pfull_bar(w), 1);
     ptx::fence_mbar_init();
   }
   if (CG == 2) ptx::cluster_sync_all();  // peer barriers must be initialised before any remote arrive / 2-CTA alloc
@@ -743,42 +766,89 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   constexpr int kEncWorkers = Cfg::kEncWorkers;
   auto encoder_prefix = [&](int w8) {
     if (w8 >= kEncWorkers) return;
-    int base = 0;   // ring slots consumed by earlier encoder items
-    int n_enc = 0;
+    int base = 0;   // ring slots consumed by earlier prefix items
+    int n_items = 0;  // encoder ITEMS (kind 4) seen: the UMMA warp has to be released after them
+    int tile_kblocks = 0;  // encoder-TILE k-blocks this worker has taken (phase of its pfull barrier in the peer CTA)
+    const bool tr_on = p.trace != nullptr && is_leader && w8 == 0;  // timeline: worker 0's wait / work split
+    unsigned long long tr_wait = 0, tr_comp = 0, tr_n = 0;
     SegIter it(p, unit);
     Segment sg;
     if (p.trace != nullptr && is_leader && w8 == 0 && lane == 0) trace_put(p, unit, p.trace_cap - 1, 1, globaltimer_ns());
-    while (it.next(sg) && sg.kind == 4) {
-      ++n_enc;
-      const int slots = (sg.kb_end + CG - 1) / CG;
+    while (it.next(sg) && sg.kind >= 4) {
+      const bool is_tile = sg.kind == 5;
+      if (!is_tile) ++n_items;
+      // encoder item: every CTA of the group streams its own k-blocks (j*CG + rank) of the whole tile-column;
+      // encoder tile: an ordinary main loop runs; the LEADER's workers reduce both halves of every B stage
+      const int slots = is_tile ? sg.kb_end : (sg.kb_end + CG - 1) / CG;
       const int n_chunks = (sg.kb_end + 31) >> 5;
+      const int col = is_tile ? decode_tile(p, sg.tile).n_blk : sg.tile;
       int signalled = 0;  // chunks this warp has reported
-      for (int j = w8; j < slots; j += kEncWorkers) {
-        const int abs_slot = base + j;
-        const int stage = abs_slot % kStages;
-        ptx::mbar_wait(full_bar(stage), static_cast<uint32_t>(abs_slot / kStages) & 1u);
-        const int kb = j * CG + static_cast<int>(cta_rank);
+      {
+        for (int j = w8; j < slots; j += kEncWorkers) {
+          const int abs_slot = base + j;
+          const int stage = abs_slot % kStages;
+          const unsigned long long tw0 = tr_on ? globaltimer_ns() : 0ull;
+          if (!is_tile || is_leader) {
+            ptx::mbar_wait(full_bar(stage), static_cast<uint32_t>(abs_slot / kStages) & 1u);
+            // encoder tile of a CTA pair: both CTAs' bytes are credited to the leader's barrier, so the leader's worker
+            // tells its partner in the peer CTA (cluster-scope release: the partner reads data, not just a flag)
+            if (is_tile && CG == 2 && lane == 0) ptx::mbar_arrive_release_cluster(ptx::mapa(pfull_bar(w8), 1));
+          } else {
+            ptx::mbar_wait_acquire_cluster(pfull_bar(w8), static_cast<uint32_t>(tile_kblocks) & 1u);
+          }
+          ++tile_kblocks;
+          const unsigned long long tw1 = tr_on ? globaltimer_ns() : 0ull;
+          const uint32_t st = smem_base + stage * Cfg::kStageBytes;
+          const int kb = is_tile ? j : j * CG + static_cast<int>(cta_rank);
+          if (is_tile) {
+            // the pair's two workers of this k-block take 16 k-rows each, over BOTH halves of the tile-column
+            const uint32_t other = (CG == 2) ? ptx::mapa(st + Cfg::kABytes, cta_rank ^ 1u) : 0u;
+            const int first_atom = static_cast<int>(cta_rank) * (Cfg::kBNLocal / kAtomMN);
 #pragma unroll 1
-        for (int g = 0; g < kBK / 8; ++g)
-          encode_stage_rows<BN>(smem_base + stage * Cfg::kStageBytes, g, lane, kb, p.K, sg.tile, p.enc_out, p.enc_ld);
-        __syncwarp();  // every lane has read the stage
-        if (lane == 0) ptx::mbar_arrive(empty_bar(stage));
-        // report k-chunk c (32 k-blocks) once this warp's last slot of it is written
-        const int c = (j * CG) >> 5;
-        if (j + kEncWorkers >= slots || (((j + kEncWorkers) * CG) >> 5) != c) {
-          __threadfence();
-          __syncwarp();
-          if (lane == 0)
-            for (int cc = signalled; cc <= c; ++cc) atomicAdd(p.enc_prog + cc, 1);  // (chunks without a slot of this warp too)
-          signalled = c + 1;
+            for (int g = (CG == 2 ? static_cast<int>(cta_rank) : 0); g < (CG == 2 ? static_cast<int>(cta_rank) + 1 : kBK / 16); ++g)
+              encode_stage_rows<BN, Cfg::kBNLocal / kAtomMN>(st + Cfg::kABytes, other, first_atom, g, lane, kb, p.K, col,
+                                                            p.enc_out, p.enc_ld);
+          } else {
+#pragma unroll 1
+            for (int g = 0; g < kBK / 16; ++g)
+              encode_stage_rows<BN, BN / kAtomMN>(st, 0u, 0, g, lane, kb, p.K, col, p.enc_out, p.enc_ld);
+          }
+          __syncwarp();  // every lane has read the stage
+          if (lane == 0) {
+            ptx::mbar_arrive(empty_bar(stage));
+            if (is_tile) {
+              if (CG == 2) ptx::mbar_arrive_cluster(ptx::mapa(empty_bar(stage), cta_rank ^ 1u));  // the other half too
+              else ptx::mbar_arrive(empty_bar(stage));  // (a single CTA: this worker was both readers)
+            }
+          }
+          if (tr_on) {
+            tr_wait += tw1 - tw0;
+            tr_comp += globaltimer_ns() - tw1;
+            ++tr_n;
+          }
+          // report k-chunk c (32 k-blocks) once this warp's last slot of it is written
+          const int c = is_tile ? (j >> 5) : ((j * CG) >> 5);
+          const int jn = j + kEncWorkers;
+          if (jn >= slots || (is_tile ? (jn >> 5) : ((jn * CG) >> 5)) != c) {
+            __threadfence();
+            __syncwarp();
+            if (lane == 0)
+              for (int cc = signalled; cc <= c; ++cc) atomicAdd(p.enc_prog + cc, 1);  // (chunks without a slot of this warp too)
+            signalled = c + 1;
+          }
         }
+        if (lane == 0)
+          for (int c = signalled; c < n_chunks; ++c) atomicAdd(p.enc_prog + c, 1);  // short tail: chunks without a slot
       }
-      if (lane == 0)
-        for (int c = signalled; c < n_chunks; ++c) atomicAdd(p.enc_prog + c, 1);  // short tail: chunks without a slot
       base += slots;
-      if (p.trace != nullptr && is_leader && w8 == 0 && lane == 0) trace_put(p, unit, p.trace_cap - 1, 0, globaltimer_ns());
+      if (p.trace != nullptr && is_leader && w8 == 0 && lane == 0) {
+        trace_put(p, unit, p.trace_cap - 1, 0, globaltimer_ns());
+        trace_put(p, unit, p.trace_cap - 1, 2, tr_wait);
+        trace_put(p, unit, p.trace_cap - 1, 3, tr_comp);
+        trace_put(p, unit, p.trace_cap - 1, 4 + 1, tr_n);
+      }
     }
-    if (n_enc > 0 && is_leader) {
+    if (n_items > 0 && is_leader) {
       ptx::named_bar_sync(2, 32 * (kEncWorkers + 1));  // workers + the UMMA warp: releases the UMMA warp (see there) ...
       if (CG == 2 && w8 == 0 && lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(pair_bar, 1));  // ... and the peer's producer
     }
@@ -822,6 +892,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int i = 0; i < CG; ++i)
               ptx::tma_load_3d(sA + i * Cfg::kBBytes, &tmB, full_bar(stage), 0, k0, b_atom0 + i * (Cfg::kBNLocal / kAtomMN));
+            ptx::mbar_arrive_cnt(empty_bar(stage), 2);  // (the worker's arrival stands in for the tcgen05.commit)
           }
           __syncwarp();
           if (++stage == kStages) {
@@ -843,6 +914,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const TileCoord tc = decode_tile(p, sg.tile);
       const int m0 = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;        // this CTA's 128 rows of A
       const bool b_is_chk = FT && tc.is_chk;
+      const bool readers = FT && sg.kind == 5;  // encoder tile: the ENCODE workers release the stages
       const int n_eff = b_is_chk ? chk_tile_width<BN, CG>(p, tc.n_blk) : BN;
       const int nb0 = (b_is_chk ? tc.n_blk * chk_cols_per_tile(BN) : tc.n_blk * BN) +
                       static_cast<int>(cta_rank) * (n_eff / CG);  // this CTA's share of B rows
@@ -898,6 +970,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               ptx::tma_load_3d(sA, &tmA, full_bar(stage), 0, k0, a_atom);
               ptx::tma_load_3d(sB, tmb_const, full_bar(stage), 0, k0, b_atom);
             }
+            if (FT && !readers) ptx::mbar_arrive_cnt(empty_bar(stage), 2);  // nobody but the UMMA reads this stage
           }
           __syncwarp();
           if (++stage == kStages) {
@@ -956,6 +1029,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               else ptx::tma_load_2d(sB + i * (kBK * 128), tmb, bar, nb0 + i * kAtomMN, k0);
             }
           }
+          if (FT && !readers) ptx::mbar_arrive_cnt(empty_bar(stage), 2);
           }
           __syncwarp();
           if (++stage == kStages) {
@@ -1011,7 +1085,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // (one k-block) take only ~512 cycles, so the 64-bit descriptors are NOT rebuilt per UMMA: the high word
       // (SBO, version, layout) and LBO are constant, only the 14-bit start-address field advances (+64 = 1024 B).
       uint32_t first = 1u;  // the first UMMA of a tile overwrites the accumulator ...
-      if (sg.kind >= 2) {   // ... unless the helper warps seeded it with the previous piece's parked sums
+      if (sg.kind == 2 || sg.kind == 3) {   // ... unless the helper warps seeded it with the previous piece's parked sums
         ptx::mbar_wait(seeded_bar(acc), (seed_phase >> acc) & 1u);
         seed_phase ^= 1u << acc;
         ptx::tc_fence_after();
@@ -1084,7 +1158,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         trace_put(p, unit, item_idx, 7, static_cast<unsigned long long>(sg.tile) | (static_cast<unsigned long long>(sg.kind) << 24));
       }
 
-      const bool parks = (sg.kind & 1) != 0;  // first / middle piece of a cut tile
+      const bool parks = sg.kind == 1 || sg.kind == 3;  // first / middle piece of a cut tile
       if (parks) {
         // park the raw sums of this piece for the unit that owns the next one
         const int slot = (sg.slice * p.sk_tiles + sg.split_idx) * CG + static_cast<int>(cta_rank);
@@ -1164,7 +1238,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       while (it.next(sg)) {
         if (FT && sg.kind == 4) continue;  // no accumulator
         ++item_idx;
-        if (sg.kind >= 2) {
+        if (sg.kind == 2 || sg.kind == 3) {
           // the accumulator stage must have been drained by this CTA's four epilogue warps (item_idx - 2 and before)
           if (item_idx >= 2) {
             const uint32_t need = 4u * static_cast<uint32_t>(item_idx - 1);

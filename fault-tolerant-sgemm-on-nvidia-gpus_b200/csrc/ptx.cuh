@@ -38,8 +38,23 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// FTSGEMM_TRYWAIT_HINT_NS > 0 passes a suspend-time hint: the waiting warp is parked by the hardware (and woken by the
+// phase completion) instead of re-issuing try_wait, which leaves the issue slots of its SM sub-partition to the warps
+// that have work (the ENCODE workers / epilogue warps share sub-partitions with the spinning producer and UMMA warps).
+#ifndef FTSGEMM_TRYWAIT_HINT_NS
+#define FTSGEMM_TRYWAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#if FTSGEMM_TRYWAIT_HINT_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(static_cast<uint32_t>(FTSGEMM_TRYWAIT_HINT_NS))
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -47,6 +62,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 // Spin on try_wait.  FTSGEMM_WATCHDOG (default on) turns a protocol bug into a trap instead of a hung GPU: any wait
@@ -119,6 +135,14 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
 __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// distributed shared memory: 16-byte load through the cluster window (address from mapa)
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t cluster_addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(cluster_addr));
   return v;
 }
 __device__ __forceinline__ float ld_shared_f1(uint32_t addr) {
@@ -221,6 +245,28 @@ __device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   // default semantics (.release.cta): a cluster-scope release here costs a full fence per call
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// cluster-scope release / acquire pair for the rare hand-offs that publish DATA across the two CTAs of a pair
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar, uint32_t parity) {
+  Watchdog wd;
+  uint32_t ok = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    wd.tick();
+  }
+}
+__device__ __forceinline__ void mbar_arrive_cnt(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 // TMA load whose completion bytes are credited to an mbarrier of the pair's leader CTA (cluster address).
 __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap *tm, uint32_t cluster_bar, int c0, int c1) {

@@ -56,18 +56,18 @@ def trace_case(pkg, kid, n, dbg=None, tag="", reuse=False, m=None, k=None):
     n_chk = hdr["n_chk_tiles"]
     t0 = min(it["prod_start"] for u in tr for it in u if it["prod_start"])
     t_end = max(it["epi_end"] for u in tr for it in u)
-    main = {"chk": [], "whole": [], "contrib": [], "finish": []}
-    epi = {"chk": [], "whole": [], "contrib": [], "finish": []}
+    main = {"chk": [], "whole": [], "contrib": [], "finish": [], "enc_tile": []}
+    epi = {"chk": [], "whole": [], "contrib": [], "finish": [], "enc_tile": []}
     chk_wait = []
     mma_gap, acc_lag = [], []
     unit_end = []
     for u in tr:
         prev_end = None
         for it in u:
-            cls = "chk" if it["tile"] < n_chk else ("whole", "contrib", "finish")[it["kind"]]
+            cls = "chk" if it["tile"] < n_chk else {0: "whole", 1: "contrib", 2: "finish", 3: "contrib", 5: "enc_tile"}[it["kind"]]
             main[cls].append(it["mma_end"] - it["mma_start"])
             epi[cls].append(it["epi_end"] - it["acc_done"])
-            if cls in ("whole", "finish") and it["check_done"]:
+            if cls in ("whole", "finish", "enc_tile") and it["check_done"]:
                 chk_wait.append(it["check_done"] - it["acc_done"])
             acc_lag.append(it["acc_done"] - it["mma_end"])
             if prev_end is not None:
@@ -88,8 +88,10 @@ def trace_case(pkg, kid, n, dbg=None, tag="", reuse=False, m=None, k=None):
                [u[0]["enc_end"] - u[0]["enc_start"] for u in tr if u and u[0].get("enc_end")]),
            "encode_all_done_after_first_start_us": (lambda a, b: None if not a else round((max(a) - min(b)) / 1e3, 2))(
                [u[0]["enc_end"] for u in tr if u and u[0].get("enc_end")], [u[0]["enc_start"] for u in tr if u and u[0].get("enc_start")]),
+           "enc_worker0_wait_work_us_slots": [(round(u[0]["enc_worker0"][0] / 1e3, 1), round(u[0]["enc_worker0"][1] / 1e3, 1), u[0]["enc_worker0"][2])
+                                              for u in tr if u and u[0].get("enc_worker0") and u[0]["enc_worker0"][2]][:6],
            "chk_items_end_us": [round((it["epi_end"] - t0) / 1e3, 1) for u in tr for it in u if it["tile"] < n_chk][:40]}
-    raw = [[{kk: (vv - t0 if kk not in ("tile", "kind") and vv else vv) for kk, vv in it.items()} for it in u] for u in tr]
+    raw = [[{kk: (vv - t0 if kk not in ("tile", "kind", "enc_worker0") and vv else vv) for kk, vv in it.items()} for it in u] for u in tr]
     name = f"trace_{kid}_{n}{('_' + tag) if tag else ''}.json"
     (OUT / name).write_text(json.dumps({"summary": res, "timeline_ns": raw}))
     print(json.dumps(res))
