@@ -118,6 +118,8 @@ struct KernelParams {
   // k-block 32c
   int *enc_prog;
   int enc_prog_target;
+  int pdl_wait;         // 1: launched as a programmatic dependent of the encode pre-pass -- checksum items (the only
+                        //    consumers of its output) execute griddepcontrol.wait before their first load
   float tau_abs, tau_rel;
   int detect_only;
   int inject_mode;
@@ -863,6 +865,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     Segment sg;
     int item_idx = -1;
     bool enc_prefix = false;
+    bool pdl_done = false;
     if (FT && (p.dbg_flags & 4) && p.enc_count != nullptr) {
       // experiment: "foreground" encode -- no main loop starts before the whole encode is done
       if (lane == 0) {
@@ -919,6 +922,10 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int nb0 = (b_is_chk ? tc.n_blk * chk_cols_per_tile(BN) : tc.n_blk * BN) +
                       static_cast<int>(cta_rank) * (n_eff / CG);  // this CTA's share of B rows
       const CUtensorMap *tmb = b_is_chk ? &tmChk : &tmB;
+      if (FT && b_is_chk && p.pdl_wait && !pdl_done) {
+        ptx::pdl_wait();  // the pre-pass kernel has completed and its writes are visible
+        pdl_done = true;
+      }
       if (FT && b_is_chk && p.enc_count != nullptr) {
         // the checksum vectors are being written by the helper warps of all CTAs: checksum items (and only they) wait
         if (lane == 0) {
@@ -1285,6 +1292,7 @@ template <int BN>
 __global__ void __launch_bounds__(kEncWarps * 32, 2)
 encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, float *__restrict__ chk, int chk_ld, int rounding,
                 int tiles_n) {
+  ptx::pdl_launch_dependents();  // the GEMM kernel may start on SMs as they drain (its checksum items wait for this grid)
   encode_b_warp<BN>(B, N, K, ldb, chk, chk_ld, rounding, tiles_n, blockIdx.x * kEncWarps + (threadIdx.x >> 5),
                     gridDim.x * kEncWarps, threadIdx.x & 31);
 }
