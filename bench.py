@@ -57,7 +57,22 @@ class ClockSampler:
             import pynvml
             pynvml.nvmlInit()
             self.nvml = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.h = None
+            try:  # NVML enumerates all GPUs of the box, CUDA only the visible ones: match by UUID
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+                try:
+                    self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+                except TypeError:
+                    self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+                self.how = "matched by UUID"
+            except Exception:
+                self.h = None
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+                self.how = "NVML index = CUDA index (UUID lookup unavailable)"
+
             self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception:
             self.nvml = None
@@ -93,7 +108,7 @@ class ClockSampler:
         sm = [x[1] for x in inside]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_sm,
                 "power_w_max": max((x[2] for x in inside), default=None), "samples": len(inside),
-                "reasons": sorted(reasons), "how": "pynvml polled from a thread during the timed region"}
+                "reasons": sorted(reasons), "how": "pynvml polled from a thread during the timed region; device " + getattr(self, "how", "?")}
 
 
 def _cpu_port_baseline(n, seconds_target=12.0):
@@ -189,7 +204,7 @@ def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--size", type=int, default=4096)
@@ -342,6 +357,7 @@ def main():
                  "cublas_tf32_gflops": round(comp["cublas_tf32"], 1), "cublas_fp32_gflops": round(comp["cublas_fp32"], 1),
                  "plain_kernel_gflops": round(comp["plain"], 1), "abft_baseline_gflops": round(comp["abft_baseline"], 1),
                  "abft_baseline_tf32_gflops": round(comp["abft_baseline_tf32"], 1),
+                 "encode_prepass_us_per_step": round((ms_step - k_ms) * 1e3, 2),
                  "tiles_checked": st["tiles"], "rows_checked": st["rows_checked"], "detected": st["detected"],
                  "max_abs_residual": st["max_abs_residual"], "max_rel_residual": st["max_rel_residual"]},
         "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
