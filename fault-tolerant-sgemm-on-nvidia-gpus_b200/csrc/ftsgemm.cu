@@ -67,6 +67,10 @@ const Variant *find_variant(int id) {
   return nullptr;
 }
 
+// slab flags of the checksum tile-columns live in front of the expected-checksum matrix (one int per 32-row slab and
+// checksum tile-column: 128 KiB for the 128 x 32 tile at 16384^2)
+constexpr size_t kChkFlagBytes = 1u << 20;
+
 // ------------------------------------------------------------------------------------------- debug knobs
 std::mutex g_dbg_mu;
 std::map<std::string, long long> g_dbg;
@@ -406,13 +410,13 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     const size_t out_floats = static_cast<size_t>(M) * p.n_chk_cols;
     const size_t n_flags = static_cast<size_t>(n_slabs) * p.tiles_c;
     const float *out_before = h->d_chk_out;
-    rc = ensure_buf(h, &h->d_chk_out, &h->chk_out_bytes, 65536 + out_floats * sizeof(float));
+    rc = ensure_buf(h, &h->d_chk_out, &h->chk_out_bytes, kChkFlagBytes + out_floats * sizeof(float));
     if (rc) return rc;
-    if (n_flags * sizeof(int) > 65536) return FTSGEMM_ERR_UNSUPPORTED;
+    if (n_flags * sizeof(int) > kChkFlagBytes) return FTSGEMM_ERR_UNSUPPORTED;
     p.chk_flags = reinterpret_cast<int *>(h->d_chk_out);  // fixed location: stale flags never equal a new epoch
-    p.chk_out = h->d_chk_out + 65536 / sizeof(float);
+    p.chk_out = h->d_chk_out + kChkFlagBytes / sizeof(float);
     if (h->d_chk_out != out_before || h->chk_epoch > (1 << 30)) {
-      FT_CUDA(h, cudaMemsetAsync(p.chk_flags, 0, 65536, stream));
+      FT_CUDA(h, cudaMemsetAsync(p.chk_flags, 0, kChkFlagBytes, stream));
       h->chk_epoch = 0;
     }
     p.chk_epoch = ++h->chk_epoch;

@@ -101,7 +101,7 @@ def case_main(spec):
                     for _ in range(reps):
                         ft.run(kid, M, N, K, dA, dB, dC, alpha, beta, opts)
                     ms = tm.stop() / reps
-                    best = min(best, ms)
+                    best = ms if spec.get("sustain") else min(best, ms)  # sustain: the LAST (power-limited) batch
                 res["gflops"][str(kid)] = round(2.0 * M * N * K / best / 1e6, 1)
             except Exception as e:  # noqa
                 res["gflops"][str(kid)] = "ERR " + str(e)[:80]
