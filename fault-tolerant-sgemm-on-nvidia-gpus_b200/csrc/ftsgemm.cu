@@ -102,6 +102,8 @@ struct ftsgemm_handle_s {
   float *d_aux = nullptr;       // baseline vectors
   size_t aux_floats = 0;
   struct CachedPlan {
+    std::vector<int> wave_target;   // per whole-tile ordinal: units that own more whole tiles than that
+    int *d_wave_target = nullptr;
     ftsgemm::Plan plan;
     std::vector<int4> packed;   // host copy (kept alive for the async upload)
     int4 *d_items = nullptr;
@@ -111,6 +113,8 @@ struct ftsgemm_handle_s {
   std::map<std::array<long long, 6>, CachedPlan> plans;  // key: kernel id, M, N, K, units, forced slices
   int *d_enc_count = nullptr;   // helper warps that have finished their share of the in-kernel encode (monotonic)
   int enc_total = 0;            // host mirror of the value the counter reaches after the last launch
+  int *d_wave_cnt = nullptr;    // wave re-synchronisation counters (cleared per launch)
+  size_t wave_cnt_cap = 0;
   int *d_enc_prog = nullptr;    // encoder items: per k-chunk progress counters (monotonic per shape)
   int enc_prog_cap = 0, enc_prog_value = 0;
   std::array<long long, 4> enc_prog_shape = {0, 0, 0, 0};
@@ -399,7 +403,7 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
   tmC = tmB;
   if (ft) {
     // checksum vectors of B: 8 columns per N-tile, appended to B as extra tile-columns of the same GEMM
-    p.dbg_flags = static_cast<int>(dbg("ft_dbg", 0)) & 5;
+    p.dbg_flags = static_cast<int>(dbg("ft_dbg", 0)) & 1;
     const int chk_ld = (p.n_chk_cols + kAtomMN - 1) / kAtomMN * kAtomMN;  // padded so the 3-D TMA view is exact; pad
                                                                           // columns are never stored (n_chk_cols mask)
     const int n_slabs = p.tiles_m * CG * (kBM / 32);
@@ -420,7 +424,7 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
       h->chk_epoch = 0;
     }
     p.chk_epoch = ++h->chk_epoch;
-    p.dbg_flags = static_cast<int>(dbg("ft_dbg", 0)) & 5;
+    p.dbg_flags = static_cast<int>(dbg("ft_dbg", 0)) & 1;
     const bool reuse = o.reuse_b_checksums && h->chk_for_b == dB && h->chk_n == N && h->chk_k == K && h->chk_bn == BN;
     need_encode = !reuse;
     chk_ld_v = chk_ld;
@@ -472,6 +476,7 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
         if (&it->second == &cp) { ++it; continue; }
         cudaFree(it->second.d_items);
         cudaFree(it->second.d_off);
+        cudaFree(it->second.d_wave_target);
         it = h->plans.erase(it);
       }
     }
@@ -485,6 +490,20 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     FT_CUDA(h, cudaMalloc(&cp.d_off, cp.plan.offsets.size() * sizeof(int)));
     FT_CUDA(h, cudaMemcpyAsync(cp.d_items, cp.packed.data(), cp.packed.size() * sizeof(int4), cudaMemcpyHostToDevice, stream));
     FT_CUDA(h, cudaMemcpyAsync(cp.d_off, cp.plan.offsets.data(), cp.plan.offsets.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    {  // wave targets (see KernelParams::wave_cnt)
+      std::vector<int> per_unit(static_cast<size_t>(cp.plan.units), 0);
+      int max_w = 0;
+      for (int u = 0; u < cp.plan.units; ++u) {
+        for (int i = cp.plan.offsets[u]; i < cp.plan.offsets[u + 1]; ++i)
+          if (cp.plan.items[i].kind == 0 && cp.plan.items[i].tile >= pin.n_chk_tiles) ++per_unit[u];
+        max_w = std::max(max_w, per_unit[u]);
+      }
+      cp.wave_target.assign(static_cast<size_t>(max_w) + 1, 0);
+      for (int u = 0; u < cp.plan.units; ++u)
+        for (int w = 0; w < per_unit[u]; ++w) ++cp.wave_target[w];
+      FT_CUDA(h, cudaMalloc(&cp.d_wave_target, cp.wave_target.size() * sizeof(int)));
+      FT_CUDA(h, cudaMemcpyAsync(cp.d_wave_target, cp.wave_target.data(), cp.wave_target.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    }
     cp.uploaded = true;
   }
   const int units = cp.plan.units;
@@ -555,6 +574,27 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
       h->enc_total += units * CG * 4;
     }
     p.enc_target = h->enc_total;
+  }
+  {
+    // Wave re-synchronisation for problems that run many waves over operands that do not fit L2.  Measured
+    // (profiles/r01_probe21_*, r01_trace_16384_per_wave.txt): without it the units' start times drift apart by ~2 us per
+    // wave and the tile time grows from 178 to 209 us over the 56 waves of 16384^3; with it the spread stays below 6 us:
+    // 16384^3 plain 750 -> 811 TFLOP/s (cuBLAS-TF32 831), ABFT 571-695 -> 721-821; 14336^3 +2-7 % / +3-12 %; neutral
+    // between 6144 and 12288, -2 % at 4096 (3 waves) -- hence the wave-count limit.
+    const long long ws = dbg("wave_sync", -2);
+    const bool on = ws >= 0 ? (ws != 0) : (pin.lockstep && static_cast<int>(cp.wave_target.size()) >= 24);
+    if (on && cp.wave_target.size() > 1) {
+      const size_t bytes = cp.wave_target.size() * sizeof(int);
+      if (h->d_wave_cnt == nullptr || h->wave_cnt_cap < cp.wave_target.size()) {
+        if (h->d_wave_cnt) FT_CUDA(h, cudaFree(h->d_wave_cnt));
+        h->d_wave_cnt = nullptr;
+        FT_CUDA(h, cudaMalloc(&h->d_wave_cnt, bytes));
+        h->wave_cnt_cap = cp.wave_target.size();
+      }
+      FT_CUDA(h, cudaMemsetAsync(h->d_wave_cnt, 0, bytes, stream));
+      p.wave_cnt = h->d_wave_cnt;
+      p.wave_target = cp.d_wave_target;
+    }
   }
   if (dbg("trace", 0) != 0) {
     const int cap = 64;
@@ -778,9 +818,11 @@ int ftsgemm_destroy(ftsgemm_handle_t h) {
   cudaFree(h->d_trace);
   cudaFree(h->d_enc_count);
   cudaFree(h->d_enc_prog);
+  cudaFree(h->d_wave_cnt);
   for (auto &kv : h->plans) {
     cudaFree(kv.second.d_items);
     cudaFree(kv.second.d_off);
+    cudaFree(kv.second.d_wave_target);
   }
   cudaFree(h->d_aux);
   cudaFree(h->d_verify);

@@ -80,7 +80,7 @@ struct KernelParams {
   // bit 0 / 1 / 2: the A / B / checksum tensor map is 3-D {32, K, rows/32} so that ONE TMA instruction fetches a whole
   // operand stage (rows % 32 == 0); otherwise the map is 2-D {rows, K} and a stage takes one instruction per 32-row atom
   int tma3d;
-  int dbg_flags;        // experiments only: bit 0 = skip the epilogue ABFT check of data tiles
+  int dbg_flags;        // experiments only: bit 0 = skip the epilogue ABFT check of data tiles (timing breakdowns)
   // Work plan (built on the host, plan.h): unit u executes items plan[plan_off[u] .. plan_off[u+1]) in order.
   //   item.x = tile (decode order: checksum tiles first), item.y = kb_begin | kb_end << 16,
   //   item.z = kind (0 whole tile, 1 first piece, 3 middle piece, 2 last piece of a cut tile, 4 encoder item:
@@ -118,6 +118,11 @@ struct KernelParams {
   // k-block 32c
   int *enc_prog;
   int enc_prog_target;
+  // wave re-synchronisation (large problems): the leader producers form a barrier at every whole-tile boundary, so that
+  // the units keep streaming the same k range of the A / B panels they share (without it the start times drift apart by
+  // ~2 us per wave and the tile time grows 17 % over the 56 waves of 16384^3, profiles/r01_trace_*_16384*)
+  int *wave_cnt;        // [w] = leader producers that have issued the last load of their w-th whole tile (cleared per launch)
+  const int *wave_target;  // [w] = number of units that own more than w whole tiles
   int pdl_wait;         // 1: launched as a programmatic dependent of the encode pre-pass -- checksum items (the only
                         //    consumers of its output) execute griddepcontrol.wait before their first load
   float tau_abs, tau_rel;
@@ -866,17 +871,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int item_idx = -1;
     bool enc_prefix = false;
     bool pdl_done = false;
-    if (FT && (p.dbg_flags & 4) && p.enc_count != nullptr) {
-      // experiment: "foreground" encode -- no main loop starts before the whole encode is done
-      if (lane == 0) {
-        ptx::Watchdog wd;
-        while (ld_acquire(p.enc_count) - p.enc_target < 0) {
-          __nanosleep(128);
-          wd.tick();
-        }
-      }
-      __syncwarp();
-    }
+    int whole_ord = 0;  // whole data tiles this unit has loaded (wave index)
     while (it.next(sg)) {
       ++item_idx;
       if (FT && sg.kind == 4) {
@@ -918,6 +913,19 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int m0 = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;        // this CTA's 128 rows of A
       const bool b_is_chk = FT && tc.is_chk;
       const bool readers = FT && sg.kind == 5;  // encoder tile: the ENCODE workers release the stages
+      const bool wave_item = p.wave_cnt != nullptr && sg.kind == 0 && !b_is_chk && is_leader;
+      if (wave_item && whole_ord > 0) {
+        // all units have finished loading their previous whole tile: start this one together
+        if (lane == 0) {
+          ptx::Watchdog wd;
+          const int need = __ldg(p.wave_target + whole_ord - 1);
+          while (ld_acquire(p.wave_cnt + whole_ord - 1) < need) {
+            __nanosleep(32);
+            wd.tick();
+          }
+        }
+        __syncwarp();
+      }
       const int n_eff = b_is_chk ? chk_tile_width<BN, CG>(p, tc.n_blk) : BN;
       const int nb0 = (b_is_chk ? tc.n_blk * chk_cols_per_tile(BN) : tc.n_blk * BN) +
                       static_cast<int>(cta_rank) * (n_eff / CG);  // this CTA's share of B rows
@@ -1044,6 +1052,10 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             phase ^= 1u;
           }
         }
+      }
+      if (wave_item) {
+        if (lane == 0) atomicAdd(p.wave_cnt + whole_ord, 1);
+        ++whole_ord;
       }
       if (p.trace != nullptr && is_leader && lane == 0) trace_put(p, unit, item_idx, 1, globaltimer_ns());
     }

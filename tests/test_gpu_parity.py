@@ -150,6 +150,28 @@ def test_encode_in_kernel_and_prepass_agree(cuda, ft, dev):
           assert np.allclose(res[0], res[2], rtol=1e-5, atol=1e-5 * max(1.0, float(np.abs(res[2]).max()))), kid
 
 
+def test_wave_sync_is_bitwise_neutral(cuda, ft, dev):
+    """The wave re-synchronisation of large problems (a barrier among the leader producers at whole-tile boundaries) only
+    delays loads: forced on a multi-wave shape, with and without cut tiles / ABFT, the results must not change a bit."""
+    rng = np.random.default_rng(11)
+    M, N, K = 2048, 2304, 288   # 72 tiles of 256x256 on 74 CTA pairs is one wave: use the 128-wide pair tile as well
+    A, B = _rand(rng, M * K), _rand(rng, N * K)
+    C0 = rng.standard_normal(M * N).astype(np.float32)
+    for kid in (6, 16, 22, 32, 21, 31):
+        outs = []
+        for sync in (0, 1):
+            try:
+                ft.debug_set("wave_sync", sync)
+                dev.stats()
+                outs.append(_run(cuda, dev, kid, M, N, K, A, B, C0, 0.5, 2.0, opts=ft.make_opts(selftest=(10000.0, 33, 7)) if kid in (16, 31, 32) else None))
+                if kid in (16, 31, 32):
+                    st = dev.stats()
+                    assert st["detected"] == st["corrected"] > 0 and st["uncorrectable"] == 0, (kid, sync, st)
+            finally:
+                ft.debug_set("wave_sync", -1)
+        assert np.array_equal(outs[0], outs[1]), kid
+
+
 @pytest.mark.parametrize("slices", [2, 3, 5])
 def test_split_k_head_forced(cuda, ft, dev, oracle, slices):
     """Force cut tiles (pieces park their accumulator, the next piece seeds tensor memory with it) on shapes where the
