@@ -111,8 +111,6 @@ struct ftsgemm_handle_s {
     bool uploaded = false;
   };
   std::map<std::array<long long, 6>, CachedPlan> plans;  // key: kernel id, M, N, K, units, forced slices
-  int *d_enc_count = nullptr;   // helper warps that have finished their share of the in-kernel encode (monotonic)
-  int enc_total = 0;            // host mirror of the value the counter reaches after the last launch
   int *d_wave_cnt = nullptr;    // wave re-synchronisation counters (cleared per launch)
   size_t wave_cnt_cap = 0;
   int *d_enc_prog = nullptr;    // encoder items: per k-chunk progress counters (monotonic per shape)
@@ -252,16 +250,15 @@ void chk_costs(const KernelParams &p, std::vector<double> *out) {
 //   2  encoder ITEMS: one unit per tile-column streams B through its shared-memory ring (no UMMA) and reduces it.  The
 //      items run while every SM is fetching cold operands and get 1/148 of the HBM bandwidth each: ~1.2 tile-times per
 //      item (715 vs 709 TFLOP/s at 4096^3, 781 vs 785 at 8192^3)
-//   0  helper warps read their share of B from global memory in the background (3-8x slower: they cannot keep enough
-//      bytes in flight next to the main loop)
+// (A fifth variant -- helper warps reading their share of B from global memory in the background of the main loops -- was
+//  3-8x slower, because a few warps per SM cannot keep enough bytes in flight, and has been removed.)
 // Modes 2 / 3 need the 3-D tensor map of B (N % 32 == 0); mode 3 also needs spare units for the checksum items.
 int encode_mode(int N, int tiles_n, int units) {
   const long long m = dbg("enc_mode", -2);
-  const bool items_ok = N % kAtomMN == 0 && dbg("enc_rounding", 0) == 0;  // (the rounding experiment only exists in modes 0/1)
+  const bool items_ok = N % kAtomMN == 0 && dbg("enc_rounding", 0) == 0;  // (the rounding experiment only exists in the pre-pass)
   const bool tiles_ok = items_ok && 2 * tiles_n <= units;
   if (m == 3) return tiles_ok ? 3 : 1;
   if (m == 2) return items_ok ? 2 : 1;
-  if (m == 0) return 0;
   return 1;
 }
 
@@ -309,10 +306,6 @@ PlanInput make_plan_input(int num_sms, int CG, int BN, int K, const KernelParams
     in.n_enc_items = p.tiles_n;
     in.enc_cost = static_cast<double>(dbg("enc_cost_permille", 1200)) * 1e-3;
     in.chk_release = std::max(0.0, in.enc_cost - in.chk_col_cost[0]) + 0.05;
-  } else if (p.tiles_c > 0 && dbg("enc_mode", -2) == 0) {
-    // helper warps stream B from global memory in the background (~1 TB/s next to the main loops)
-    const double enc_us = 4.0 * static_cast<double>(p.N) * K / 1.0e6 + 3.0;
-    in.chk_release = enc_us / tile_us;
   }
   return in;
 }
@@ -432,9 +425,15 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     if (need_encode && enc_mode_v == 1) {
       // stand-alone pre-pass in the caller's stream
       const int rounding = static_cast<int>(dbg("enc_rounding", 0));
-      const int grid = 4 * h->num_sms;
-#define FT_ENC(bn) \
-  if (BN == bn) encode_b_kernel<bn><<<grid, kEncWarps * 32, 0, stream>>>(dB, N, K, N, h->d_chk, chk_ld, rounding, p.tiles_n);
+      // grid-stride over (column block, k-row group) items.  Item size (8 / 4 KiB) and grid (2 / 4 blocks per SM) make no
+      // measurable difference (profiles/r01_probe22_*: 695-698 TFLOP/s at 4096^3 for all four): the pass is HBM time.
+      const int grid = static_cast<int>(dbg("enc_blocks_per_sm", 4)) * h->num_sms;
+      const bool small_items = dbg("enc_kr", 8) == 4;
+#define FT_ENC(bn)                                                                                                          \
+  if (BN == bn) {                                                                                                           \
+    if (small_items) encode_b_kernel<bn, 4><<<grid, kEncWarps * 32, 0, stream>>>(dB, N, K, N, h->d_chk, chk_ld, rounding, p.tiles_n); \
+    else encode_b_kernel<bn, 8><<<grid, kEncWarps * 32, 0, stream>>>(dB, N, K, N, h->d_chk, chk_ld, rounding, p.tiles_n);             \
+  }
       FT_ENC(32) FT_ENC(64) FT_ENC(128) FT_ENC(256)
 #undef FT_ENC
       FT_CUDA(h, cudaGetLastError());
@@ -554,26 +553,6 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     p.enc_prog_target = h->enc_prog_value;
     p.enc_out = h->d_chk;
     p.enc_ld = chk_ld_v;
-    p.enc_rounding = static_cast<int>(dbg("enc_rounding", 0));
-  }
-  if (ft && enc_mode_v == 0) {
-    // In-kernel encode: the helper warps of every CTA stream their share of B while the first main loops run; checksum
-    // items wait until all of them have reported (monotonic counter, so a launch that reuses the vectors waits for
-    // nothing new).
-    if (h->enc_total > (1 << 30)) {
-      FT_CUDA(h, cudaMemsetAsync(h->d_enc_count, 0, sizeof(int), stream));
-      h->enc_total = 0;
-    }
-    p.enc_count = h->d_enc_count;
-    if (need_encode) {
-      p.enc_b = dB;
-      p.enc_ldb = N;
-      p.enc_out = h->d_chk;
-      p.enc_ld = chk_ld_v;
-      p.enc_rounding = static_cast<int>(dbg("enc_rounding", 0));
-      h->enc_total += units * CG * 4;
-    }
-    p.enc_target = h->enc_total;
   }
   {
     // Wave re-synchronisation for problems that run many waves over operands that do not fit L2.  Measured
@@ -792,11 +771,6 @@ int ftsgemm_create(ftsgemm_handle_t *out) {
     delete h;
     return FTSGEMM_ERR_CUBLAS;
   }
-  if (cudaMalloc(&h->d_enc_count, sizeof(int)) != cudaSuccess ||
-      cudaMemset(h->d_enc_count, 0, sizeof(int)) != cudaSuccess) {
-    ftsgemm_destroy(h);
-    return FTSGEMM_ERR_CUDA;
-  }
   if (cudaMalloc(&h->d_stats, sizeof(DeviceStats)) != cudaSuccess ||
       cudaMemset(h->d_stats, 0, sizeof(DeviceStats)) != cudaSuccess ||
       cudaMalloc(&h->d_verify, 4 * sizeof(double)) != cudaSuccess) {
@@ -816,7 +790,6 @@ int ftsgemm_destroy(ftsgemm_handle_t h) {
   cudaFree(h->d_chk_out);
   cudaFree(h->d_sk);
   cudaFree(h->d_trace);
-  cudaFree(h->d_enc_count);
   cudaFree(h->d_enc_prog);
   cudaFree(h->d_wave_cnt);
   for (auto &kv : h->plans) {

@@ -104,14 +104,10 @@ struct KernelParams {
   float *chk_out;       // M x n_chk_cols, column-major (ld = M): expected checksums r1/r2 (hi, lo each)
   int *chk_flags;       // [slab * tiles_c + c] = chk_epoch once checksum tile-column c of that 32-row slab is published
   int chk_epoch;
-  // in-kernel encode (helper warps): B -> enc_out[k][enc_ld] (= the checksum operand the tmChk tensor map reads)
-  const float *enc_b;   // != nullptr: this launch encodes B itself
-  int enc_ldb;
+  // in-kernel encode (encoder items / tiles): the ENCODE workers write enc_out[k][enc_ld] (= the checksum operand the
+  // tmChk tensor map reads)
   float *enc_out;
   int enc_ld;
-  int enc_rounding;
-  int *enc_count;       // != nullptr: every helper warp adds 1 when its share is written; checksum items wait until
-  int enc_target;       //             the counter has reached enc_target (a later launch that reuses B waits for nothing new)
   // encoder items (kind 4, always a prefix of a unit's list): the unit streams B[tile-column] through the shared-memory
   // ring and its helper warps write the checksum vectors; every helper warp adds 1 to enc_prog[c] when its share of the
   // k-blocks [32c, 32c+32) of the tile-column is done, checksum items wait for enc_prog[c] >= enc_prog_target before
@@ -567,11 +563,11 @@ struct TransposeReduce {
 
 // One warp encodes items (column block t, KR consecutive k-rows), item = gw, gw + nw, ...; t fastest, so that warps
 // running side by side read neighbouring 1 KiB segments of the same rows of B.
-template <int BN>
+template <int BN, int KRQ>
 __device__ __forceinline__ void encode_b_warp(const float *__restrict__ B, int N, int K, int ldb, float *__restrict__ chk,
                                               int chk_ld, int rounding, int tiles_n, int gw, int nw, int lane) {
   constexpr int J = BN >= 128 ? BN / 128 : 0;   // float4 loads per lane and k-row
-  constexpr int KR = (J == 2) ? 8 : 16;         // k-rows per item: 16 float4 (J = 2, 1) in flight per lane
+  constexpr int KR = (J == 2) ? KRQ : 2 * KRQ;  // k-rows per item: 2 * KRQ float4 (J = 2, 1) in flight per lane
   constexpr int NV = 2 * KR;
   const int k_items = (K + KR - 1) / KR;
   const int total = tiles_n * k_items;
@@ -934,18 +930,6 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         ptx::pdl_wait();  // the pre-pass kernel has completed and its writes are visible
         pdl_done = true;
       }
-      if (FT && b_is_chk && p.enc_count != nullptr) {
-        // the checksum vectors are being written by the helper warps of all CTAs: checksum items (and only they) wait
-        if (lane == 0) {
-          ptx::Watchdog wd;
-          while (ld_acquire(p.enc_count) - p.enc_target < 0) {
-            __nanosleep(128);
-            wd.tick();
-          }
-        }
-        __syncwarp();
-        ptx::fence_proxy_async();  // generic-proxy writes (st.global) -> async-proxy reads (TMA)
-      }
       if (p.trace != nullptr && is_leader && lane == 0) trace_put(p, unit, item_idx, 0, globaltimer_ns());
       // The loop body is specialised OUTSIDE the k loop: with 3-D tensor maps a stage is exactly two TMA instructions
       // (predicated-off TMA instructions still cost issue time on the single producer thread).
@@ -1238,15 +1222,6 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================================================================== helper warps (TMEM lane quadrant = warp & 3)
     const int q = warp & 3;
     if (FT && p.enc_prog != nullptr) encoder_prefix(q);
-    if (FT && p.enc_b != nullptr && p.enc_count != nullptr) {
-      if (p.trace != nullptr && is_leader && q == 0 && lane == 0) trace_put(p, unit, p.trace_cap - 1, 1, globaltimer_ns());
-      encode_b_warp<BN>(p.enc_b, p.N, p.K, p.enc_ldb, p.enc_out, p.enc_ld, p.enc_rounding, p.tiles_n,
-                        static_cast<int>(blockIdx.x) * 4 + q, static_cast<int>(gridDim.x) * 4, lane);
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) atomicAdd(p.enc_count, 1);
-      if (p.trace != nullptr && is_leader && q == 0 && lane == 0) trace_put(p, unit, p.trace_cap - 1, 0, globaltimer_ns());
-    }
     if (p.sk_tiles > 0) {
       const uint32_t seeded_leader = (CG == 2) ? ptx::mapa(seeded_bar(0), 0) : seeded_bar(0);
       const size_t ws_slab = static_cast<size_t>(kBM) * BN;
@@ -1300,12 +1275,12 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kEncWarps = 8;
 
-template <int BN>
+template <int BN, int KRQ>
 __global__ void __launch_bounds__(kEncWarps * 32, 2)
 encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, float *__restrict__ chk, int chk_ld, int rounding,
                 int tiles_n) {
   ptx::pdl_launch_dependents();  // the GEMM kernel may start on SMs as they drain (its checksum items wait for this grid)
-  encode_b_warp<BN>(B, N, K, ldb, chk, chk_ld, rounding, tiles_n, blockIdx.x * kEncWarps + (threadIdx.x >> 5),
+  encode_b_warp<BN, KRQ>(B, N, K, ldb, chk, chk_ld, rounding, tiles_n, blockIdx.x * kEncWarps + (threadIdx.x >> 5),
                     gridDim.x * kEncWarps, threadIdx.x & 31);
 }
 
