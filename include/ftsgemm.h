@@ -124,7 +124,9 @@ typedef struct ftsgemm_stats {
 } ftsgemm_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------- */
-int ftsgemm_create(ftsgemm_handle_t *out);   /* binds to the current CUDA device; owns cuBLAS handle + workspace */
+int ftsgemm_create(ftsgemm_handle_t *out);   /* binds to the current CUDA device; owns cuBLAS handle + workspace.
+                                                 A handle is one in-order context: calls on it must be issued from one
+                                                 stream at a time (use one handle per concurrently used stream). */
 int ftsgemm_destroy(ftsgemm_handle_t h);
 int ftsgemm_abi_version(void);
 const char *ftsgemm_error_string(int code);
