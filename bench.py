@@ -207,7 +207,10 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--size", type=int, default=4096)
+    ap.add_argument("--size", type=int, default=4096, help="M=N=K of the block each GPU computes (weak scaling)")
+    ap.add_argument("--global-size", type=int, default=0,
+                    help="G > 0: ONE G^3 product sharded over the P x Q rank grid (M = G/P, N = G/Q, K = G per rank; strong "
+                         "scaling, BASELINE.json config 5: --gpus 8 --global-size 32768)")
     ap.add_argument("--id", type=int, default=31, help="fused ABFT kernel id (31 = 256x256 CTA-pair tile, 16 = literal huge 128x128)")
     ap.add_argument("--sweep", action="store_true", help="also print the README-style table 1024..16384 to stderr")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -239,6 +242,11 @@ def main():
     while P * P * 2 <= world and world % (P * 2) == 0:
         P *= 2
     Q = world // P
+    if args.global_size > 0:
+        G = args.global_size
+        if G % (P * 256) or G % (Q * 256):
+            raise SystemExit("--global-size must be a multiple of 256 * the rank grid")
+        M, N, K = G // P, G // Q, G
     g = torch.Generator(device="cuda").manual_seed(1234 + rank)
 
     def ref_dist(count):
@@ -355,14 +363,18 @@ def main():
     achieved = flops / (k_ms * 1e-3) / 1e12
     info = [k for k in pkg.kernel_table() if k["id"] == args.id][0]
     out = {
-        "metric": METRIC, "value": round(value, 1), "unit": "GFLOPS", "n_gpus": world, "steps": steps, "warmup": W,
-        "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": round(value / world / README_ABFT_HUGE_4096, 2) if n == 4096 else None,
+        "metric": METRIC if (n == 4096 and args.global_size == 0) else
+                  METRIC.replace("M=N=K=4096", f"one {args.global_size}^3 product" if args.global_size > 0 else f"M=N=K={n}"),
+        "value": round(value, 1), "unit": "GFLOPS", "n_gpus": world, "steps": steps, "warmup": W,
+        "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "strong" if args.global_size > 0 else "weak",
+        "vs_baseline": round(value / world / README_ABFT_HUGE_4096, 2) if (n == 4096 and args.global_size == 0) else None,
         "dtype": "tf32 multiply, f32 accumulate", "data": "synthetic",
         "config": {"workload": f"fused ABFT SGEMM id {args.id} ({info['name']}, tile {info['tile'][0]}x{info['tile'][1]}), "
-                               f"M=N=K={n} per GPU, alpha=1, beta=-1.5 (sgemm.cu:22,234), reference input distribution",
+                               + (f"one {args.global_size}^3 product, block M={M} N={N} K={K} per GPU" if args.global_size > 0 else f"M=N=K={n} per GPU")
+                               + ", alpha=1, beta=-1.5 (sgemm.cu:22,234), reference input distribution",
                    "sharding": f"{P}x{Q} C-block grid, A/B row-panels resident per GPU, NCCL all-reduce of fault counters per step" if world > 1 else "single GPU",
-                   "l2": f"inputs {3 * 4 * n * n / 2**20:.0f} MiB per step vs 126 MB L2: larger than L2, no flush needed" if n >= 4096 else "L2-resident working set (small size)",
+                   "l2": (f"inputs {4 * (M * K + N * K + M * N) / 2**20:.0f} MiB per step vs 126 MB L2: larger than L2, no flush needed"
+                          if 4 * (M * K + N * K + M * N) > 160e6 else "L2-resident working set (small size)"),
                    "baseline_note": "vs_baseline = per-GPU value / 4005 GFLOPS (README.md:53 abft_kernel_huge @4096, GPU unspecified)"},
         "abft": {"overhead_pct_vs_cublas_tf32": round(100.0 * (comp["cublas_tf32"] / (value / world) - 1.0), 2),
                  "overhead_pct_vs_own_plain_kernel": round(100.0 * (comp["plain"] / (value / world) - 1.0), 2),
@@ -376,7 +388,7 @@ def main():
         "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
                      "frac": round(achieved / tf32_peak, 4), "traffic": None,
                      "note": f"kernel ftsgemm_tc_kernel alone (encode reused), 2*M*N*K per launch / CUDA-event mean; peak = bf16 burst {peaks['bf16_tflops']} / 2, {peaks['src']}"},
-        "e2e": {"value": round(e2e_val, 1), "unit": "GFLOPS", "h2d_bytes_per_step": 3 * 4 * n * n, "d2h_bytes_per_step": 4 * n * n,
+        "e2e": {"value": round(e2e_val, 1), "unit": "GFLOPS", "h2d_bytes_per_step": 4 * (M * K + N * K + M * N), "d2h_bytes_per_step": 4 * M * N,
                 "steps": e2e_steps, "finite": result_ok},
         "gpu_launches": 2 * steps,  # encode_b_kernel + ftsgemm_tc_kernel per step
         "clocks": clocks,
