@@ -149,6 +149,33 @@ def test_encode_in_kernel_and_prepass_agree(cuda, ft, dev):
           assert np.allclose(res[0], res[2], rtol=1e-5, atol=1e-5 * max(1.0, float(np.abs(res[2]).max()))), kid
 
 
+def test_encode_variants_long_k_and_odd_k_blocks(cuda, ft, dev, oracle):
+    """Encoder items / tiles publish their progress per chunk of 32 k-blocks and, on a CTA pair, alternate k-blocks between
+    the two CTAs: K = 4128 is 129 k-blocks (5 chunks, an odd count: the peer's last slot lies past the end of K and is
+    zero-filled).  Verdicts and results must agree with the pre-pass and the TF32 model."""
+    rng = np.random.default_rng(21)
+    M, N, K = 512, 768, 4128
+    A, B = _rand(rng, M * K), _rand(rng, N * K)
+    C0 = rng.standard_normal(M * N).astype(np.float32)
+    model = oracle.sgemm_nt_tf32_model(M, N, K, 1.0, A, B, 0.5, C0, "trunc")
+    faults = [{"row": 300, "col": 5, "xor": 1 << 30}, {"row": 511, "col": 767, "add": 123.0}]
+    outs = {}
+    for kid in (31, 16):
+        for mode in (3, 2, 1):
+            try:
+                ft.debug_set("enc_mode", mode)
+                dev.stats()
+                got = _run(cuda, dev, kid, M, N, K, A, B, C0, 1.0, 0.5, opts=ft.make_opts(faults=faults))
+                st = dev.stats()
+                assert st["detected"] == 2 and st["corrected"] == 2 and st["uncorrectable"] == 0, (kid, mode, st)
+                assert oracle.error_metrics(model, got)["rel_fro"] < TOL_MODEL, (kid, mode)
+                outs[(kid, mode)] = got
+            finally:
+                ft.debug_set("enc_mode", -1)
+        assert np.array_equal(outs[(kid, 3)], outs[(kid, 2)])
+        assert np.allclose(outs[(kid, 3)], outs[(kid, 1)], rtol=1e-5, atol=1e-5 * np.abs(outs[(kid, 1)]).max())
+
+
 def test_wave_sync_is_bitwise_neutral(cuda, ft, dev):
     """The wave re-synchronisation of large problems (a barrier among the leader producers at whole-tile boundaries) only
     delays loads: forced on a multi-wave shape, with and without cut tiles / ABFT, the results must not change a bit."""
