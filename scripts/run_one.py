@@ -1,4 +1,5 @@
-"""Run one kernel id at one size a few times (target for ncu).  usage: run_one.py ID N [reps] [inject]"""
+"""Run one kernel id at one size a few times (target for ncu / compute-sanitizer).
+usage: run_one.py ID N [reps] [key=value debug knobs ...]"""
 import sys
 from pathlib import Path
 import numpy as np
@@ -8,7 +9,10 @@ import __graft_entry__ as ge
 import cuda_rt as cu
 pkg = ge.load_package()
 kid, n = int(sys.argv[1]), int(sys.argv[2])
-reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+reps = int(sys.argv[3]) if len(sys.argv) > 3 and '=' not in sys.argv[3] else 3
+for a in sys.argv[3:]:
+    if '=' in a:
+        pkg.debug_set(a.split('=')[0], int(a.split('=')[1]))
 rng = np.random.default_rng(0)
 A = (rng.integers(-9, 10, n * n) * 0.1).astype(np.float32)
 B = (rng.integers(-9, 10, n * n) * 0.1).astype(np.float32)
