@@ -16,13 +16,13 @@
 //                             TMEM, two accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1
 //   warp 2   TMEM allocator
 //   warps 4-7 epilogue      : tcgen05.ld (lane = row), per-row ABFT detect / locate / correct, C = alpha*acc + beta*C
-//   warps 8-11 helpers      : (a) ENCODE of B in the background of the first tiles' main loops (the SM's LSU and issue
-//                             slots are idle while one thread feeds the tensor core), (b) seeding tensor memory with the
-//                             parked accumulator of the previous K-piece of a cut tile (plan.h)
+//   warps 8-11 helpers      : (a) seeding tensor memory with the parked accumulator of the previous K-piece of a cut
+//                             tile (plan.h), (b) together with the epilogue warps, the ENCODE workers of encoder
+//                             items / tiles (optional in-kernel encode: they reduce B stages from shared memory)
 //
 // ABFT scheme.  With b~ = the TF32 value the tensor core actually consumes and J_t the columns
 // of N-tile t:
-//   encode    (helper warps of this kernel, or the pre-pass encode_b_kernel; reference ENCODE ft_sgemm_huge.cuh:150-168)
+//   encode    (pre-pass encode_b_kernel, or the ENCODE workers of this kernel; reference ENCODE ft_sgemm_huge.cuh:150-168)
 //             e_t[k] = sum_{n in J_t} b~[n,k]      w_t[k] = sum_{n in J_t} (n-n0+1) b~[n,k]     (2-way TF32 split each)
 //   checksum GEMM (reference CHECKSUM-GEMV :171-213): the 4 checksum vectors of every N-tile are appended to B as extra
 //             "rows", i.e. the SAME kernel computes extra tile-columns  R = A * [e_t, w_t]^T  first (FP32 accumulate in
