@@ -121,15 +121,18 @@ def _cpu_port_baseline(n, seconds_target=12.0):
         A = (rng.integers(-9, 10, n * n) * 0.1).astype(np.float32)
         B = (rng.integers(-9, 10, n * n) * 0.1).astype(np.float32)
     nn = n if n > 1024 else min(n, 1024)
-    rows = np.arange(4, dtype=np.int32)
-    t0 = time.time()
-    O.sgemm_nt_rows(nn, nn, nn, 1.0, A, B, 0.0, None, rows)
-    t_probe = max(time.time() - t0, 1e-4)
-    nrows = int(max(4, min(nn, 4 * seconds_target / t_probe)))
-    rows = np.linspace(0, nn - 1, nrows).astype(np.int32)
-    t0 = time.time()
-    O.sgemm_nt_rows(nn, nn, nn, 1.0, A, B, 0.0, None, rows)
-    dt = time.time() - t0
+    # chunks of 64 sampled rows (enough for the OpenMP team to reach its steady rate) until the time budget is spent:
+    # a one-shot extrapolation from a short probe was off by 2-3x
+    chunk = 64
+    all_rows = np.linspace(0, nn - 1, min(nn, 4096)).astype(np.int32)
+    O.sgemm_nt_rows(nn, nn, nn, 1.0, A, B, 0.0, None, all_rows[:4])  # first touch / thread start-up
+    nrows, dt = 0, 0.0
+    while dt < seconds_target and nrows < len(all_rows):
+        rows = all_rows[nrows:nrows + chunk]
+        t0 = time.time()
+        O.sgemm_nt_rows(nn, nn, nn, 1.0, A, B, 0.0, None, rows)
+        dt += time.time() - t0
+        nrows += len(rows)
     gf = 2.0 * nrows * nn * nn / dt / 1e9
     return {"value": round(gf, 3), "unit": "GFLOPS", "cores": O.num_threads(), "kind": "port",
             "sample": f"{nrows} of {nn} rows x {nn} cols x K={nn} (sequential-k fp32, OpenMP over columns), {dt:.1f} s"}
