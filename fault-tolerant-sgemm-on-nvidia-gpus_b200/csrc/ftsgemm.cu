@@ -290,6 +290,7 @@ PlanInput make_plan_input(int num_sms, int CG, int BN, int K, const KernelParams
   in.max_slices = force == 0 ? 1 : 2;
   in.force_slices = force > 1 ? static_cast<int>(force) : 0;
   in.slab_bytes = static_cast<size_t>(CG) * kBM * BN * sizeof(float);
+  in.full_search = dbg("plan_full_search", 0) != 0 ? 1 : 0;
   // operands larger than ~3/4 of the 126 MB L2: keep the units in k-lockstep (plan.h)
   const long long lock = dbg("lockstep", -2);
   in.lockstep = lock >= 0 ? static_cast<int>(lock)
@@ -467,7 +468,7 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
   const bool encode_items = enc_plan != 0;
   const PlanInput pin = make_plan_input(h->num_sms, CG, BN, K, p, enc_plan);
   const std::array<long long, 6> key = {v.info.id, M, N, K, pin.units,
-                                        pin.force_slices * 16 + pin.max_slices + enc_plan * 1024 + pin.lockstep * 8192};
+                                        pin.force_slices * 16 + pin.max_slices + enc_plan * 1024 + pin.lockstep * 8192 + pin.full_search * 16384};
   ftsgemm_handle_s::CachedPlan &cp = h->plans[key];
   if (!cp.uploaded) {
     if (h->plans.size() > 64) {  // bound the cache: drop everything but this entry

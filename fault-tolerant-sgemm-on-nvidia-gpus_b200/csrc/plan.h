@@ -68,6 +68,8 @@ struct PlanInput {
   double seed_overhead = 0.0;        // extra tile-times of a seeded piece (its accumulator stage is loaded before the first UMMA)
   int max_slices = 2;   // 1 disables cutting
   int force_slices = 0; // > 1: cut into exactly this many equal pieces (tests)
+  int full_search = 0;  // 1: always try the full candidate menu (default: a reduced menu from 8 waves up, where a cut
+                        //    can only buy a few per cent and the simulation of thousands of items is what costs)
   int lockstep = 0;     // 1: the operands do not fit in L2, so the units must keep streaming the SAME k range of the
                         //    panels they share (measured at 8192^3: first pieces of mixed lengths put the units out of
                         //    phase and every whole tile got 10 % slower, HBM-bound): one cut fraction for all cut tiles
@@ -245,18 +247,27 @@ inline Plan build_plan(const PlanInput &in) {
         const double chk0 = in.n_chk_tiles > 0 ? in.chk_col_cost[0] : 0.5;
         const int n_chk_units = std::min(in.n_chk_tiles, P);
         std::vector<int> he, hl;
+        const bool reduced = !in.full_search && T >= 8 * P;  // planning time: 0.3-0.5 s -> 20 ms for 4000+ tiles
         he.push_back(0);
-        const int e_extra[] = {P - n_chk_units, T % P, P / 2, P, P / 4, (3 * P) / 4, 2 * P - n_chk_units};
-        for (int e : e_extra) add_unique(&he, e, 1, T);
         hl.push_back(0);
-        const int l_extra[] = {P / 8, P / 4, (3 * P) / 8, P / 2, (5 * P) / 8, (3 * P) / 4, P, T % P, (T % P) / 2};
-        for (int e : l_extra) add_unique(&hl, e, 1, T);
-        const double fes[] = {chk0, 0.25, 1.0 / 3, 0.5, 2.0 / 3, 0.75};
+        if (reduced) {
+          const int e_extra[] = {P - n_chk_units, P};
+          for (int e : e_extra) add_unique(&he, e, 1, T);
+          const int l_extra[] = {T % P, (T % P) / 2, P / 2, P};
+          for (int e : l_extra) add_unique(&hl, e, 1, T);
+        } else {
+          const int e_extra[] = {P - n_chk_units, T % P, P / 2, P, P / 4, (3 * P) / 4, 2 * P - n_chk_units};
+          for (int e : e_extra) add_unique(&he, e, 1, T);
+          const int l_extra[] = {P / 8, P / 4, (3 * P) / 8, P / 2, (5 * P) / 8, (3 * P) / 4, P, T % P, (T % P) / 2};
+          for (int e : l_extra) add_unique(&hl, e, 1, T);
+        }
+        const double fes[] = {chk0, 0.5, 0.25, 1.0 / 3, 2.0 / 3, 0.75};
         const double fls[] = {0.5, 1.0 / 3, 2.0 / 3};
+        const int n_fe = reduced ? 2 : 6;
         for (int He : he)
           for (int Hl : hl) {
             if (He + Hl <= 0 || He + Hl > T) continue;
-            for (int a = 0; a < (He > 0 ? 6 : 1); ++a)
+            for (int a = 0; a < (He > 0 ? n_fe : 1); ++a)
               for (int b = 0; b < (Hl > 0 ? 3 : 1); ++b) {
                 Cut c;
                 c.He = He;
