@@ -176,6 +176,46 @@ def test_encode_variants_long_k_and_odd_k_blocks(cuda, ft, dev, oracle):
         assert np.allclose(outs[(kid, 3)], outs[(kid, 1)], rtol=1e-5, atol=1e-5 * np.abs(outs[(kid, 1)]).max())
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_random_shapes_and_knobs(cuda, ft, dev, oracle, seed):
+    """Seeded fuzz over ragged shapes, kernel variants, alpha/beta and every decomposition knob (cut pieces, encode
+    variants, wave re-synchronisation): results against the TF32 model, the ABFT variant bit-equal to its plain twin when
+    fault-free, an injected fault corrected."""
+    rng = np.random.default_rng(1000 + seed)
+    M = int(rng.integers(1, 380)) * 4
+    N = int(rng.integers(1, 380)) * 4
+    K = int(rng.integers(1, 1100))
+    name = ["small", "medium", "huge", "wide", "giant", "pair128"][seed % 6]
+    alpha = float(rng.choice([1.0, 0.75, -2.0]))
+    beta = float(rng.choice([0.0, -1.5, 1.0]))
+    knobs = {"splitk": int(rng.choice([-1, 0, 2, 3])), "enc_mode": int(rng.choice([1, 2, 3])),
+             "wave_sync": int(rng.choice([0, 1])), "pdl": int(rng.choice([0, 1]))}
+    A, B = rng.standard_normal(M * K).astype(np.float32), rng.standard_normal(N * K).astype(np.float32)
+    C0 = rng.standard_normal(M * N).astype(np.float32)
+    model = oracle.sgemm_nt_tf32_model(M, N, K, alpha, A, B, beta, C0, "trunc")
+    fr, fc = int(rng.integers(0, M)), int(rng.integers(0, N))
+    try:
+        for k, v in knobs.items():
+            ft.debug_set(k, v)
+        plain = _run(cuda, dev, ft.SGEMM_IDS[name], M, N, K, A, B, C0, alpha, beta)
+        dev.stats()
+        abft = _run(cuda, dev, ft.ABFT_IDS[name], M, N, K, A, B, C0, alpha, beta)
+        st = dev.stats()
+        assert st["detected"] == 0 and st["rows_checked"] > 0, (knobs, st)
+        assert np.array_equal(plain, abft), (name, M, N, K, knobs)
+        assert oracle.error_metrics(model, abft)["rel_fro"] < TOL_MODEL, (name, M, N, K, knobs)
+        fixed = _run(cuda, dev, ft.ABFT_IDS[name], M, N, K, A, B, C0, alpha, beta,
+                     opts=ft.make_opts(faults=[{"row": fr, "col": fc, "xor": 1 << 30}]))
+        st = dev.stats()
+        assert st["detected"] == 1 and st["corrected"] == 1, (name, M, N, K, knobs, st)
+        diff = np.flatnonzero(fixed != abft)
+        assert set(diff) <= {fr + fc * M}
+        assert oracle.error_metrics(model, fixed)["rel_fro"] < TOL_MODEL
+    finally:
+        for k in knobs:
+            ft.debug_set(k, -1)
+
+
 def test_wave_sync_is_bitwise_neutral(cuda, ft, dev):
     """The wave re-synchronisation of large problems (a barrier among the leader producers at whole-tile boundaries) only
     delays loads: forced on a multi-wave shape, with and without cut tiles / ABFT, the results must not change a bit."""
