@@ -342,6 +342,9 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
   const int BN = v.bn, CG = v.cg;
   const bool ft = v.info.fault_tolerant != 0;
   if ((M % 4) || (N % 4)) return FTSGEMM_ERR_UNSUPPORTED;  // TMA global strides must be multiples of 16 bytes
+  // work-plan items carry k-block indices in 16 bits and tile indices in 31; the trace / wave tables are sized per unit
+  if ((K + kBK - 1) / kBK > 65535) return FTSGEMM_ERR_UNSUPPORTED;
+  if ((static_cast<long long>(M + kBM * CG - 1) / (kBM * CG)) * ((N + BN - 1) / BN) > (1ll << 28)) return FTSGEMM_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB) | reinterpret_cast<uintptr_t>(dC)) & 15)
     return FTSGEMM_ERR_INVALID_ARG;
 
