@@ -559,6 +559,14 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     p.enc_ld = chk_ld_v;
   }
   {
+    // Helper-assisted final epilogues (the helper warp of each TMEM lane quadrant takes the upper half of the columns).
+    // Measured (profiles/r01_probe24_*, beta = -1.5): ABFT +2.4 % at 1024^3, +5 % at 2048^3, +2 % at 3072^3, +0.8 % at
+    // 4096^3, +0.5 % at 8192^3; plain kernel +10.6 % at 1024^3 (one wave: the whole epilogue is exposed), neutral in
+    // between, -0.7 % at 8192^3 (the pair barriers cost more than the 3.6 us tail they shorten) -- hence the rule.
+    const long long ea = dbg("epi_assist", -2);
+    p.epi_assist = ea >= 0 ? (ea != 0) : (ft || cp.plan.items.size() <= 3 * static_cast<size_t>(units));
+  }
+  {
     // Wave re-synchronisation for problems that run many waves over operands that do not fit L2.  Measured
     // (profiles/r01_probe21_*, r01_trace_16384_per_wave.txt): without it the units' start times drift apart by ~2 us per
     // wave and the tile time grows from 178 to 209 us over the 56 waves of 16384^3; with it the spread stays below 6 us:

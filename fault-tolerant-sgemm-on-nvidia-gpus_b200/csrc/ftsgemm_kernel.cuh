@@ -119,6 +119,9 @@ struct KernelParams {
   // ~2 us per wave and the tile time grows 17 % over the 56 waves of 16384^3, profiles/r01_trace_*_16384*)
   int *wave_cnt;        // [w] = leader producers that have issued the last load of their w-th whole tile (cleared per launch)
   const int *wave_target;  // [w] = number of units that own more than w whole tiles
+  int epi_assist;       // 1: the helper warp of each TMEM lane quadrant takes the upper half of the columns of every final
+                        //    data-tile epilogue (check sums + store pass), halving the epilogue the units expose at the
+                        //    end of their lists -- and the whole epilogue of a one-wave problem
   int pdl_wait;         // 1: launched as a programmatic dependent of the encode pre-pass -- checksum items (the only
                         //    consumers of its output) execute griddepcontrol.wait before their first load
   float tau_abs, tau_rel;
@@ -156,7 +159,7 @@ struct TileCfg {
   static constexpr int kTmemNeeded = kAccStages * BN;
   static constexpr int kTmemCols = kTmemNeeded <= 32 ? 32 : kTmemNeeded <= 64 ? 64 : kTmemNeeded <= 128 ? 128
                                    : kTmemNeeded <= 256 ? 256 : 512;
-  static constexpr int kBarBytes = 256;
+  static constexpr int kBarBytes = 2048;  // barriers (512) + the epilogue pairs' exchange area (4 x 32 lanes x 3 floats)
   static constexpr int kMaxSmem = 227 * 1024 - 1024 /*alignment slack*/ - kBarBytes;
   static constexpr int kStagesFit = kMaxSmem / kStageBytes;
   static constexpr int kStages = kStagesFit > FTSGEMM_MAX_STAGES ? FTSGEMM_MAX_STAGES : kStagesFit;
@@ -261,10 +264,10 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
 // ------------------------------------------------------------------------------------------------------------
 template <int BN>
 __device__ __forceinline__ void store_tile(uint32_t taddr, float *crow, bool row_ok, int n0, int n_limit, int ldc,
-                                           float alpha, float beta) {
+                                           float alpha, float beta, int c_begin = 0, int c_end = BN / 32) {
   const bool full_n = (n0 + BN <= n_limit);
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     uint32_t v[32];
     ptx::tmem_ld_x32(taddr + c * 32, v);
     ptx::tmem_wait_ld();
@@ -298,9 +301,32 @@ __device__ __forceinline__ void store_tile(uint32_t taddr, float *crow, bool row
 // ABFT check of one accumulator tile (executed by the 4 epilogue warps, lane = row).  Returns the column to replace
 // (or -1) and its corrected value.  q = TMEM lane quadrant of this warp, m = global row of this lane.
 // ------------------------------------------------------------------------------------------------------------
+// The per-row sums of one chunk range of the accumulator (pass 1 of the check; also run by the assisting helper warp).
+template <int BN>
+__device__ __forceinline__ void abft_row_sums(uint32_t taddr, int c_begin, int c_end, float &s1, float &s2, float &sabs) {
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; ++c) {
+    uint32_t v[32];
+    ptx::tmem_ld_x32(taddr + c * 32, v);
+    ptx::tmem_wait_ld();
+    const float wbase = static_cast<float>(c * 32 + 1);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float f = u2f(v[i]);
+      s1 += f;
+      s2 = fmaf(f, wbase + static_cast<float>(i), s2);
+      sabs += fabsf(f);
+    }
+  }
+}
+
+// c_mid < BN / 32: a helper warp of the same TMEM lane quadrant sums the chunks [c_mid, BN/32) and hands its three partial
+// sums over through shared memory (xchg, 3 floats per lane) at named barrier pair_bar (64 threads); the same barrier
+// also orders the injection before the helper's reads.
 template <int BN>
 __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr, int q, int lane, int m, int m0_cta,
-                                           int n0, int n_blk, int &fix_col, float &fix_val) {
+                                           int n0, int n_blk, int &fix_col, float &fix_val, int c_mid = BN / 32,
+                                           uint32_t xchg = 0u, int pair_bar = 0) {
   // ---- fault injection into the TMEM accumulator (reference: ft_sgemm_huge.cuh:324-327) ----
   if (p.inject_mode == 1) {
     if ((p.selftest_row >> 5) == q && p.selftest_col < BN) {
@@ -323,21 +349,19 @@ __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr
       }
     }
   }
+  const bool assisted = c_mid < BN / 32;
+  if (assisted && p.inject_mode != 0) {  // the helper may only read the accumulator after the injection
+    ptx::tc_fence_before();
+    ptx::named_bar_sync(pair_bar, 64);
+  }
   // ---- pass 1: actual row checksums (thread-local: lane == row) ----
   float s1 = 0.0f, s2 = 0.0f, sabs = 0.0f;
-#pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
-    uint32_t v[32];
-    ptx::tmem_ld_x32(taddr + c * 32, v);
-    ptx::tmem_wait_ld();
-    const float wbase = static_cast<float>(c * 32 + 1);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float f = u2f(v[i]);
-      s1 += f;
-      s2 = fmaf(f, wbase + static_cast<float>(i), s2);
-      sabs += fabsf(f);
-    }
+  abft_row_sums<BN>(taddr, 0, c_mid, s1, s2, sabs);
+  if (assisted) {
+    ptx::named_bar_sync(pair_bar, 64);  // the helper's partial sums are in shared memory
+    s1 += ptx::ld_shared_f1(xchg + lane * 12);
+    s2 += ptx::ld_shared_f1(xchg + lane * 12 + 4);
+    sabs += ptx::ld_shared_f1(xchg + lane * 12 + 8);
   }
   // ---- expected checksums published by the checksum tile-columns (wait for this 32-row slab's flag) ----
   {
@@ -715,6 +739,8 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t epi_count = tmem_slot + 8u;
   // peer CTA: worker w's "the leader saw k-block j complete" hand-off (the pair's TMA bytes are credited to the leader)
   auto pfull_bar = [&](int w) { return epi_count + 8u + 8u * w; };
+  auto xchg_base = [&](int q) { return bar_base + 512u + static_cast<uint32_t>(q) * (32u * 12u); };
+  constexpr int kMid = BN / 64;  // chunks [0, kMid) to the epilogue warp, [kMid, BN/32) to its helper (BN >= 64)
   volatile uint32_t *tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
@@ -1177,9 +1203,13 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
         if (lane == 0) atomicExch(p.chk_flags + ((m0_cta >> 5) + q) * p.tiles_c + tc.n_blk, p.chk_epoch);
       } else {
+        // final epilogue of a data tile; with epi_assist the helper warp of this quadrant owns the chunks [kMid, BN/32)
+        const bool assist = p.epi_assist != 0 && BN >= 64;
+        const int c_mid = assist ? kMid : BN / 32;
         int fix_col = -1;
         float fix_val = 0.0f;
-        if (FT && !(p.dbg_flags & 1)) abft_check<BN>(p, taddr, q, lane, m, m0_cta, n0, tc.n_blk, fix_col, fix_val);
+        if (FT && !(p.dbg_flags & 1))
+          abft_check<BN>(p, taddr, q, lane, m, m0_cta, n0, tc.n_blk, fix_col, fix_val, c_mid, xchg_base(q), 4 + q);
         if (tracer) trace_put(p, unit, item_idx, 5, globaltimer_ns());
         if (FT) {
           // rare: write the recomputed elements back into the accumulator (one lane = one row at a time, like the
@@ -1198,7 +1228,15 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ptx::tmem_wait_st();
           }
         }
-        store_tile<BN>(taddr, p.C + m, m < p.M, n0, p.N, p.ldc, p.alpha, p.beta);
+        if (assist && FT && !(p.dbg_flags & 1)) {  // corrections are in tensor memory: the helper may store its half
+          ptx::tc_fence_before();
+          ptx::named_bar_sync(4 + q, 64);
+        }
+        store_tile<BN>(taddr, p.C + m, m < p.M, n0, p.N, p.ldc, p.alpha, p.beta, 0, c_mid);
+        if (assist) {  // both halves are out of tensor memory
+          ptx::tc_fence_before();
+          ptx::named_bar_sync(4 + q, 64);
+        }
       }
       // release this accumulator stage back to the MMA warp (of the leader CTA)
       ptx::tc_fence_before();
@@ -1222,18 +1260,61 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================================================================== helper warps (TMEM lane quadrant = warp & 3)
     const int q = warp & 3;
     if (FT && p.enc_prog != nullptr) encoder_prefix(q);
-    if (p.sk_tiles > 0) {
+    if (p.sk_tiles > 0 || (p.epi_assist != 0 && BN >= 64)) {
       const uint32_t seeded_leader = (CG == 2) ? ptx::mapa(seeded_bar(0), 0) : seeded_bar(0);
       const size_t ws_slab = static_cast<size_t>(kBM) * BN;
+      const int row = q * 32 + lane;
+      const bool assist_on = p.epi_assist != 0 && BN >= 64;
+      // The upper half of the final epilogue of item `a` (same structure as the epilogue warp's lower half: the barriers of
+      // the pair must match one to one).
+      auto assist = [&](const Segment &a, int a_acc, uint32_t a_phase) {
+        if (!assist_on) return;
+        // Observe EVERY item's accumulator-complete phase, assisted or not: a parity wait is only unambiguous within one
+        // phase of the barrier, and a run of four parking / checksum items would otherwise put this warp two phases ahead.
+        ptx::mbar_wait(tfull_bar(a_acc), a_phase);
+        const bool parks = a.kind == 1 || a.kind == 3;
+        if (parks) return;
+        const TileCoord tc = decode_tile(p, a.tile);
+        if (FT && tc.is_chk) return;
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a_acc * BN;
+        const int m0_cta = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;
+        const int m = m0_cta + row;
+        if (FT && !(p.dbg_flags & 1)) {
+          if (p.inject_mode != 0) {
+            ptx::named_bar_sync(4 + q, 64);  // injected
+            ptx::tc_fence_after();
+          }
+          float s1 = 0.0f, s2 = 0.0f, sabs = 0.0f;
+          abft_row_sums<BN>(taddr, kMid, BN / 32, s1, s2, sabs);
+          ptx::st_shared_u32(xchg_base(q) + lane * 12, f2u(s1));
+          ptx::st_shared_u32(xchg_base(q) + lane * 12 + 4, f2u(s2));
+          ptx::st_shared_u32(xchg_base(q) + lane * 12 + 8, f2u(sabs));
+          ptx::named_bar_sync(4 + q, 64);  // partial sums handed over
+          ptx::named_bar_sync(4 + q, 64);  // verdict reached, corrections written to tensor memory
+          ptx::tc_fence_after();
+        }
+        store_tile<BN>(taddr, p.C + m, m < p.M, tc.n_blk * BN, p.N, p.ldc, p.alpha, p.beta, kMid, BN / 32);
+        ptx::tc_fence_before();
+        ptx::named_bar_sync(4 + q, 64);  // both halves are out of tensor memory
+      };
       int acc = 0;
+      uint32_t acc_phase = 0;
       int item_idx = -1;
+      bool have_prev = false;
+      Segment prev;
+      int prev_acc = 0;
+      uint32_t prev_phase = 0;
       SegIter it(p, unit);
       Segment sg;
       while (it.next(sg)) {
         if (FT && sg.kind == 4) continue;  // no accumulator
         ++item_idx;
         if (sg.kind == 2 || sg.kind == 3) {
-          // the accumulator stage must have been drained by this CTA's four epilogue warps (item_idx - 2 and before)
+          // Seed first (it has to be in tensor memory before this item's first UMMA, i.e. during the previous item's main
+          // loop), assist the previous item's epilogue afterwards.  The accumulator stage must have been drained by this
+          // CTA's four epilogue warps (item_idx - 2 and before).  A parked accumulator never depends on a helper warp
+          // (parking epilogues are not assisted), so waiting here for another unit's flag cannot close a cycle.
           if (item_idx >= 2) {
             const uint32_t need = 4u * static_cast<uint32_t>(item_idx - 1);
             ptx::Watchdog wd;
@@ -1253,8 +1334,15 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             else ptx::mbar_arrive(seeded_bar(acc));
           }
         }
+        if (have_prev) assist(prev, prev_acc, prev_phase);
+        prev = sg;
+        prev_acc = acc;
+        prev_phase = acc_phase;
+        have_prev = true;
         acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
       }
+      if (have_prev) assist(prev, prev_acc, prev_phase);
     }
   }
 

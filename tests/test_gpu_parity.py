@@ -189,7 +189,7 @@ def test_random_shapes_and_knobs(cuda, ft, dev, oracle, seed):
     alpha = float(rng.choice([1.0, 0.75, -2.0]))
     beta = float(rng.choice([0.0, -1.5, 1.0]))
     knobs = {"splitk": int(rng.choice([-1, 0, 2, 3])), "enc_mode": int(rng.choice([1, 2, 3])),
-             "wave_sync": int(rng.choice([0, 1])), "pdl": int(rng.choice([0, 1]))}
+             "wave_sync": int(rng.choice([0, 1])), "pdl": int(rng.choice([0, 1])), "epi_assist": int(rng.choice([0, 1]))}
     A, B = rng.standard_normal(M * K).astype(np.float32), rng.standard_normal(N * K).astype(np.float32)
     C0 = rng.standard_normal(M * N).astype(np.float32)
     model = oracle.sgemm_nt_tf32_model(M, N, K, alpha, A, B, beta, C0, "trunc")
@@ -214,6 +214,36 @@ def test_random_shapes_and_knobs(cuda, ft, dev, oracle, seed):
     finally:
         for k in knobs:
             ft.debug_set(k, -1)
+
+
+def test_epilogue_assist_is_neutral(cuda, ft, dev):
+    """The helper-assisted epilogue splits the columns of a final data-tile epilogue between the epilogue warp and the helper
+    warp of the same TMEM lane quadrant (row sums exchanged through shared memory): results bit-identical with it on and
+    off, injected faults in both column halves and on the split corrected."""
+    rng = np.random.default_rng(13)
+    M, N, K = 640, 1024, 352
+    A, B = _rand(rng, M * K), _rand(rng, N * K)
+    C0 = rng.standard_normal(M * N).astype(np.float32)
+    faults = [{"row": 5, "col": 3, "xor": 1 << 29}, {"row": 300, "col": 127, "add": 77.0}, {"row": 301, "col": 128, "add": -9.0},
+              {"row": 639, "col": 1023, "xor": 1 << 31}, {"row": 129, "col": 700, "add": 1e30}]
+    for kid, plain in ((31, 21), (16, 6), (15, 5), (12, 2), (32, 22)):
+        outs = []
+        for on in (1, 0):
+            try:
+                ft.debug_set("epi_assist", on)
+                a = _run(cuda, dev, plain, M, N, K, A, B, C0, 1.0, -1.5)
+                dev.stats()
+                b = _run(cuda, dev, kid, M, N, K, A, B, C0, 1.0, -1.5)
+                assert np.array_equal(a, b) and dev.stats()["detected"] == 0, (kid, on)
+                c = _run(cuda, dev, kid, M, N, K, A, B, C0, 1.0, -1.5, opts=ft.make_opts(faults=faults))
+                st = dev.stats()
+                assert st["detected"] == 5 and st["corrected"] == 5 and st["uncorrectable"] == 0, (kid, on, st)
+                assert np.count_nonzero(c != b) <= 5 and np.allclose(c, b, rtol=1e-4, atol=1e-3)
+                outs.append((a, c))
+            finally:
+                ft.debug_set("epi_assist", -1)
+        assert np.array_equal(outs[0][0], outs[1][0]), kid
+        assert np.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-4), kid
 
 
 def test_wave_sync_is_bitwise_neutral(cuda, ft, dev):
