@@ -100,8 +100,11 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // named barrier among a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
+// barrier.cta.sync without .aligned (bar.sync would be the aligned form): the lanes of a warp leave a spin loop (mbarrier
+// wait) at different iterations and are not guaranteed to have reconverged when they get here; __syncwarp() in front anyway.
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+  __syncwarp();
+  asm volatile("barrier.cta.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 __device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -238,6 +241,7 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   return r;
 }
 __device__ __forceinline__ void cluster_sync_all() {
+  __syncwarp();  // .aligned: the warp has to be converged (single-lane blocks precede some call sites)
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // shared::cluster address of the same shared-memory variable in CTA `rank` of the cluster
