@@ -241,10 +241,9 @@ def main():
     W = max(args.warmup, 3)
     steps = args.steps
     # 2-D block sharding of a (P*n) x (Q*n) product over the ranks: rank (p,q) owns A row-panel p, B row-panel q, C block
-    P = 1
-    while P * P * 2 <= world and world % (P * 2) == 0:
-        P *= 2
-    Q = world // P
+    # (P x Q from the package's own sharding helper: 1x1, 1x2, 2x2, 2x4)
+    from importlib import import_module
+    P, Q = import_module("ftsgemm_b200.sharding").shard_grid(world)
     if args.global_size > 0:
         G = args.global_size
         if G % (P * 256) or G % (Q * 256):
