@@ -164,7 +164,10 @@ def run_reference_arm(args):
         def one(z):
             r.ref_cpu_gemm(1.0, -1.5, O._p(X), O._p(A), n_ref, O._p(z))
 
+        t_begin = time.time()
         for i in range(warm + steps):
+            if times and time.time() - t_begin > 120.0:
+                break  # 128 instances take ~38 s per step on the pool's hosts: keep the whole arm within a few minutes
             for z in outs:
                 z.fill(0.0)
             ths = [threading.Thread(target=one, args=(z,)) for z in outs]
