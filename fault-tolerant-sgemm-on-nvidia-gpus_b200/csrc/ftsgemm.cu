@@ -433,10 +433,24 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
       // measurable difference (profiles/r01_probe22_*: 695-698 TFLOP/s at 4096^3 for all four): the pass is HBM time.
       const int grid = static_cast<int>(dbg("enc_blocks_per_sm", 4)) * h->num_sms;
       const bool small_items = dbg("enc_kr", 8) == 4;
+      const bool chain = dbg("pdl_chain", 1) != 0;
 #define FT_ENC(bn)                                                                                                          \
   if (BN == bn) {                                                                                                           \
-    if (small_items) encode_b_kernel<bn, 4><<<grid, kEncWarps * 32, 0, stream>>>(dB, N, K, N, h->d_chk, chk_ld, rounding, p.tiles_n); \
-    else encode_b_kernel<bn, 8><<<grid, kEncWarps * 32, 0, stream>>>(dB, N, K, N, h->d_chk, chk_ld, rounding, p.tiles_n);             \
+    cudaLaunchConfig_t ec;                                                                                                  \
+    memset(&ec, 0, sizeof(ec));                                                                                             \
+    ec.gridDim = dim3(grid);                                                                                                \
+    ec.blockDim = dim3(kEncWarps * 32);                                                                                     \
+    ec.stream = stream;                                                                                                     \
+    cudaLaunchAttribute ea[1];                                                                                              \
+    ea[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                          \
+    ea[0].val.programmaticStreamSerializationAllowed = 1;                                                                   \
+    ec.attrs = ea;                                                                                                          \
+    ec.numAttrs = chain ? 1 : 0;                                                                                            \
+    const float *eb = dB;                                                                                                   \
+    float *eo = h->d_chk;                                                                                                   \
+    int en = N, ek = K, el = chk_ld, er = rounding, et = p.tiles_n;                                                         \
+    if (small_items) FT_CUDA(h, cudaLaunchKernelEx(&ec, encode_b_kernel<bn, 4>, eb, en, ek, en, eo, el, er, et));           \
+    else FT_CUDA(h, cudaLaunchKernelEx(&ec, encode_b_kernel<bn, 8>, eb, en, ek, en, eo, el, er, et));                       \
   }
       FT_ENC(32) FT_ENC(64) FT_ENC(128) FT_ENC(256)
 #undef FT_ENC
@@ -599,6 +613,10 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     p.trace = h->d_trace;
     p.trace_cap = cap;
   }
+  // Programmatic dependent launch by default: the kernel's launch latency and prologue overlap the tail of whatever
+  // precedes it in the stream; unless it follows its own pre-pass (pdl_wait = 1: only the checksum items wait) every
+  // thread executes griddepcontrol.wait before the first global access.
+  if (p.pdl_wait == 0 && dbg("pdl_chain", 1) != 0) p.pdl_wait = 2;
   h->last_stream = stream;
   int lrc = FTSGEMM_ERR_UNSUPPORTED;
 #define FT_DISPATCH(bn, cg)                                                          \

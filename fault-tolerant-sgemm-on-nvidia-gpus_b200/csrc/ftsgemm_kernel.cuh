@@ -124,6 +124,9 @@ struct KernelParams {
                         //    end of their lists -- and the whole epilogue of a one-wave problem
   int pdl_wait;         // 1: launched as a programmatic dependent of the encode pre-pass -- checksum items (the only
                         //    consumers of its output) execute griddepcontrol.wait before their first load
+                        // 2: launched as a programmatic dependent of whatever precedes it in the stream: every thread
+                        //    executes griddepcontrol.wait after the prologue (barrier init, tensor-memory allocation), so
+                        //    that only the launch latency and the prologue overlap the predecessor's tail
   float tau_abs, tau_rel;
   int detect_only;
   int inject_mode;
@@ -323,10 +326,39 @@ __device__ __forceinline__ void abft_row_sums(uint32_t taddr, int c_begin, int c
 // c_mid < BN / 32: a helper warp of the same TMEM lane quadrant sums the chunks [c_mid, BN/32) and hands its three partial
 // sums over through shared memory (xchg, 3 floats per lane) at named barrier pair_bar (64 threads); the same barrier
 // also orders the injection before the helper's reads.
+// The expected checksums of one row (4 floats published by the checksum tile-columns).  The epilogue warps try to fetch
+// them BEFORE they wait for the accumulator (try_prefetch: the slab flag is polled once; when it is already raised the
+// four loads are in flight during the wait), so that a flag round trip + a load round trip (~1.5 us) leave the critical
+// path of every data-tile epilogue -- which is exposed at the end of every unit's list, and entirely in one-wave problems.
+struct ExpectedChk {
+  float e0, e1, w0, w1;
+  bool ready;
+};
+__device__ __forceinline__ void load_expected(const KernelParams &p, int m, int n_blk, ExpectedChk &x) {
+  x.e0 = x.e1 = x.w0 = x.w1 = 0.0f;
+  if (m < p.M) {
+    const float *cp = p.chk_out + static_cast<size_t>(n_blk) * kChkPerTile * p.M + m;
+    x.e0 = __ldcg(cp);
+    x.e1 = __ldcg(cp + p.M);
+    x.w0 = __ldcg(cp + 2 * static_cast<size_t>(p.M));
+    x.w1 = __ldcg(cp + 3 * static_cast<size_t>(p.M));
+  }
+}
+__device__ __forceinline__ void try_prefetch_expected(const KernelParams &p, int q, int lane, int m, int m0_cta, int n_blk,
+                                                      ExpectedChk &x) {
+  const int *flag = p.chk_flags + ((m0_cta >> 5) + q) * p.tiles_c;
+  int ok = 1;
+  if (lane == 0)
+    for (int c = 0; c < p.tiles_c; ++c) ok &= (ld_acquire(flag + c) == p.chk_epoch) ? 1 : 0;
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  x.ready = ok != 0;
+  if (x.ready) load_expected(p, m, n_blk, x);
+}
+
 template <int BN>
 __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr, int q, int lane, int m, int m0_cta,
-                                           int n0, int n_blk, int &fix_col, float &fix_val, int c_mid = BN / 32,
-                                           uint32_t xchg = 0u, int pair_bar = 0) {
+                                           int n0, int n_blk, int &fix_col, float &fix_val, ExpectedChk &xp,
+                                           int c_mid = BN / 32, uint32_t xchg = 0u, int pair_bar = 0) {
   // ---- fault injection into the TMEM accumulator (reference: ft_sgemm_huge.cuh:324-327) ----
   if (p.inject_mode == 1) {
     if ((p.selftest_row >> 5) == q && p.selftest_col < BN) {
@@ -363,8 +395,9 @@ __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr
     s2 += ptx::ld_shared_f1(xchg + lane * 12 + 4);
     sabs += ptx::ld_shared_f1(xchg + lane * 12 + 8);
   }
-  // ---- expected checksums published by the checksum tile-columns (wait for this 32-row slab's flag) ----
-  {
+  // ---- expected checksums published by the checksum tile-columns (wait for this 32-row slab's flag unless the
+  //      prefetch already found it raised) ----
+  if (!xp.ready) {
     const int *flag = p.chk_flags + ((m0_cta >> 5) + q) * p.tiles_c;
     if (lane == 0) {
       for (int c = 0; c < p.tiles_c; ++c) {
@@ -376,15 +409,9 @@ __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr
       }
     }
     __syncwarp();
+    load_expected(p, m, n_blk, xp);
   }
-  float r1 = 0.0f, r2 = 0.0f;
-  if (m < p.M) {
-    const float *cp = p.chk_out + static_cast<size_t>(n_blk) * kChkPerTile * p.M + m;
-    const float e0 = __ldcg(cp), e1 = __ldcg(cp + p.M);
-    const float w0 = __ldcg(cp + 2 * static_cast<size_t>(p.M)), w1 = __ldcg(cp + 3 * static_cast<size_t>(p.M));
-    r1 = e0 + e1;
-    r2 = w0 + w1;
-  }
+  const float r1 = xp.e0 + xp.e1, r2 = xp.w0 + xp.w1;
   const float d1 = r1 - s1, d2 = r2 - s2;
   const float thr = p.tau_abs + p.tau_rel * sabs;
   const bool flagged = !(fabsf(d1) <= thr);  // also true for NaN
@@ -750,6 +777,9 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const bool is_leader = cta_rank == 0;
   const int unit = blockIdx.x / CG;        // persistent work unit = CTA (CG=1) or CTA pair (CG=2)
 
+  // the next kernel in the stream (if it was launched as a programmatic dependent) may be scheduled as soon as this
+  // grid's CTAs retire; it synchronises with griddepcontrol.wait itself
+  ptx::pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&tmA);
     ptx::tma_prefetch_desc(&tmB);
@@ -789,6 +819,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (p.pdl_wait == 2) ptx::pdl_wait();  // everything before this line touched no global memory
 
   // ENCODE workers (encoder items, kind 4): the four helper warps and the four epilogue warps (idle until the first
   // accumulator is complete) share the ring slots of the encoder prefix, worker w8 taking slots w8, w8 + 8, ...
@@ -952,7 +983,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int nb0 = (b_is_chk ? tc.n_blk * chk_cols_per_tile(BN) : tc.n_blk * BN) +
                       static_cast<int>(cta_rank) * (n_eff / CG);  // this CTA's share of B rows
       const CUtensorMap *tmb = b_is_chk ? &tmChk : &tmB;
-      if (FT && b_is_chk && p.pdl_wait && !pdl_done) {
+      if (FT && b_is_chk && p.pdl_wait == 1 && !pdl_done) {
         ptx::pdl_wait();  // the pre-pass kernel has completed and its writes are visible
         pdl_done = true;
       }
@@ -1179,6 +1210,16 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int m0_cta = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;
       const int n0 = (FT && tc.is_chk) ? tc.n_blk * chk_cols_per_tile(BN) : tc.n_blk * BN;
       const int m = m0_cta + row;
+      ExpectedChk xp;
+      xp.ready = false;
+      if (FT && !tc.is_chk && (sg.kind == 0 || sg.kind == 2 || sg.kind == 5) && !(p.dbg_flags & 1)) {
+        // poll the slab flag (at most ~2 polls per microsecond) until it is raised or the accumulator is complete
+        try_prefetch_expected(p, q, lane, m, m0_cta, tc.n_blk, xp);
+        while (!xp.ready && !ptx::mbar_try_wait(tfull_bar(acc), acc_phase)) {
+          __nanosleep(400);
+          try_prefetch_expected(p, q, lane, m, m0_cta, tc.n_blk, xp);
+        }
+      }
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
@@ -1209,7 +1250,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int fix_col = -1;
         float fix_val = 0.0f;
         if (FT && !(p.dbg_flags & 1))
-          abft_check<BN>(p, taddr, q, lane, m, m0_cta, n0, tc.n_blk, fix_col, fix_val, c_mid, xchg_base(q), 4 + q);
+          abft_check<BN>(p, taddr, q, lane, m, m0_cta, n0, tc.n_blk, fix_col, fix_val, xp, c_mid, xchg_base(q), 4 + q);
         if (tracer) trace_put(p, unit, item_idx, 5, globaltimer_ns());
         if (FT) {
           // rare: write the recomputed elements back into the accumulator (one lane = one row at a time, like the
@@ -1367,6 +1408,7 @@ template <int BN, int KRQ>
 __global__ void __launch_bounds__(kEncWarps * 32, 2)
 encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, float *__restrict__ chk, int chk_ld, int rounding,
                 int tiles_n) {
+  ptx::pdl_wait();               // (a programmatic dependent itself: the predecessor may still be reading the old vectors)
   ptx::pdl_launch_dependents();  // the GEMM kernel may start on SMs as they drain (its checksum items wait for this grid)
   encode_b_warp<BN, KRQ>(B, N, K, ldb, chk, chk_ld, rounding, tiles_n, blockIdx.x * kEncWarps + (threadIdx.x >> 5),
                     gridDim.x * kEncWarps, threadIdx.x & 31);
