@@ -113,7 +113,7 @@ int main(int argc, char **argv) {
   random_matrix(Cm.data(), n);
   std::fill(Cm.begin(), Cm.end(), 0.0f);
 
-  float *dA, *dB, *dC, *dCref;
+  float *dA, *dB, *dC, *dCref, *dCtf = nullptr;
   CUDA_OR_DIE(cudaMalloc(&dA, count * sizeof(float)));
   CUDA_OR_DIE(cudaMalloc(&dB, count * sizeof(float)));
   CUDA_OR_DIE(cudaMalloc(&dC, count * sizeof(float)));
@@ -154,12 +154,31 @@ int main(int argc, char **argv) {
     double rel = 0;
     // verify_matrix (utils.cu:61-77) against the FP32 cuBLAS result.  Single-pass TF32 leaves a K-dependent fraction of
     // near-zero elements outside the element-wise 1 %/0.01 rule (1e-5 at K = 1024, a few 1e-4 at K = 16384; cuBLAS-TF32
-    // does too), so for the TF32 engines the verdict is the norm-wise tolerance this build is specified to: "failed" iff
-    // the Frobenius-norm relative error exceeds 1e-3; the element count goes to stderr.
+    // does too), so for the TF32 engines the verdict has two parts: (1) norm-wise, the tolerance this build is specified
+    // to -- Frobenius-norm relative error vs FP32 cuBLAS <= 1e-3 -- and (2) ELEMENT-wise with the
+    // reference's own rule against a TF32 reference with the same operand rounding (the plain tcgen05 kernel id 21, or
+    // id 6 when id 21 itself is under test; cuBLAS-TF32 rounds its operands differently and is therefore only judged
+    // norm-wise), so that a single wrong element (e.g. a mis-corrected fault) fails the run although it is invisible in
+    // the norm.  The element count vs FP32 goes to stderr.
     const int vrc = ftsgemm_verify(h, dCref, dC, M, N, &first_bad, &rel, nullptr);
     const double bad_frac = static_cast<double>(ftsgemm_verify_bad_count(h)) / (static_cast<double>(M) * N);
     const bool tf32_engine = ftsgemm_kernel_lookup(run_id, &info) == FTSGEMM_OK && (info.engine == 1 || run_id == 7 || run_id == 30);
-    const bool failed = tf32_engine ? (rel > 1e-3) : (vrc != FTSGEMM_OK);
+    long long tf_bad = 0;
+    if (tf32_engine && info.engine == 1) {
+      const int tf_ref_id = run_id == FTSGEMM_ID_SGEMM_GIANT ? FTSGEMM_ID_SGEMM_HUGE : FTSGEMM_ID_SGEMM_GIANT;
+      if (!dCtf) CUDA_OR_DIE(cudaMalloc(&dCtf, count * sizeof(float)));
+      rc = ftsgemm_run(h, tf_ref_id, M, N, K, dA, dB, dCtf, 1.0f, 0.0f, nullptr);
+      if (rc) {
+        fprintf(stderr, "[Kernel Launch Error] %s\n", ftsgemm_error_string(rc));
+        return EXIT_FAILURE;
+      }
+      long long fb2 = -1;
+      double rel2 = 0;
+      if (ftsgemm_verify(h, dCtf, dC, M, N, &fb2, &rel2, nullptr) != FTSGEMM_OK) tf_bad = ftsgemm_verify_bad_count(h);
+    }
+    const bool failed = tf32_engine ? (rel > 1e-3 || tf_bad != 0) : (vrc != FTSGEMM_OK);
+    if (tf32_engine && tf_bad != 0)
+      fprintf(stderr, "[verify] kernel %d: %lld elements outside 1%%/0.01 of the TF32 reference (plain tcgen05 kernel)\n", id, tf_bad);
     if (failed)
       printf("kernel %d failed to pass the correctness verification against NVIDIA cuBLAS. Exited.\n", id);
     if (vrc != FTSGEMM_OK && !failed)

@@ -113,9 +113,6 @@ struct ftsgemm_handle_s {
   std::map<std::array<long long, 6>, CachedPlan> plans;  // key: kernel id, M, N, K, units, forced slices
   int *d_wave_cnt = nullptr;    // wave re-synchronisation counters (cleared per launch)
   size_t wave_cnt_cap = 0;
-  int *d_enc_prog = nullptr;    // encoder items: per k-chunk progress counters (monotonic per shape)
-  int enc_prog_cap = 0, enc_prog_value = 0;
-  std::array<long long, 4> enc_prog_shape = {0, 0, 0, 0};
   int chk_epoch = 0;
   float *d_sk = nullptr;        // split-K partial tiles + flags
   size_t sk_bytes = 0;
@@ -125,6 +122,7 @@ struct ftsgemm_handle_s {
   float *d_stage[3] = {nullptr, nullptr, nullptr};  // run_host staging A, B, C
   size_t stage_bytes[3] = {0, 0, 0};
   double *d_verify = nullptr;   // {first_bad (as long long), num, den}
+  std::map<int, int> max_units;     // per kernel instantiation (BN * 8 + FT * 4 + CG): co-resident CTAs / CTA pairs
   cudaStream_t last_stream = nullptr;
   int last_cuda_error = 0;
   unsigned long long last_verify_bad = 0;
@@ -149,6 +147,28 @@ namespace {
       return FTSGEMM_ERR_CUBLAS;                           \
     }                                                      \
   } while (0)
+
+// Every entry point runs on the device the handle was created on, whatever the caller's current device is.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(ftsgemm_handle_t h) {
+    if (h && cudaGetDevice(&prev) == cudaSuccess && prev != h->device) switched = cudaSetDevice(h->device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+// The kernels' watchdog (ptx.cuh) raises a device-wide flag instead of trapping; reported once, then cleared.
+int check_abort_flag(ftsgemm_handle_t h) {
+  int flag = 0;
+  FT_CUDA(h, cudaMemcpyFromSymbol(&flag, ptx::g_abort_flag, sizeof(int)));
+  if (flag == 0) return FTSGEMM_OK;
+  flag = 0;
+  FT_CUDA(h, cudaMemcpyToSymbol(ptx::g_abort_flag, &flag, sizeof(int)));
+  return FTSGEMM_ERR_TIMEOUT;
+}
 
 int make_tmap_2d(ftsgemm_handle_t h, CUtensorMap *tm, const float *base, uint64_t inner, uint64_t outer,
                  uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer) {
@@ -189,17 +209,57 @@ int make_tmap_3d(ftsgemm_handle_t h, CUtensorMap *tm, const float *base, uint64_
   return FTSGEMM_OK;
 }
 
+// Largest grid (in work units = CTAs or CTA pairs) of this instantiation whose CTAs are all resident at once.  The
+// persistent kernel's inter-CTA waits (checksum flags, parked accumulators, wave counters) are only deadlock-free for
+// such a grid, so the planner never gets more units than this -- on a device partition (MPS active-thread percentage,
+// green context) that is fewer than multiProcessorCount / CG.  Cached per handle (= per device).
+template <int BN, bool FT, int CG>
+int query_max_units(ftsgemm_handle_t h, int *out) {
+  using Cfg = TileCfg<BN, FT, CG>;
+  const int key = BN * 8 + (FT ? 4 : 0) + CG;
+  auto it = h->max_units.find(key);
+  if (it != h->max_units.end()) {
+    *out = it->second;
+    return FTSGEMM_OK;
+  }
+  auto kern = ftsgemm_tc_kernel<BN, FT, CG>;
+  FT_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  int units = 0;
+  if (CG > 1) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(h->num_sms / CG * CG);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FT_CUDA(h, cudaOccupancyMaxActiveClusters(&units, kern, &cfg));
+  } else {
+    int per_sm = 0;
+    FT_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, Cfg::kSmemBytes));
+    units = (per_sm > 0 ? 1 : 0) * h->num_sms;  // one persistent CTA per SM
+  }
+  if (units > h->num_sms / CG) units = h->num_sms / CG;
+  h->max_units[key] = units;
+  *out = units;
+  return FTSGEMM_OK;
+}
+
 template <int BN, bool FT, int CG>
 int launch_tc(ftsgemm_handle_t h, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
               const KernelParams &p, int units, cudaStream_t stream) {
-  // p.pdl_wait: the launch directly follows the encode pre-pass in this stream and may overlap its tail
+  // p.pdl_wait: the launch may overlap the tail of its predecessor in the stream (KernelParams::pdl_wait)
   using Cfg = TileCfg<BN, FT, CG>;
   auto kern = ftsgemm_tc_kernel<BN, FT, CG>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FT_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  int resident = 0;
+  const int qrc = query_max_units<BN, FT, CG>(h, &resident);  // (also sets the shared-memory attribute, once per handle)
+  if (qrc) return qrc;
+  if (units > resident) return FTSGEMM_ERR_UNSUPPORTED;  // the plan was built for more units than can be co-resident
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(units * CG);
@@ -237,41 +297,10 @@ void chk_costs(const KernelParams &p, std::vector<double> *out) {
     out->push_back(std::max(0.58, static_cast<double>(chk_tile_width<BNv, CGv>(p, c)) / BNv));
 }
 
-// How the checksum vectors of B are produced (debug knob enc_mode; default 1).  Four variants were built and measured
-// (profiles/r01_probe12_*, r01_probe14_*, r01_trace_*); whichever way the 4*N*K bytes of B are summed it costs about the
-// same machine time, so the simplest one is the default:
-//   1  stand-alone pre-pass kernel in front of the GEMM: 10.7 us per step at 4096^3 in a loop (5.6 %), ~45 us at 8192^3
-//      (3 %); B is left in L2 for the GEMM's first wave                                                    [default]
-//   3  encoder TILES: the first data tile of every tile-column also reduces its own B stages from shared memory -- no
-//      extra HBM / L2 traffic, one launch per GEMM.  The two ENCODE workers of a k-block (one per CTA, 16 k-rows each, the
-//      other CTA's half read through distributed shared memory) need ~1.9 us per stage, and a stage is only refilled
-//      after that, so an encoder tile's main loop runs at 0.55 instead of 0.33 us per k-block (77 vs 42 us at 4096^3):
-//      695 vs 691 TFLOP/s at 4096^3, 755 vs 770 at 8192^3
-//   2  encoder ITEMS: one unit per tile-column streams B through its shared-memory ring (no UMMA) and reduces it.  The
-//      items run while every SM is fetching cold operands and get 1/148 of the HBM bandwidth each: ~1.2 tile-times per
-//      item (715 vs 709 TFLOP/s at 4096^3, 781 vs 785 at 8192^3)
-// (A fifth variant -- helper warps reading their share of B from global memory in the background of the main loops -- was
-//  3-8x slower, because a few warps per SM cannot keep enough bytes in flight, and has been removed.)
-// Modes 2 / 3 need the 3-D tensor map of B (N % 32 == 0); mode 3 also needs spare units for the checksum items.
-int encode_mode(int N, int tiles_n, int units) {
-  const long long m = dbg("enc_mode", -2);
-  const bool items_ok = N % kAtomMN == 0 && dbg("enc_rounding", 0) == 0;  // (the rounding experiment only exists in the pre-pass)
-  const bool tiles_ok = items_ok && 2 * tiles_n <= units;
-  if (m == 3) return tiles_ok ? 3 : 1;
-  if (m == 2) return items_ok ? 2 : 1;
-  return 1;
-}
-
-// raster index (among the data tiles) of tile (m_blk = 0, n_blk = t): inverse of decode_tile
-int encoder_tile_index(const KernelParams &p, int t) {
-  const int g = t / p.group_n;
-  return g * p.group_n * p.tiles_m + (t - g * p.group_n);
-}
-
-PlanInput make_plan_input(int num_sms, int CG, int BN, int K, const KernelParams &p, int enc_plan /* 0 none, 2 items, 3 tiles */) {
+PlanInput make_plan_input(int max_units, int CG, int BN, int K, const KernelParams &p) {
   PlanInput in;
   long long units = dbg("grid", 0);
-  in.units = units > 0 ? static_cast<int>(units) : num_sms / CG;
+  in.units = (units > 0 && units <= max_units) ? static_cast<int>(units) : max_units;
   in.n_chk_tiles = p.tiles_c * p.tiles_m;
   in.n_data_tiles = p.tiles_m * p.tiles_n;
   in.num_kb = (K + kBK - 1) / kBK;
@@ -295,19 +324,6 @@ PlanInput make_plan_input(int num_sms, int CG, int BN, int K, const KernelParams
   const long long lock = dbg("lockstep", -2);
   in.lockstep = lock >= 0 ? static_cast<int>(lock)
                           : (4.0 * K * (static_cast<double>(p.M) + p.N) > 96.0 * 1024 * 1024 ? 1 : 0);
-  in.chk_release = 0.0;
-  if (p.tiles_c > 0 && enc_plan == 3) {
-    // the first data tile of every tile-column encodes it; the checksum tiles follow the encoders k-chunk by k-chunk:
-    // started 0.45 tile-times in they never catch up with them (0.45 + 0.58 f >= f)
-    for (int t = 0; t < p.tiles_n; ++t) in.enc_tiles.push_back(encoder_tile_index(p, t));
-    in.enc_tile_cost = static_cast<double>(dbg("enc_tile_cost_permille", 1850)) * 1e-3;
-    in.chk_release = std::max(0.0, in.enc_tile_cost - in.chk_col_cost[0]) + 0.02;
-  } else if (p.tiles_c > 0 && enc_plan == 2) {
-    // one encoder item per tile-column of B; the checksum tiles follow them k-chunk by k-chunk
-    in.n_enc_items = p.tiles_n;
-    in.enc_cost = static_cast<double>(dbg("enc_cost_permille", 1200)) * 1e-3;
-    in.chk_release = std::max(0.0, in.enc_cost - in.chk_col_cost[0]) + 0.05;
-  }
   return in;
 }
 
@@ -366,7 +382,7 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
   p.detect_only = o.detect_only;
   p.inject_mode = ft ? o.inject_mode : 0;
   p.selftest_value = o.selftest_value;
-  p.selftest_row = o.selftest_row & (kBM - 1);
+  p.selftest_row = o.selftest_row & (kBM - 1);  // (>= 0: validated by load_opts)
   p.selftest_col = o.selftest_col % BN;
   p.n_faults = o.n_faults < 0 ? 0 : (o.n_faults > kMaxFaults ? kMaxFaults : o.n_faults);
   for (int i = 0; i < p.n_faults; ++i) {
@@ -380,8 +396,6 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
 
   CUtensorMap tmA, tmB, tmC;
   const bool allow3d = dbg("tma3d", 1) != 0;
-  bool need_encode = false;
-  int chk_ld_v = 0, enc_mode_v = 1;
   int rc;
   if (allow3d && M % kAtomMN == 0) {
     rc = make_tmap_3d(h, &tmA, dA, M, K, M, kBM / kAtomMN);
@@ -423,10 +437,7 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     p.chk_epoch = ++h->chk_epoch;
     p.dbg_flags = static_cast<int>(dbg("ft_dbg", 0)) & 1;
     const bool reuse = o.reuse_b_checksums && h->chk_for_b == dB && h->chk_n == N && h->chk_k == K && h->chk_bn == BN;
-    need_encode = !reuse;
-    chk_ld_v = chk_ld;
-    enc_mode_v = encode_mode(N, p.tiles_n, static_cast<int>(dbg("grid", 0) > 0 ? dbg("grid", 0) : h->num_sms / CG));
-    if (need_encode && enc_mode_v == 1) {
+    if (!reuse) {
       // stand-alone pre-pass in the caller's stream
       const int rounding = static_cast<int>(dbg("enc_rounding", 0));
       // grid-stride over (column block, k-row group) items.  Item size (8 / 4 KiB) and grid (2 / 4 blocks per SM) make no
@@ -455,7 +466,6 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
       FT_ENC(32) FT_ENC(64) FT_ENC(128) FT_ENC(256)
 #undef FT_ENC
       FT_CUDA(h, cudaGetLastError());
-      need_encode = false;
       // The GEMM launch below becomes a programmatic dependent of this kernel: its CTAs start on SMs as they drain, and
       // only its checksum items wait for the pre-pass to complete.  Measured: +7.8 % at 2048^3, +1.2 % at 4096^3, but
       // -1.4 % at 8192^3 (CTAs that start early fall out of k-lockstep with the others), hence the size limit.
@@ -481,11 +491,19 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     if (rc) return rc;
   }
   // ---- work plan (plan.h), cached per shape on the handle
-  const int enc_plan = (ft && need_encode && enc_mode_v >= 2) ? enc_mode_v : 0;
-  const bool encode_items = enc_plan != 0;
-  const PlanInput pin = make_plan_input(h->num_sms, CG, BN, K, p, enc_plan);
+  int max_units = 0;
+  {
+    int qrc = FTSGEMM_ERR_UNSUPPORTED;
+#define FT_QUERY(bn, cg) \
+  if (BN == bn && CG == cg) qrc = ft ? query_max_units<bn, true, cg>(h, &max_units) : query_max_units<bn, false, cg>(h, &max_units);
+    FT_QUERY(32, 1) FT_QUERY(64, 1) FT_QUERY(128, 1) FT_QUERY(256, 1) FT_QUERY(128, 2) FT_QUERY(256, 2)
+#undef FT_QUERY
+    if (qrc) return qrc;
+    if (max_units < 1) return FTSGEMM_ERR_UNSUPPORTED;  // not a single CTA (pair) of this kernel fits on the device partition
+  }
+  const PlanInput pin = make_plan_input(max_units, CG, BN, K, p);
   const std::array<long long, 6> key = {v.info.id, M, N, K, pin.units,
-                                        pin.force_slices * 16 + pin.max_slices + enc_plan * 1024 + pin.lockstep * 8192 + pin.full_search * 16384};
+                                        pin.force_slices * 16 + pin.max_slices + pin.lockstep * 8192 + pin.full_search * 16384};
   ftsgemm_handle_s::CachedPlan &cp = h->plans[key];
   if (!cp.uploaded) {
     if (h->plans.size() > 64) {  // bound the cache: drop everything but this entry
@@ -541,36 +559,6 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
       h->sk_epoch = 0;
     }
     p.sk_epoch = ++h->sk_epoch;
-  }
-  if (encode_items) {
-    // Encoder items: per launch every helper warp of every encoder unit adds 1 to each k-chunk counter; the counters
-    // are monotonic while the shape stays the same and are cleared when it changes.
-    const int n_chunks = ((K + kBK - 1) / kBK + 31) / 32;
-    int workers = 4;
-    if (BN == 32) workers = TileCfg<32, true, 1>::kEncWorkers;
-    else if (BN == 64) workers = TileCfg<64, true, 1>::kEncWorkers;
-    else if (BN == 128) workers = CG == 1 ? TileCfg<128, true, 1>::kEncWorkers : TileCfg<128, true, 2>::kEncWorkers;
-    else workers = CG == 1 ? TileCfg<256, true, 1>::kEncWorkers : TileCfg<256, true, 2>::kEncWorkers;
-    // every ENCODE worker warp of every CTA of the group reports every k-chunk once
-    const int inc = workers * CG * p.tiles_n;
-    const std::array<long long, 4> shape = {N, K, BN, CG * 8 + enc_plan};
-    if (h->d_enc_prog == nullptr || h->enc_prog_cap < n_chunks) {
-      if (h->d_enc_prog) FT_CUDA(h, cudaFree(h->d_enc_prog));
-      h->d_enc_prog = nullptr;
-      FT_CUDA(h, cudaMalloc(&h->d_enc_prog, static_cast<size_t>(n_chunks) * sizeof(int)));
-      h->enc_prog_cap = n_chunks;
-      h->enc_prog_shape = {0, 0, 0, 0};
-    }
-    if (h->enc_prog_shape != shape || h->enc_prog_value > (1 << 30) - inc) {
-      FT_CUDA(h, cudaMemsetAsync(h->d_enc_prog, 0, static_cast<size_t>(h->enc_prog_cap) * sizeof(int), stream));
-      h->enc_prog_shape = shape;
-      h->enc_prog_value = 0;
-    }
-    h->enc_prog_value += inc;
-    p.enc_prog = h->d_enc_prog;
-    p.enc_prog_target = h->enc_prog_value;
-    p.enc_out = h->d_chk;
-    p.enc_ld = chk_ld_v;
   }
   {
     // Helper-assisted final epilogues (the helper warp of each TMEM lane quadrant takes the upper half of the columns).
@@ -695,6 +683,7 @@ const char *ftsgemm_error_string(int code) {
     case FTSGEMM_ERR_NO_DEVICE: return "no sm_100 CUDA device available (libftsgemm has no CPU fallback)";
     case FTSGEMM_ERR_CUBLAS: return "cuBLAS error";
     case FTSGEMM_ERR_VERIFY: return "verification failed";
+    case FTSGEMM_ERR_TIMEOUT: return "device-side wait timed out (grid not co-resident or protocol error): the launch's result is undefined";
   }
   return "unknown error";
 }
@@ -732,10 +721,7 @@ int ftsgemm_debug_schedule(int kernel_id, int M, int N, int K, int num_sms, int 
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
   plan_tiles(M, N, v->bn, v->cg, v->info.fault_tolerant != 0, &p);
-  const long long gunits = dbg("grid", 0);
-  const int em = encode_mode(N, p.tiles_n, static_cast<int>(gunits > 0 ? gunits : num_sms / v->cg));
-  const int enc_plan = (v->info.fault_tolerant != 0 && em >= 2 && p.tiles_c > 0) ? em : 0;
-  const PlanInput pin = make_plan_input(num_sms, v->cg, v->bn, K, p, enc_plan);
+  const PlanInput pin = make_plan_input(num_sms / v->cg, v->cg, v->bn, K, p);
   const Plan plan = build_plan(pin);
   if (hdr) {
     hdr[0] = plan.units; hdr[1] = pin.n_chk_tiles + pin.n_data_tiles; hdr[2] = pin.n_chk_tiles; hdr[3] = plan.sk_tiles;
@@ -746,9 +732,7 @@ int ftsgemm_debug_schedule(int kernel_id, int M, int N, int K, int num_sms, int 
     for (int i = plan.offsets[u]; i < plan.offsets[u + 1]; ++i) {
       const PlanItem &it = plan.items[i];
       if (rows && n < cap) {
-        TileCoord tc;
-        if (it.kind == 4) { tc.is_chk = false; tc.m_blk = -1; tc.n_blk = it.tile; }
-        else tc = decode_tile(p, it.tile);
+        const TileCoord tc = decode_tile(p, it.tile);
         int *r = rows + 9 * n;
         r[0] = u; r[1] = it.tile; r[2] = tc.is_chk ? 1 : 0; r[3] = tc.m_blk; r[4] = tc.n_blk;
         r[5] = it.kb_begin; r[6] = it.kb_end; r[7] = it.kind; r[8] = it.slice;
@@ -813,6 +797,7 @@ int ftsgemm_create(ftsgemm_handle_t *out) {
 
 int ftsgemm_destroy(ftsgemm_handle_t h) {
   if (!h) return FTSGEMM_OK;
+  DeviceGuard guard(h);
   cudaDeviceSynchronize();
   if (h->cublas) cublasDestroy(h->cublas);
   cudaFree(h->d_stats);
@@ -820,7 +805,6 @@ int ftsgemm_destroy(ftsgemm_handle_t h) {
   cudaFree(h->d_chk_out);
   cudaFree(h->d_sk);
   cudaFree(h->d_trace);
-  cudaFree(h->d_enc_prog);
   cudaFree(h->d_wave_cnt);
   for (auto &kv : h->plans) {
     cudaFree(kv.second.d_items);
@@ -836,6 +820,20 @@ int ftsgemm_destroy(ftsgemm_handle_t h) {
 
 int ftsgemm_last_cuda_error(ftsgemm_handle_t h) { return h ? h->last_cuda_error : 0; }
 
+// Copies the caller's options over the defaults.  struct_size is the caller's sizeof(ftsgemm_opts): anything smaller
+// than the first published layout (e.g. 0 from a zero-initialised struct) is an error, not "all defaults".
+static int load_opts(const ftsgemm_opts *opts, ftsgemm_opts *o) {
+  ftsgemm_default_opts(o);
+  if (!opts) return FTSGEMM_OK;
+  if (opts->struct_size < FTSGEMM_OPTS_V1_SIZE) return FTSGEMM_ERR_INVALID_ARG;
+  memcpy(o, opts, opts->struct_size < sizeof(*o) ? opts->struct_size : sizeof(*o));
+  o->struct_size = sizeof(*o);
+  if (o->inject_mode < 0 || o->inject_mode > 2 || o->selftest_row < 0 || o->selftest_col < 0 || o->n_faults < 0 ||
+      o->n_faults > FTSGEMM_MAX_FAULTS)
+    return FTSGEMM_ERR_INVALID_ARG;
+  return FTSGEMM_OK;
+}
+
 int ftsgemm_run(ftsgemm_handle_t h, int kernel_id, int M, int N, int K, const float *dA, const float *dB, float *dC,
                 float alpha, float beta, const ftsgemm_opts *opts) {
   if (!h) return FTSGEMM_ERR_NO_DEVICE;
@@ -843,8 +841,9 @@ int ftsgemm_run(ftsgemm_handle_t h, int kernel_id, int M, int N, int K, const fl
   const Variant *v = find_variant(kernel_id);
   if (!v) return FTSGEMM_ERR_INVALID_ARG;
   ftsgemm_opts o;
-  ftsgemm_default_opts(&o);
-  if (opts) memcpy(&o, opts, opts->struct_size < sizeof(o) ? opts->struct_size : sizeof(o));
+  const int orc = load_opts(opts, &o);
+  if (orc) return orc;
+  DeviceGuard guard(h);
   cudaStream_t stream = static_cast<cudaStream_t>(o.stream);
   switch (v->info.engine) {
     case 0: return run_cublas(h, v->info.id == 7, M, N, K, dA, dB, dC, alpha, beta, stream);
@@ -857,7 +856,10 @@ int ftsgemm_run(ftsgemm_handle_t h, int kernel_id, int M, int N, int K, const fl
 int ftsgemm_get_stats(ftsgemm_handle_t h, ftsgemm_stats *out) {
   if (!h) return FTSGEMM_ERR_NO_DEVICE;
   if (!out) return FTSGEMM_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   FT_CUDA(h, cudaStreamSynchronize(h->last_stream));
+  const int arc = check_abort_flag(h);
+  if (arc) return arc;
   DeviceStats ds;
   FT_CUDA(h, cudaMemcpy(&ds, h->d_stats, sizeof(ds), cudaMemcpyDeviceToHost));
   FT_CUDA(h, cudaMemset(h->d_stats, 0, sizeof(DeviceStats)));
@@ -895,27 +897,32 @@ int ftsgemm_run_host(ftsgemm_handle_t h, int kernel_id, int M, int N, int K, con
       FT_CUDA(h, cudaMalloc(&h->d_stage[i], bytes[i]));
       h->stage_bytes[i] = bytes[i];
     }
-  cudaStream_t stream = opts ? static_cast<cudaStream_t>(opts->stream) : nullptr;
+  ftsgemm_opts o;
+  const int orc = load_opts(opts, &o);
+  if (orc) return orc;
+  DeviceGuard guard(h);
+  cudaStream_t stream = static_cast<cudaStream_t>(o.stream);
   FT_CUDA(h, cudaMemcpyAsync(h->d_stage[0], hA, bytes[0], cudaMemcpyHostToDevice, stream));
   FT_CUDA(h, cudaMemcpyAsync(h->d_stage[1], hB, bytes[1], cudaMemcpyHostToDevice, stream));
   if (beta != 0.0f) FT_CUDA(h, cudaMemcpyAsync(h->d_stage[2], hC, bytes[2], cudaMemcpyHostToDevice, stream));
-  ftsgemm_opts o;
-  ftsgemm_default_opts(&o);
-  if (opts) memcpy(&o, opts, opts->struct_size < sizeof(o) ? opts->struct_size : sizeof(o));
   o.reuse_b_checksums = 0;  // the staging buffer content changed
   int rc = ftsgemm_run(h, kernel_id, M, N, K, h->d_stage[0], h->d_stage[1], h->d_stage[2], alpha, beta, &o);
   if (rc) return rc;
   FT_CUDA(h, cudaMemcpyAsync(hC, h->d_stage[2], bytes[2], cudaMemcpyDeviceToHost, stream));
   FT_CUDA(h, cudaStreamSynchronize(stream));
-  return FTSGEMM_OK;
+  return check_abort_flag(h);
 }
 
 int ftsgemm_baseline(ftsgemm_handle_t h, int M, int N, int K, const float *dA, const float *dB, float *dC,
                      float alpha, float beta, int math_mode, const ftsgemm_opts *opts, float *residual_out) {
   if (!h) return FTSGEMM_ERR_NO_DEVICE;
   if (!dA || !dB || !dC || M <= 0 || N <= 0 || K <= 0) return FTSGEMM_ERR_INVALID_ARG;
-  cudaStream_t stream = opts ? static_cast<cudaStream_t>(opts->stream) : nullptr;
-  const bool host_sync = opts ? opts->baseline_host_sync != 0 : true;
+  ftsgemm_opts o;
+  const int orc = load_opts(opts, &o);
+  if (orc) return orc;
+  DeviceGuard guard(h);
+  cudaStream_t stream = static_cast<cudaStream_t>(o.stream);
+  const bool host_sync = o.baseline_host_sync != 0;
   const int mx = M > N ? M : N;
   // aux layout: ones[mx] | c_row[M] | c_col[N] | a_col[256] | b_row[256] | acol_x_b[N] | brow_x_a[M] | res[2] | consts[3]
   const size_t need = static_cast<size_t>(mx) + M + N + 256 + 256 + N + M + 2 + 3;
@@ -976,6 +983,7 @@ int ftsgemm_verify(ftsgemm_handle_t h, const float *d_ref, const float *d_x, int
                    double *rel_fro, void *stream_v) {
   if (!h) return FTSGEMM_ERR_NO_DEVICE;
   if (!d_ref || !d_x || M <= 0 || N <= 0) return FTSGEMM_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   unsigned long long init[4];
   init[0] = ~0ull;

@@ -17,12 +17,11 @@
 //   warp 2   TMEM allocator
 //   warps 4-7 epilogue      : tcgen05.ld (lane = row), per-row ABFT detect / locate / correct, C = alpha*acc + beta*C
 //   warps 8-11 helpers      : (a) seeding tensor memory with the parked accumulator of the previous K-piece of a cut
-//                             tile (plan.h), (b) together with the epilogue warps, the ENCODE workers of encoder
-//                             items / tiles (optional in-kernel encode: they reduce B stages from shared memory)
+//                             tile (plan.h), (b) the upper half of the columns of every final data-tile epilogue
 //
 // ABFT scheme.  With b~ = the TF32 value the tensor core actually consumes and J_t the columns
 // of N-tile t:
-//   encode    (pre-pass encode_b_kernel, or the ENCODE workers of this kernel; reference ENCODE ft_sgemm_huge.cuh:150-168)
+//   encode    (pre-pass encode_b_kernel; reference ENCODE ft_sgemm_huge.cuh:150-168)
 //             e_t[k] = sum_{n in J_t} b~[n,k]      w_t[k] = sum_{n in J_t} (n-n0+1) b~[n,k]     (2-way TF32 split each)
 //   checksum GEMM (reference CHECKSUM-GEMV :171-213): the 4 checksum vectors of every N-tile are appended to B as extra
 //             "rows", i.e. the SAME kernel computes extra tile-columns  R = A * [e_t, w_t]^T  first (FP32 accumulate in
@@ -83,9 +82,7 @@ struct KernelParams {
   int dbg_flags;        // experiments only: bit 0 = skip the epilogue ABFT check of data tiles (timing breakdowns)
   // Work plan (built on the host, plan.h): unit u executes items plan[plan_off[u] .. plan_off[u+1]) in order.
   //   item.x = tile (decode order: checksum tiles first), item.y = kb_begin | kb_end << 16,
-  //   item.z = kind (0 whole tile, 1 first piece, 3 middle piece, 2 last piece of a cut tile, 4 encoder item:
-  //            tile = tile-column of B, no accumulator, 5 encoder tile: a whole data tile whose B stages are also
-  //            reduced to the checksum vectors of its tile-column) | piece << 8,
+  //   item.z = kind (0 whole tile, 1 first piece, 3 middle piece, 2 last piece of a cut tile) | piece << 8,
   //   item.w = index among the cut tiles
   // The last sk_tiles data tiles are cut along K into up to sk_slices pieces so that the list scheduler can level the
   // units' finishing times.  Piece p parks its raw accumulator; piece p+1 loads it into tensor memory BEFORE its first
@@ -104,16 +101,6 @@ struct KernelParams {
   float *chk_out;       // M x n_chk_cols, column-major (ld = M): expected checksums r1/r2 (hi, lo each)
   int *chk_flags;       // [slab * tiles_c + c] = chk_epoch once checksum tile-column c of that 32-row slab is published
   int chk_epoch;
-  // in-kernel encode (encoder items / tiles): the ENCODE workers write enc_out[k][enc_ld] (= the checksum operand the
-  // tmChk tensor map reads)
-  float *enc_out;
-  int enc_ld;
-  // encoder items (kind 4, always a prefix of a unit's list): the unit streams B[tile-column] through the shared-memory
-  // ring and its helper warps write the checksum vectors; every helper warp adds 1 to enc_prog[c] when its share of the
-  // k-blocks [32c, 32c+32) of the tile-column is done, checksum items wait for enc_prog[c] >= enc_prog_target before
-  // k-block 32c
-  int *enc_prog;
-  int enc_prog_target;
   // wave re-synchronisation (large problems): the leader producers form a barrier at every whole-tile boundary, so that
   // the units keep streaming the same k range of the A / B panels they share (without it the start times drift apart by
   // ~2 us per wave and the tile time grows 17 % over the 56 waves of 16384^3, profiles/r01_trace_*_16384*)
@@ -167,10 +154,6 @@ struct TileCfg {
   static constexpr int kStagesFit = kMaxSmem / kStageBytes;
   static constexpr int kStages = kStagesFit > FTSGEMM_MAX_STAGES ? FTSGEMM_MAX_STAGES : kStagesFit;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kBarBytes;
-  // ENCODE workers of an encoder item (helper warps first, then epilogue warps): each owns every kEncWorkers-th ring slot.
-  // A worker's parity wait on a stage is only unambiguous if its previous slot is not older than the stage's previous
-  // use, i.e. kEncWorkers <= kStages (8 workers on a 7-stage ring read unfilled stages: measured as a hang).
-  static constexpr int kEncWorkers = kStages < 8 ? kStages : 8;
 };
 
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
@@ -232,7 +215,7 @@ __host__ __device__ __forceinline__ int chk_tile_width(const KernelParams &p, in
 // ------------------------------------------------------------------------------------------------------------
 struct Segment {
   int tile, kb_begin, kb_end;
-  int kind;   // 0 whole tile, 1 first piece, 3 middle piece, 2 last piece, 4 encoder item, 5 encoder tile
+  int kind;   // 0 whole tile, 1 first piece, 3 middle piece, 2 last piece
   int slice;
   int split_idx;
 };
@@ -404,7 +387,7 @@ __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr
         ptx::Watchdog wd;
         while (ld_acquire(flag + c) != p.chk_epoch) {
           __nanosleep(64);
-          wd.tick();
+          if (wd.tick()) break;
         }
       }
     }
@@ -552,7 +535,7 @@ __device__ __forceinline__ void sk_seed(const KernelParams &p, uint32_t taddr, c
     ptx::Watchdog wd;
     while (ld_acquire(flag) != p.sk_epoch) {
       __nanosleep(64);
-      wd.tick();
+      if (wd.tick()) break;
     }
   }
   __syncwarp();
@@ -677,66 +660,6 @@ __device__ __forceinline__ void encode_b_warp(const float *__restrict__ B, int N
   }
 }
 
-// ENCODE from shared memory (encoder items).  One ring stage holds B[n0 .. n0+BN) x 32 k-rows exactly as the UMMA
-// operand layout has it: [atom = 32 n][k][32 floats], 128-byte rows whose four 32-byte granules are XOR-ed with (k & 3)
-// (SWIZZLE_128B with 32-byte atoms).  One call reduces k-rows 8g .. 8g+7 of a stage: every lane sums float4 pieces of
-// a row, the 32-lane totals are formed by the transposing butterfly, and lane 2i writes the (hi, lo) TF32 pair of value
-// i (e and w of 8 rows) to the checksum operand.  A helper warp owns whole stages (every 4th slot of the ring), so the
-// four warps work on four stages at once and nothing but the stage's own barriers synchronises them.
-// LOCAL_ATOMS = atoms of the row held by this CTA starting at local_base (all BN/32 for an encoder item; BN/32/CG for
-// an encoder tile of a CTA pair, whose other half sits in the peer CTA's stage and is read through distributed shared
-// memory at peer_base).  One call reduces k-rows 16h .. 16h+15 of the stage.
-//
-// Instruction budget: an ENCODE worker has to finish a 32 KiB stage in ~2.3 us (7 workers, one k-block per 0.33 us of
-// main loop); the first version (8 rows per call, FP64 butterfly) needed 2.7 us from local and 5.5 us with the
-// distributed-shared-memory half (device timeline, worker 0: 104 us of work for 19 k-blocks) and tripled the main loop
-// of its tile.  Per float4: 4 mask operations (the truncation the tensor core applies), s = sum of the four,
-// t = b1 + 2 b2 + 3 b3, e += s, w += w0 * s + t; the lane partials (8 TF32 values, exact in FP32) of 16 rows x (e, w)
-// are reduced over the 32 lanes by one FP32 transposing butterfly (31 exchange steps, <= 5 roundings of 2^-24 per total:
-// far below the 2^-22 the (hi, lo) TF32 pair keeps) and every lane writes one pair.
-template <int BN, int LOCAL_ATOMS>
-__device__ __forceinline__ void encode_stage_rows(uint32_t local_base, uint32_t peer_base, int first_atom, int h, int lane,
-                                                  int kb, int K, int t, float *__restrict__ chk, int chk_ld) {
-  // atoms [first_atom, first_atom + LOCAL_ATOMS) of the row are at local_base, the others at peer_base (the other CTA)
-  const int peer_first = first_atom == 0 ? LOCAL_ATOMS : 0;
-  float v[32];
-#pragma unroll
-  for (int u = 0; u < 16; ++u) {
-    const int kr = h * 16 + u;
-    float e = 0.0f, w = 0.0f;
-#pragma unroll
-    for (int idx0 = 0; idx0 < BN / 4; idx0 += 32) {
-      const int idx = idx0 + lane;  // float4 index within the k-row (over all atoms)
-      if (BN / 4 >= 32 || idx < BN / 4) {
-        const int atom = idx >> 3, c4 = idx & 7;
-        float4 x;
-        if (LOCAL_ATOMS >= BN / 32 || (atom >= first_atom && atom < first_atom + LOCAL_ATOMS))
-          x = ptx::ld_shared_f4(local_base + (atom - first_atom) * (kBK * 128) + kr * 128 + c4 * 16);
-        else
-          x = ptx::ld_dsmem_f4(peer_base + (atom - peer_first) * (kBK * 128) + kr * 128 + c4 * 16);
-        const int granule = (c4 >> 1) ^ (kr & 3);
-        const float w0 = static_cast<float>(atom * 32 + granule * 8 + (c4 & 1) * 4 + 1);
-        const float b0 = u2f(f2u(x.x) & 0xFFFFE000u), b1 = u2f(f2u(x.y) & 0xFFFFE000u),
-                    b2 = u2f(f2u(x.z) & 0xFFFFE000u), b3 = u2f(f2u(x.w) & 0xFFFFE000u);
-        const float s4 = (b0 + b1) + (b2 + b3);
-        const float t4 = fmaf(3.0f, b3, fmaf(2.0f, b2, b1));
-        e += s4;
-        w += fmaf(w0, s4, t4);
-      }
-    }
-    v[2 * u] = e;
-    v[2 * u + 1] = w;
-  }
-  int idx = 0;
-  TransposeReduce<float, 32, 16>::run(v, lane, idx);
-  const int k = kb * kBK + h * 16 + (idx >> 1);
-  if (k < K) {
-    const float hi = u2f(f2u(v[0]) & 0xFFFFE000u);
-    const float lo = u2f(f2u(v[0] - hi) & 0xFFFFE000u);  // v - hi is exact
-    *reinterpret_cast<float2 *>(chk + static_cast<size_t>(k) * chk_ld + t * kChkPerTile + (idx & 1) * 2) = make_float2(hi, lo);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------------------
 // The kernel.
 // ------------------------------------------------------------------------------------------------------------
@@ -758,14 +681,10 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   auto seeded_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 4 + a); };  // leader: TMEM stage a holds the seed
-  // peer CTA only: the leader has consumed its last encoder slot (see the producer)
-  const uint32_t pair_bar = bar_base + 8u * (2 * kStages + 6);
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 7);
   // number of (epilogue warp, item) pairs this CTA has finished: the helper warps' view of which accumulator stages
   // are drained (a counter, not an mbarrier: the helpers may be many items behind while they encode B)
   const uint32_t epi_count = tmem_slot + 8u;
-  // peer CTA: worker w's "the leader saw k-block j complete" hand-off (the pair's TMA bytes are credited to the leader)
-  auto pfull_bar = [&](int w) { return epi_count + 8u + 8u * w; };
   auto xchg_base = [&](int q) { return bar_base + 512u + static_cast<uint32_t>(q) * (32u * 12u); };
   constexpr int kMid = BN / 64;  // chunks [0, kMid) to the epilogue warp, [kMid, BN/32) to its helper (BN >= 64)
   volatile uint32_t *tmem_slot_ptr =
@@ -788,10 +707,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(full_bar(s), CG);   // leader's own arrive.expect_tx (+ the peer's remote arrive)
-      // one tcgen05.commit (multicast to both CTAs when CG = 2); with ABFT two more arrivals say that nobody else still
-      // reads the stage: the two ENCODE workers of an encoder tile's k-block (one per CTA; a CTA pair's workers read both
-      // halves), or the producer itself right after filling it
-      ptx::mbar_init(empty_bar(s), FT ? 3 : 1);
+      ptx::mbar_init(empty_bar(s), 1);   // one tcgen05.commit (multicast to both CTAs when CG = 2)
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
@@ -799,9 +715,6 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ptx::mbar_init(seeded_bar(a), 4 * CG);  // one arrive per helper warp of every CTA in the group
     }
     ptx::st_shared_u32(epi_count, 0u);
-    ptx::mbar_init(pair_bar, 1);
-    if (FT)
-      for (int w = 0; w < Cfg::kEncWorkers; ++w) ptx::mbar_init(pfull_bar(w), 1);
     ptx::fence_mbar_init();
   }
   if (CG == 2) ptx::cluster_sync_all();  // peer barriers must be initialised before any remote arrive / 2-CTA alloc
@@ -821,99 +734,6 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_slot_ptr;
   if (p.pdl_wait == 2) ptx::pdl_wait();  // everything before this line touched no global memory
 
-  // ENCODE workers (encoder items, kind 4): the four helper warps and the four epilogue warps (idle until the first
-  // accumulator is complete) share the ring slots of the encoder prefix, worker w8 taking slots w8, w8 + 8, ...
-  constexpr int kEncWorkers = Cfg::kEncWorkers;
-  auto encoder_prefix = [&](int w8) {
-    if (w8 >= kEncWorkers) return;
-    int base = 0;   // ring slots consumed by earlier prefix items
-    int n_items = 0;  // encoder ITEMS (kind 4) seen: the UMMA warp has to be released after them
-    int tile_kblocks = 0;  // encoder-TILE k-blocks this worker has taken (phase of its pfull barrier in the peer CTA)
-    const bool tr_on = p.trace != nullptr && is_leader && w8 == 0;  // timeline: worker 0's wait / work split
-    unsigned long long tr_wait = 0, tr_comp = 0, tr_n = 0;
-    SegIter it(p, unit);
-    Segment sg;
-    if (p.trace != nullptr && is_leader && w8 == 0 && lane == 0) trace_put(p, unit, p.trace_cap - 1, 1, globaltimer_ns());
-    while (it.next(sg) && sg.kind >= 4) {
-      const bool is_tile = sg.kind == 5;
-      if (!is_tile) ++n_items;
-      // encoder item: every CTA of the group streams its own k-blocks (j*CG + rank) of the whole tile-column;
-      // encoder tile: an ordinary main loop runs; the LEADER's workers reduce both halves of every B stage
-      const int slots = is_tile ? sg.kb_end : (sg.kb_end + CG - 1) / CG;
-      const int n_chunks = (sg.kb_end + 31) >> 5;
-      const int col = is_tile ? decode_tile(p, sg.tile).n_blk : sg.tile;
-      int signalled = 0;  // chunks this warp has reported
-      {
-        for (int j = w8; j < slots; j += kEncWorkers) {
-          const int abs_slot = base + j;
-          const int stage = abs_slot % kStages;
-          const unsigned long long tw0 = tr_on ? globaltimer_ns() : 0ull;
-          if (!is_tile || is_leader) {
-            ptx::mbar_wait(full_bar(stage), static_cast<uint32_t>(abs_slot / kStages) & 1u);
-            // encoder tile of a CTA pair: both CTAs' bytes are credited to the leader's barrier, so the leader's worker
-            // tells its partner in the peer CTA (cluster-scope release: the partner reads data, not just a flag)
-            if (is_tile && CG == 2 && lane == 0) ptx::mbar_arrive_release_cluster(ptx::mapa(pfull_bar(w8), 1));
-          } else {
-            ptx::mbar_wait_acquire_cluster(pfull_bar(w8), static_cast<uint32_t>(tile_kblocks) & 1u);
-          }
-          ++tile_kblocks;
-          const unsigned long long tw1 = tr_on ? globaltimer_ns() : 0ull;
-          const uint32_t st = smem_base + stage * Cfg::kStageBytes;
-          const int kb = is_tile ? j : j * CG + static_cast<int>(cta_rank);
-          if (is_tile) {
-            // the pair's two workers of this k-block take 16 k-rows each, over BOTH halves of the tile-column
-            const uint32_t other = (CG == 2) ? ptx::mapa(st + Cfg::kABytes, cta_rank ^ 1u) : 0u;
-            const int first_atom = static_cast<int>(cta_rank) * (Cfg::kBNLocal / kAtomMN);
-#pragma unroll 1
-            for (int g = (CG == 2 ? static_cast<int>(cta_rank) : 0); g < (CG == 2 ? static_cast<int>(cta_rank) + 1 : kBK / 16); ++g)
-              encode_stage_rows<BN, Cfg::kBNLocal / kAtomMN>(st + Cfg::kABytes, other, first_atom, g, lane, kb, p.K, col,
-                                                            p.enc_out, p.enc_ld);
-          } else {
-#pragma unroll 1
-            for (int g = 0; g < kBK / 16; ++g)
-              encode_stage_rows<BN, BN / kAtomMN>(st, 0u, 0, g, lane, kb, p.K, col, p.enc_out, p.enc_ld);
-          }
-          __syncwarp();  // every lane has read the stage
-          if (lane == 0) {
-            ptx::mbar_arrive(empty_bar(stage));
-            if (is_tile) {
-              if (CG == 2) ptx::mbar_arrive_cluster(ptx::mapa(empty_bar(stage), cta_rank ^ 1u));  // the other half too
-              else ptx::mbar_arrive(empty_bar(stage));  // (a single CTA: this worker was both readers)
-            }
-          }
-          if (tr_on) {
-            tr_wait += tw1 - tw0;
-            tr_comp += globaltimer_ns() - tw1;
-            ++tr_n;
-          }
-          // report k-chunk c (32 k-blocks) once this warp's last slot of it is written
-          const int c = is_tile ? (j >> 5) : ((j * CG) >> 5);
-          const int jn = j + kEncWorkers;
-          if (jn >= slots || (is_tile ? (jn >> 5) : ((jn * CG) >> 5)) != c) {
-            __threadfence();
-            __syncwarp();
-            if (lane == 0)
-              for (int cc = signalled; cc <= c; ++cc) atomicAdd(p.enc_prog + cc, 1);  // (chunks without a slot of this warp too)
-            signalled = c + 1;
-          }
-        }
-        if (lane == 0)
-          for (int c = signalled; c < n_chunks; ++c) atomicAdd(p.enc_prog + c, 1);  // short tail: chunks without a slot
-      }
-      base += slots;
-      if (p.trace != nullptr && is_leader && w8 == 0 && lane == 0) {
-        trace_put(p, unit, p.trace_cap - 1, 0, globaltimer_ns());
-        trace_put(p, unit, p.trace_cap - 1, 2, tr_wait);
-        trace_put(p, unit, p.trace_cap - 1, 3, tr_comp);
-        trace_put(p, unit, p.trace_cap - 1, 4 + 1, tr_n);
-      }
-    }
-    if (n_items > 0 && is_leader) {
-      ptx::named_bar_sync(2, 32 * (kEncWorkers + 1));  // workers + the UMMA warp: releases the UMMA warp (see there) ...
-      if (CG == 2 && w8 == 0 && lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(pair_bar, 1));  // ... and the peer's producer
-    }
-  };
-
   if (warp == 0) {
     // ===================================================================== TMA producer (every CTA)
     // warp-uniform loop, one elected lane issues the TMA instructions (see ptx::elect_one)
@@ -922,50 +742,13 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     SegIter it(p, unit);
     Segment sg;
     int item_idx = -1;
-    bool enc_prefix = false;
     bool pdl_done = false;
     int whole_ord = 0;  // whole data tiles this unit has loaded (wave index)
     while (it.next(sg)) {
       ++item_idx;
-      if (FT && sg.kind == 4) {
-        // encoder item: this CTA streams k-blocks j*CG + rank of tile-column sg.tile of B through the ring (whole BN
-        // rows per stage, no A, no UMMA); its helper warps consume the stages.  Every CTA of the group takes the same
-        // number of slots (a slot past the end of K is zero-filled by TMA), so the rings stay in step.
-        const int b_atom0 = sg.tile * (BN / kAtomMN);
-        const int slots = (sg.kb_end + CG - 1) / CG;
-        for (int j = 0; j < slots; ++j) {
-          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sA = smem_base + stage * Cfg::kStageBytes;
-          const int k0 = (j * CG + static_cast<int>(cta_rank)) * kBK;
-          if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(full_bar(stage), static_cast<uint32_t>(CG * Cfg::kBBytes));
-            if (CG == 2) ptx::mbar_arrive(full_bar(stage));  // the barrier counts CG arrivals (normally the peer's)
-#pragma unroll
-            for (int i = 0; i < CG; ++i)
-              ptx::tma_load_3d(sA + i * Cfg::kBBytes, &tmB, full_bar(stage), 0, k0, b_atom0 + i * (Cfg::kBNLocal / kAtomMN));
-            ptx::mbar_arrive_cnt(empty_bar(stage), 2);  // (the worker's arrival stands in for the tcgen05.commit)
-          }
-          __syncwarp();
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1u;
-          }
-        }
-        enc_prefix = true;
-        continue;
-      }
-      if (FT && CG == 2 && enc_prefix && !is_leader) {
-        // In ordinary items this CTA's loads are credited to the LEADER's full barriers.  During the encoder slots both
-        // CTAs run their own barriers at their own pace, so the peer must not touch the leader's barriers before the
-        // leader's helpers have consumed the leader's last encoder slot (measured: without this the pair desynchronised
-        // at K = 8192).
-        ptx::mbar_wait(pair_bar, 0u);
-        enc_prefix = false;
-      }
       const TileCoord tc = decode_tile(p, sg.tile);
       const int m0 = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;        // this CTA's 128 rows of A
       const bool b_is_chk = FT && tc.is_chk;
-      const bool readers = FT && sg.kind == 5;  // encoder tile: the ENCODE workers release the stages
       const bool wave_item = p.wave_cnt != nullptr && sg.kind == 0 && !b_is_chk && is_leader;
       if (wave_item && whole_ord > 0) {
         // all units have finished loading their previous whole tile: start this one together
@@ -974,7 +757,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int need = __ldg(p.wave_target + whole_ord - 1);
           while (ld_acquire(p.wave_cnt + whole_ord - 1) < need) {
             __nanosleep(32);
-            wd.tick();
+            if (wd.tick()) break;
           }
         }
         __syncwarp();
@@ -998,18 +781,6 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t stage_tx = b_is_chk ? static_cast<uint32_t>(Cfg::kABytes + p.chk_box_bytes)
                                            : static_cast<uint32_t>(Cfg::kStageBytes);
         for (int kb = sg.kb_begin; kb < sg.kb_end; ++kb) {
-          if (FT && b_is_chk && p.enc_prog != nullptr && (kb & 31) == 0) {
-            // the checksum vectors of k-blocks [kb, kb + 32) come from the encoder items running on other units
-            if (lane == 0) {
-              ptx::Watchdog wd;
-              while (ld_acquire(p.enc_prog + (kb >> 5)) - p.enc_prog_target < 0) {
-                __nanosleep(64);
-                wd.tick();
-              }
-            }
-            __syncwarp();
-            ptx::fence_proxy_async();  // generic-proxy writes (st.global) -> async-proxy reads (TMA)
-          }
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sA = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sB = sA + Cfg::kABytes;
@@ -1026,7 +797,6 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               ptx::tma_load_3d(sA, &tmA, full_bar(stage), 0, k0, a_atom);
               ptx::tma_load_3d(sB, tmb_const, full_bar(stage), 0, k0, b_atom);
             }
-            if (FT && !readers) ptx::mbar_arrive_cnt(empty_bar(stage), 2);  // nobody but the UMMA reads this stage
           }
           __syncwarp();
           if (++stage == kStages) {
@@ -1040,17 +810,6 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         else fast_loop(&tmB);
       } else {
         for (int kb = sg.kb_begin; kb < sg.kb_end; ++kb) {
-          if (FT && b_is_chk && p.enc_prog != nullptr && (kb & 31) == 0) {
-            if (lane == 0) {
-              ptx::Watchdog wd;
-              while (ld_acquire(p.enc_prog + (kb >> 5)) - p.enc_prog_target < 0) {
-                __nanosleep(64);
-                wd.tick();
-              }
-            }
-            __syncwarp();
-            ptx::fence_proxy_async();
-          }
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sA = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sB = sA + Cfg::kABytes;
@@ -1085,7 +844,6 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               else ptx::tma_load_2d(sB + i * (kBK * 128), tmb, bar, nb0 + i * kAtomMN, k0);
             }
           }
-          if (FT && !readers) ptx::mbar_arrive_cnt(empty_bar(stage), 2);
           }
           __syncwarp();
           if (++stage == kStages) {
@@ -1113,25 +871,11 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t seed_phase = 0;  // bit a: parity of seeded_bar(a)
-    bool enc_pending = false;
     SegIter it(p, unit);
     Segment sg;
     int item_idx = -1;
     while (it.next(sg)) {
       ++item_idx;
-      if (FT && sg.kind == 4) {  // encoder item: no UMMA, but the ring moved on by the same number of slots
-        const int adv = stage + (sg.kb_end + CG - 1) / CG;
-        if ((adv / kStages) & 1) phase ^= 1u;
-        stage = adv % kStages;
-        enc_pending = true;
-        continue;
-      }
-      if (FT && enc_pending) {
-        // A parity wait is only unambiguous within one phase of the barrier: this warp took no part in the encoder
-        // slots, so it must not look at a full barrier before the helper warps have consumed the last of them.
-        ptx::named_bar_sync(2, 32 * (Cfg::kEncWorkers + 1));
-        enc_pending = false;
-      }
       uint32_t idesc_t = idesc;
       if (FT) {
         const TileCoord tc = decode_tile(p, sg.tile);
@@ -1189,7 +933,6 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         acc_phase ^= 1u;
       }
     }
-    if (FT && enc_pending) ptx::named_bar_sync(2, 32 * (Cfg::kEncWorkers + 1));  // a unit with encoder items only
   } else if (warp >= 4 && warp < 8) {
     // ===================================================================== epilogue (4 warps per CTA, lane = row)
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
@@ -1202,17 +945,15 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const size_t ws_slab = static_cast<size_t>(kBM) * BN;  // floats per (unit, CTA) partial tile
     int item_idx = -1;
     const bool tracer = p.trace != nullptr && is_leader && q == 0 && lane == 0;
-    if (FT && p.enc_prog != nullptr) encoder_prefix(4 + q);
     while (it.next(sg)) {
       ++item_idx;
-      if (FT && sg.kind == 4) continue;  // encoder items have no accumulator
       const TileCoord tc = decode_tile(p, sg.tile);
       const int m0_cta = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;
       const int n0 = (FT && tc.is_chk) ? tc.n_blk * chk_cols_per_tile(BN) : tc.n_blk * BN;
       const int m = m0_cta + row;
       ExpectedChk xp;
       xp.ready = false;
-      if (FT && !tc.is_chk && (sg.kind == 0 || sg.kind == 2 || sg.kind == 5) && !(p.dbg_flags & 1)) {
+      if (FT && !tc.is_chk && (sg.kind == 0 || sg.kind == 2) && !(p.dbg_flags & 1)) {
         // poll the slab flag (at most ~2 polls per microsecond) until it is raised or the accumulator is complete
         try_prefetch_expected(p, q, lane, m, m0_cta, tc.n_blk, xp);
         while (!xp.ready && !ptx::mbar_try_wait(tfull_bar(acc), acc_phase)) {
@@ -1300,7 +1041,6 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   else if (warp >= 8) {
     // ===================================================================== helper warps (TMEM lane quadrant = warp & 3)
     const int q = warp & 3;
-    if (FT && p.enc_prog != nullptr) encoder_prefix(q);
     if (p.sk_tiles > 0 || (p.epi_assist != 0 && BN >= 64)) {
       const uint32_t seeded_leader = (CG == 2) ? ptx::mapa(seeded_bar(0), 0) : seeded_bar(0);
       const size_t ws_slab = static_cast<size_t>(kBM) * BN;
@@ -1349,7 +1089,6 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       SegIter it(p, unit);
       Segment sg;
       while (it.next(sg)) {
-        if (FT && sg.kind == 4) continue;  // no accumulator
         ++item_idx;
         if (sg.kind == 2 || sg.kind == 3) {
           // Seed first (it has to be in tensor memory before this item's first UMMA, i.e. during the previous item's main
@@ -1361,7 +1100,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ptx::Watchdog wd;
             while (ptx::ld_acquire_shared_u32(epi_count) < need) {
               __nanosleep(64);
-              wd.tick();
+              if (wd.tick()) break;
             }
           }
           ptx::tc_fence_after();
@@ -1399,8 +1138,11 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Stand-alone encode pre-pass (same per-warp routine as the in-kernel helpers): used when the caller asks for it
-// (debug knob enc_mode = 1) -- the A/B partner of the in-kernel encode.
+// Stand-alone encode pre-pass in front of the GEMM kernel (HBM-bound: it reads B once).  Four in-kernel alternatives
+// were built and measured over two rounds -- helper warps reducing B stages from shared memory ("encoder tiles" /
+// "encoder items"), and the idle warps of every CTA reducing B straight from global memory -- and removed: on an SM
+// whose ingest port and shared-memory port are saturated by TMA + UMMA a second reader of B is starved (background
+// loads ran 6x slower than on an idle SM), profiles/README.md.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kEncWarps = 8;
 

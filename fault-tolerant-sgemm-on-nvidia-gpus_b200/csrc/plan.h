@@ -13,10 +13,8 @@
 // as in the checksum tile-columns.  (Adding independently accumulated partial sums, the usual split-K, raised the
 // fault-free ABFT residual 6x, profiles/r01_probe8_residual_vs_splitk.jsonl.)
 //
-// Global item order:  [encoder tiles][encoder items][early first pieces][checksum tiles][whole data tiles, raster order]
+// Global item order:  [early first pieces][checksum tiles][whole data tiles, raster order]
 //                     [late first pieces][2nd pieces][3rd pieces]...
-//   * encoder items (ABFT, one per tile-column of B) produce the checksum vectors the checksum tiles consume; they wait
-//     for nothing and must be a prefix of their unit's list (the helper warps consume the ring from its initial state);
 //   * early first pieces run at the very start: their epilogue only parks the accumulator (no checksum needed); made as
 //     long as a checksum item they keep all units in step (the units that share A / B panels then stream the same k range);
 //   * late first pieces and all later pieces run at the end, longest first, and level the finishing times.
@@ -31,11 +29,9 @@
 namespace ftsgemm {
 
 struct PlanItem {
-  int tile;        // decode order: checksum tiles first, then data tiles (encoder items: the tile-column of B)
+  int tile;        // decode order: checksum tiles first, then data tiles
   int kb_begin, kb_end;
-  int kind;        // 0 whole tile, 1 first piece (park), 3 middle piece (seed + park), 2 last piece (seed + finish),
-                   // 4 encoder item (streams a tile-column of B through shared memory and writes its checksum vectors),
-                   // 5 encoder tile (a whole data tile whose B stages are also reduced to the checksum vectors)
+  int kind;        // 0 whole tile, 1 first piece (park), 3 middle piece (seed + park), 2 last piece (seed + finish)
   int slice;       // piece index within its tile
   int split_idx;   // index among the cut tiles (workspace slot), -1 otherwise
 };
@@ -56,13 +52,7 @@ struct PlanInput {
   int num_kb;           // k-blocks per tile
   int tiles_m;          // checksum tile t belongs to checksum tile-column t / tiles_m
   std::vector<double> chk_col_cost;  // tile-times of one tile of each checksum tile-column
-  double chk_release = 0.0;          // tile-times before checksum items can start (in-kernel encode of B)
-  int n_enc_items = 0;               // encoder items (one per tile-column of B), first in every unit's list
-  double enc_cost = 0.0;             // tile-times of one encoder item
-  std::vector<int> enc_tiles;        // encoder TILES: raster indices of the data tiles that also encode their tile-column
-                                     // (first in their unit's list; checksum items never share a unit with them, because
-                                     // an encoder tile's epilogue waits for checksum tiles that wait for ALL encoder tiles)
-  double enc_tile_cost = 1.0;        // tile-times of one encoder tile
+  double chk_release = 0.0;          // tile-times before checksum items can start (their operand comes from the pre-pass)
   double item_overhead = 0.0;        // tile-times per item (pipeline fill + drain)
   double park_latency = 0.0;         // tile-times between the end of a piece's main loop and its successor's start
   double seed_overhead = 0.0;        // extra tile-times of a seeded piece (its accumulator stage is loaded before the first UMMA)
@@ -111,22 +101,10 @@ inline double schedule(const PlanInput &in, const Cut &c, Plan *out) {
   std::vector<std::vector<PlanItem>> lists;
   if (out) lists.resize(in.units);
   std::vector<double> first_whole(in.units, -1.0);
-  std::vector<char> enc_unit(in.units, 0);
-  std::vector<LU> skipped;
   double makespan = 0.0;
   auto give = [&](const PlanItem &it, double cost, double release, bool is_whole) -> double {
     LU lu = pq.top();
     pq.pop();
-    if (it.kind == 0 && it.tile < in.n_chk_tiles) {  // checksum item: not behind an encoder tile
-      skipped.clear();
-      while (enc_unit[lu.second] && !pq.empty()) {
-        skipped.push_back(lu);
-        lu = pq.top();
-        pq.pop();
-      }
-      for (const LU &s : skipped) pq.push(s);
-    }
-    if (it.kind == 5) enc_unit[lu.second] = 1;
     if (lu.first < release) lu.first = release;  // the unit idles until the item's input exists
     if (is_whole && first_whole[lu.second] < 0.0) first_whole[lu.second] = lu.first;
     lu.first += cost + in.item_overhead;
@@ -152,17 +130,10 @@ inline double schedule(const PlanInput &in, const Cut &c, Plan *out) {
                             len + (p > 0 ? in.seed_overhead : 0.0), ready[i], false);
     ready[i] = end + in.park_latency;
   };
-  std::vector<char> is_enc_tile(static_cast<size_t>(in.n_data_tiles), 0);
-  for (int d : in.enc_tiles) {
-    is_enc_tile[static_cast<size_t>(d)] = 1;
-    give(PlanItem{in.n_chk_tiles + d, 0, in.num_kb, 5, 0, -1}, in.enc_tile_cost, 0.0, true);
-  }
-  for (int t = 0; t < in.n_enc_items; ++t) give(PlanItem{t, 0, in.num_kb, 4, 0, -1}, in.enc_cost, 0.0, false);
   for (int i = 0; i < c.He; ++i) piece(i, 0);
   for (int t = 0; t < in.n_chk_tiles; ++t)
     give(PlanItem{t, 0, in.num_kb, 0, 0, -1}, in.chk_col_cost[static_cast<size_t>(t / in.tiles_m)], in.chk_release, false);
-  for (int d = 0; d < whole; ++d)
-    if (!is_enc_tile[static_cast<size_t>(d)]) give(PlanItem{in.n_chk_tiles + d, 0, in.num_kb, 0, 0, -1}, 1.0, 0.0, true);
+  for (int d = 0; d < whole; ++d) give(PlanItem{in.n_chk_tiles + d, 0, in.num_kb, 0, 0, -1}, 1.0, 0.0, true);
   for (int i = c.He; i < H; ++i) piece(i, 0);
   for (int p = 1; p < max_pieces; ++p) {
     std::vector<int> order;
@@ -220,11 +191,8 @@ inline Plan build_plan(const PlanInput &in) {
     const size_t slab_cap = std::min<size_t>((static_cast<size_t>(256) << 20) / std::max<size_t>(1, in.slab_bytes * (pieces - 1)),
                                              65536 / (8 * sizeof(int) * (pieces - 1)));
     const int hcap = static_cast<int>(std::min<size_t>(slab_cap, static_cast<size_t>(T)));
-    int max_enc = -1;
-    for (int d : in.enc_tiles) max_enc = std::max(max_enc, d);
     auto consider = [&](const Cut &c) {
       if (c.He + c.Hl <= 0 || c.He + c.Hl > hcap) return;
-      if (T - (c.He + c.Hl) <= max_enc) return;  // the cut tiles are the last ones of the raster: no encoder tile among them
       const double t = schedule(in, c, nullptr);
       if (best < 0.0 || t < best) {
         best = t;

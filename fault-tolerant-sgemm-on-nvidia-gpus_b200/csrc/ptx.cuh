@@ -65,13 +65,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 #endif
   return ok != 0;
 }
-// Spin on try_wait.  FTSGEMM_WATCHDOG (default on) turns a protocol bug into a trap instead of a hung GPU: any wait
-// longer than kWatchdogNs of wall time (%globaltimer; far beyond any legal wait) traps.  The clock is only read on the
-// slow path (every 1024 failed polls).
+// Spin on try_wait.  FTSGEMM_WATCHDOG (default on) turns a protocol bug -- or a grid whose CTAs are not all resident
+// (the persistent kernel's inter-CTA waits need that) -- into a REPORTED error instead of a hung GPU or a poisoned
+// context: a wait longer than kWatchdogNs of wall time (%globaltimer; far beyond any legal wait) raises the device-wide
+// abort flag and returns; from then on every wait of the grid falls through at its next slow-path check, the kernel
+// terminates with an undefined result, and the host reports FTSGEMM_ERR_TIMEOUT from ftsgemm_get_stats / the next
+// launch (csrc/ftsgemm.cu).  The clock and the flag are only read on the slow path (every 1024 failed polls).
 #ifndef FTSGEMM_WATCHDOG
 #define FTSGEMM_WATCHDOG 1
 #endif
 constexpr unsigned long long kWatchdogNs = 1500ull * 1000 * 1000;
+__device__ int g_abort_flag = 0;  // one copy per device; cleared by the host after it has been reported
 __device__ __forceinline__ unsigned long long globaltimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -80,19 +84,26 @@ __device__ __forceinline__ unsigned long long globaltimer() {
 struct Watchdog {
   uint32_t spins = 0;
   unsigned long long t0 = 0;
-  __device__ __forceinline__ void tick() {
+  // returns true when the wait has to be abandoned
+  __device__ __forceinline__ bool tick() {
 #if FTSGEMM_WATCHDOG
     if ((++spins & 1023u) == 0u) {
+      if (*reinterpret_cast<volatile int *>(&g_abort_flag) != 0) return true;
       const unsigned long long t = globaltimer();
       if (t0 == 0) t0 = t;
-      else if (t - t0 > kWatchdogNs) __trap();
+      else if (t - t0 > kWatchdogNs) {
+        atomicExch(&g_abort_flag, 1);
+        return true;
+      }
     }
 #endif
+    return false;
   }
 };
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   Watchdog wd;
-  while (!mbar_try_wait(bar, parity)) wd.tick();
+  while (!mbar_try_wait(bar, parity))
+    if (wd.tick()) break;
 }
 
 // programmatic dependent launch: let the next kernel in the stream start while this one drains / wait for the previous one
@@ -270,7 +281,7 @@ __device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar, uint32_t
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) break;
-    wd.tick();
+    if (wd.tick()) break;
   }
 }
 __device__ __forceinline__ void mbar_arrive_cnt(uint32_t bar, uint32_t count) {

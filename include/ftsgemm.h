@@ -36,7 +36,11 @@ enum {
   FTSGEMM_ERR_CUDA = -3,         /* a CUDA runtime/driver call failed; see ftsgemm_last_cuda_error */
   FTSGEMM_ERR_NO_DEVICE = -4,    /* no sm_100 device / driver (the product has NO CPU fallback) */
   FTSGEMM_ERR_CUBLAS = -5,
-  FTSGEMM_ERR_VERIFY = -6        /* used by the driver helpers only */
+  FTSGEMM_ERR_VERIFY = -6,       /* used by the driver helpers only */
+  FTSGEMM_ERR_TIMEOUT = -7       /* a device-side wait of the persistent kernel timed out (its CTAs were not all resident,
+                                    e.g. the SMs were taken by another context): reported by the next synchronising call
+                                    (ftsgemm_get_stats, ftsgemm_run_host); the affected launch's output is undefined, the
+                                    CUDA context stays usable */
 };
 
 /* Kernel ids: the reference's table (sgemm.cu:235-237) is kept verbatim for ids 0,1-6,10,11-16.
@@ -102,6 +106,9 @@ typedef struct ftsgemm_opts {
   int baseline_host_sync;/* id 10/30: 1 = host-synchronise between stages like the reference
                             (baseline_ft_sgemm.cuh:7,19,26,30); 0 = stream-ordered */
 } ftsgemm_opts;
+/* sizeof(ftsgemm_opts) of ABI version 1: the smallest struct_size the library accepts (a zero-initialised struct is
+ * rejected with FTSGEMM_ERR_INVALID_ARG instead of silently meaning "all defaults on the default stream"). */
+#define FTSGEMM_OPTS_V1_SIZE (offsetof(ftsgemm_opts, baseline_host_sync) + sizeof(int))
 
 typedef struct ftsgemm_event {
   int row, col;          /* global element that was located (col = -1 if not locatable) */

@@ -97,83 +97,48 @@ def test_ft_equals_plain_bitwise_when_fault_free(cuda, ft, dev):
             ft.debug_set("splitk", -1)
 
 
-def test_encode_in_kernel_and_prepass_agree(cuda, ft, dev):
-    """The checksum vectors of B come from the stand-alone pre-pass kernel (mode 1, default) or from inside the GEMM
-    kernel: encoder tiles (mode 3: the first data tile of every tile-column also reduces its own B stages from shared
-    memory, checksum items follow k-chunk by k-chunk), encoder items (mode 2: a unit streams a tile-column of B through
-    its ring).  All of them and the cached-checksum path must give the same results and verdicts."""
+def test_prepass_encode_and_cached_checksums_agree(cuda, ft, dev, oracle):
+    """The checksum vectors of B come from the encode pre-pass in front of the GEMM kernel; back-to-back launches reuse the
+    flags / epochs, and the cached-checksum path (reuse_b_checksums) must give the same results and verdicts.  Also the
+    ragged N / K tail and the narrow-tile (scalar) encode path, all FT tile widths, and a long odd K (129 k-blocks)."""
     rng = np.random.default_rng(5)
     M, N, K = 1024, 1280, 768
     A, B = _rand(rng, M * K), _rand(rng, N * K)
     C0 = rng.standard_normal(M * N).astype(np.float32)
     faults = [{"row": 77, "col": 300, "xor": 1 << 29}, {"row": 900, "col": 1279, "add": -55.0}]
-    outs = []
-    for mode in (3, 2, 1):
-        try:
-            ft.debug_set("enc_mode", mode)
-            dev.stats()
-            for rep in range(3):  # back-to-back launches reuse the flags / epochs / counters
-                got = _run(cuda, dev, 31, M, N, K, A, B, C0, 1.0, -1.5, opts=ft.make_opts(faults=faults))
-            st = dev.stats()
-            assert st["detected"] == 6 and st["corrected"] == 6 and st["uncorrectable"] == 0
-            outs.append(got)
-        finally:
-            ft.debug_set("enc_mode", -1)
-    # modes 3 / 2 reduce the lane partials with an FP32 butterfly, mode 1 with an FP64 one: the checksum vectors agree to
-    # 2^-22, so only the RECOMPUTED (corrected) elements may differ, in their last bits
-    assert np.array_equal(outs[0], outs[1])
-    assert np.count_nonzero(outs[0] != outs[2]) <= 2 and np.allclose(outs[0], outs[2], rtol=1e-5, atol=1e-5 * np.abs(outs[2]).max())
+    dev.stats()
+    for rep in range(3):
+        got = _run(cuda, dev, 31, M, N, K, A, B, C0, 1.0, -1.5, opts=ft.make_opts(faults=faults))
+    st = dev.stats()
+    assert st["detected"] == 6 and st["corrected"] == 6 and st["uncorrectable"] == 0
     dA, dB = cuda.from_numpy(A).cuda(), cuda.from_numpy(B).cuda()
     dC = cuda.from_numpy(C0.copy()).cuda()
     dev.run(31, M, N, K, dA, dB, dC, 1.0, -1.5, ft.make_opts(faults=faults))
     dC2 = cuda.from_numpy(C0.copy()).cuda()
     dev.run(31, M, N, K, dA, dB, dC2, 1.0, -1.5, ft.make_opts(faults=faults, reuse_b_checksums=True))
     cuda.cuda.synchronize()
-    assert cuda.equal(dC, dC2) and np.array_equal(dC.cpu().numpy(), outs[2])  # (the default is mode 1)
-    # ragged N / K tail and the narrow-tile (scalar) encode path against the pre-pass, all FT tile widths
-    for (M2, N2, K2) in ((260, 388, 72), (260, 416, 200)):  # N % 32 != 0: pre-pass only; ragged last tile, K tail
-      A2, B2 = _rand(rng, M2 * K2), _rand(rng, N2 * K2)
-      C2 = np.zeros(M2 * N2, np.float32)
-      for kid in (11, 12, 16, 15, 31, 32):
-          res = []
-          for mode in (3, 2, 1):
-              try:
-                  ft.debug_set("enc_mode", mode)
-                  dev.stats()
-                  res.append(_run(cuda, dev, kid, M2, N2, K2, A2, B2, C2, 1.0, 0.0, opts=ft.make_opts(selftest=(10000.0, 17, 5))))
-                  st = dev.stats()
-                  assert st["detected"] == st["corrected"] > 0 and st["uncorrectable"] == 0, (kid, mode, st)
-              finally:
-                  ft.debug_set("enc_mode", -1)
-          assert np.array_equal(res[0], res[1]), kid
-          assert np.allclose(res[0], res[2], rtol=1e-5, atol=1e-5 * max(1.0, float(np.abs(res[2]).max()))), kid
-
-
-def test_encode_variants_long_k_and_odd_k_blocks(cuda, ft, dev, oracle):
-    """Encoder items / tiles publish their progress per chunk of 32 k-blocks and, on a CTA pair, alternate k-blocks between
-    the two CTAs: K = 4128 is 129 k-blocks (5 chunks, an odd count: the peer's last slot lies past the end of K and is
-    zero-filled).  Verdicts and results must agree with the pre-pass and the TF32 model."""
-    rng = np.random.default_rng(21)
+    assert cuda.equal(dC, dC2) and np.array_equal(dC.cpu().numpy(), got)
+    for (M2, N2, K2) in ((260, 388, 72), (260, 416, 200)):  # N % 32 != 0; ragged last tile, K tail
+        A2, B2 = _rand(rng, M2 * K2), _rand(rng, N2 * K2)
+        C2 = np.zeros(M2 * N2, np.float32)
+        model = oracle.sgemm_nt_tf32_model(M2, N2, K2, 1.0, A2, B2, 0.0, C2, "trunc")
+        for kid in (11, 12, 16, 15, 31, 32):
+            dev.stats()
+            res = _run(cuda, dev, kid, M2, N2, K2, A2, B2, C2, 1.0, 0.0, opts=ft.make_opts(selftest=(10000.0, 17, 5)))
+            st = dev.stats()
+            assert st["detected"] == st["corrected"] > 0 and st["uncorrectable"] == 0, (kid, st)
+            assert oracle.error_metrics(model, res)["rel_fro"] < TOL_MODEL, kid
     M, N, K = 512, 768, 4128
     A, B = _rand(rng, M * K), _rand(rng, N * K)
     C0 = rng.standard_normal(M * N).astype(np.float32)
     model = oracle.sgemm_nt_tf32_model(M, N, K, 1.0, A, B, 0.5, C0, "trunc")
     faults = [{"row": 300, "col": 5, "xor": 1 << 30}, {"row": 511, "col": 767, "add": 123.0}]
-    outs = {}
     for kid in (31, 16):
-        for mode in (3, 2, 1):
-            try:
-                ft.debug_set("enc_mode", mode)
-                dev.stats()
-                got = _run(cuda, dev, kid, M, N, K, A, B, C0, 1.0, 0.5, opts=ft.make_opts(faults=faults))
-                st = dev.stats()
-                assert st["detected"] == 2 and st["corrected"] == 2 and st["uncorrectable"] == 0, (kid, mode, st)
-                assert oracle.error_metrics(model, got)["rel_fro"] < TOL_MODEL, (kid, mode)
-                outs[(kid, mode)] = got
-            finally:
-                ft.debug_set("enc_mode", -1)
-        assert np.array_equal(outs[(kid, 3)], outs[(kid, 2)])
-        assert np.allclose(outs[(kid, 3)], outs[(kid, 1)], rtol=1e-5, atol=1e-5 * np.abs(outs[(kid, 1)]).max())
+        dev.stats()
+        got = _run(cuda, dev, kid, M, N, K, A, B, C0, 1.0, 0.5, opts=ft.make_opts(faults=faults))
+        st = dev.stats()
+        assert st["detected"] == 2 and st["corrected"] == 2 and st["uncorrectable"] == 0, (kid, st)
+        assert oracle.error_metrics(model, got)["rel_fro"] < TOL_MODEL, kid
 
 
 @pytest.mark.parametrize("seed", range(10))
@@ -188,7 +153,7 @@ def test_random_shapes_and_knobs(cuda, ft, dev, oracle, seed):
     name = ["small", "medium", "huge", "wide", "giant", "pair128"][seed % 6]
     alpha = float(rng.choice([1.0, 0.75, -2.0]))
     beta = float(rng.choice([0.0, -1.5, 1.0]))
-    knobs = {"splitk": int(rng.choice([-1, 0, 2, 3])), "enc_mode": int(rng.choice([1, 2, 3])),
+    knobs = {"splitk": int(rng.choice([-1, 0, 2, 3])), 
              "wave_sync": int(rng.choice([0, 1])), "pdl": int(rng.choice([0, 1])), "epi_assist": int(rng.choice([0, 1]))}
     A, B = rng.standard_normal(M * K).astype(np.float32), rng.standard_normal(N * K).astype(np.float32)
     C0 = rng.standard_normal(M * N).astype(np.float32)

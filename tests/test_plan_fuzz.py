@@ -10,9 +10,8 @@ from test_schedule import TILE_N, _simulate
 @settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
 @given(kid=st.sampled_from([1, 2, 6, 5, 21, 22, 11, 12, 16, 15, 31, 32]),
        m4=st.integers(1, 3000), n4=st.integers(1, 3000), K=st.integers(1, 20000),
-       sms=st.sampled_from([148, 132, 20, 8, 2]), splitk=st.sampled_from([-1, 0, 2, 3, 4]),
-       enc=st.sampled_from([1, 2, 3]))
-def test_random_plans(ft, kid, m4, n4, K, sms, splitk, enc):
+       sms=st.sampled_from([148, 132, 20, 8, 2]), splitk=st.sampled_from([-1, 0, 2, 3, 4]))
+def test_random_plans(ft, kid, m4, n4, K, sms, splitk):
     M, N = 4 * m4, 4 * n4
     bn = TILE_N[kid]
     cg = 2 if kid in (21, 22, 31, 32) else 1
@@ -21,18 +20,14 @@ def test_random_plans(ft, kid, m4, n4, K, sms, splitk, enc):
         N = min(N, bn * 100)
     try:
         ft.debug_set("splitk", splitk)
-        ft.debug_set("enc_mode", enc)
         hdr, segs = ft.debug_schedule(kid, M, N, K, sms)
     finally:
         ft.debug_set("splitk", -1)
-        ft.debug_set("enc_mode", -1)
     num_kb = -(-K // 32)
     assert hdr["num_kb"] == num_kb and hdr["cta_group"] == cg
     cover = {}
     for s in segs:
         assert 0 <= s["kb_begin"] < s["kb_end"] <= num_kb and 0 <= s["unit"] < hdr["units"]
-        if s["kind"] == 4:
-            continue
         cover.setdefault(s["tile"], []).append((s["kb_begin"], s["kb_end"], s["kind"]))
     assert sorted(cover) == list(range(hdr["num_tiles"]))
     for pieces in cover.values():
@@ -40,5 +35,5 @@ def test_random_plans(ft, kid, m4, n4, K, sms, splitk, enc):
         assert pieces[0][0] == 0 and pieces[-1][1] == num_kb
         assert all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
         kinds = [p[2] for p in pieces]
-        assert kinds in ([0], [5]) or kinds == [1] + [3] * (len(kinds) - 2) + [2]
+        assert kinds == [0] or kinds == [1] + [3] * (len(kinds) - 2) + [2]
     assert _simulate(hdr, segs, 2), "circular wait in the schedule"

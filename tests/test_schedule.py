@@ -16,12 +16,10 @@ def _simulate(hdr, segs, acc_stages):
     units = hdr["units"]
     per_unit = [[] for _ in range(units)]
     for s in segs:
-        if s["kind"] != 4:  # encoder items wait for nothing and own no accumulator: they can never block
-            per_unit[s["unit"]].append(s)
+        per_unit[s["unit"]].append(s)
     tiles_c = 0
     chk_done = {}     # (m_blk, c) -> bool
     piece_at = {}     # (tile, piece) -> (unit, idx)
-    enc_tiles = []    # (unit, idx) of encoder tiles: checksum tiles consume what their main loops produce
     for u, lst in enumerate(per_unit):
         for i, s in enumerate(lst):
             if s["is_chk"]:
@@ -29,8 +27,6 @@ def _simulate(hdr, segs, acc_stages):
                 tiles_c = max(tiles_c, s["n_blk"] + 1)
             if s["kind"] in (1, 2, 3):
                 piece_at[(s["tile"], s["slice"])] = (u, i)
-            if s["kind"] == 5:
-                enc_tiles.append((u, i))
     mma_done = [0] * units   # number of items whose main loop finished
     epi_done = [0] * units
     done_epi = set()         # (unit, idx)
@@ -44,15 +40,13 @@ def _simulate(hdr, segs, acc_stages):
                 s = lst[mma_done[u]]
                 if s["kind"] in (2, 3) and piece_at[(s["tile"], s["slice"] - 1)] not in done_epi:
                     break
-                if s["is_chk"] and any(mma_done[eu] <= ei for eu, ei in enc_tiles):
-                    break  # (conservative: the checksum tile cannot finish before every encoder tile's main loop has)
                 mma_done[u] += 1
                 progress = True
             while epi_done[u] < mma_done[u]:
                 i = epi_done[u]
                 s = lst[i]
                 ok = True
-                if hdr["n_chk_tiles"] and not s["is_chk"] and s["kind"] in (0, 2, 5):  # parking pieces are not checked
+                if hdr["n_chk_tiles"] and not s["is_chk"] and s["kind"] in (0, 2):  # parking pieces are not checked
                     ok = all(chk_done[(s["m_blk"], c)] for c in range(tiles_c))
                 if not ok:
                     break
@@ -69,37 +63,19 @@ def _simulate(hdr, segs, acc_stages):
                                    (1536, 2560, 1000), (256, 256, 64), (128, 4096, 32), (5120, 384, 4096),
                                    (16384, 16384, 1024), (32768, 1024, 256)])
 @pytest.mark.parametrize("num_sms", [148, 16, 6])
-@pytest.mark.parametrize("enc_mode", [1, 2, 3])  # pre-pass kernel | encoder items | encoder tiles inside the GEMM kernel
-def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms, enc_mode):
+def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms):
     M, N, K = shape
-    try:
-        ft.debug_set("enc_mode", enc_mode)
-        hdr, segs = ft.debug_schedule(kid, M, N, K, num_sms)
-    finally:
-        ft.debug_set("enc_mode", -1)
+    hdr, segs = ft.debug_schedule(kid, M, N, K, num_sms)
     units, num_kb, H, S = hdr["units"], hdr["num_kb"], hdr["sk_tiles"], hdr["sk_slices"]
     assert hdr["num_kb"] == -(-K // 32)
     first_cut = hdr["num_tiles"] - H
     cover = {}
-    enc_cols = []
     for s in segs:
         assert 0 <= s["kb_begin"] < s["kb_end"] <= num_kb
-        if s["kind"] == 4:  # encoder item: one per tile-column of B, the whole K range
-            assert (s["kb_begin"], s["kb_end"]) == (0, num_kb)
-            enc_cols.append(s["n_blk"])
-            continue
+        assert s["kind"] in (0, 1, 2, 3)
         cover.setdefault(s["tile"], []).append((s["kb_begin"], s["kb_end"], s["kind"], s["slice"]))
         if s["kind"] in (1, 2, 3):
             assert s["tile"] >= first_cut and not s["is_chk"]
-    tiles_n = -(-N // TILE_N[kid])
-    enc_tile_cols = sorted(s["n_blk"] for s in segs if s["kind"] == 5)
-    if kid in (11, 12, 16, 15, 31, 32) and N % 32 == 0 and enc_mode == 2:
-        assert sorted(enc_cols) == list(range(tiles_n)) and not enc_tile_cols
-    elif kid in (11, 12, 16, 15, 31, 32) and N % 32 == 0 and enc_mode == 3 and 2 * tiles_n <= units:
-        assert enc_tile_cols == list(range(tiles_n)) and not enc_cols
-        assert all(s["m_blk"] == 0 for s in segs if s["kind"] == 5)
-    else:
-        assert not enc_cols and not enc_tile_cols
     assert sorted(cover) == list(range(hdr["num_tiles"]))
     for t, pieces in cover.items():
         pieces.sort()
@@ -107,13 +83,13 @@ def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms, enc_m
         for a, b in zip(pieces, pieces[1:]):
             assert a[1] == b[0]  # contiguous, no overlap
         if len(pieces) == 1:
-            assert pieces[0][2] in (0, 5) and t < first_cut
+            assert pieces[0][2] == 0 and t < first_cut
         else:
             assert t >= first_cut and 2 <= len(pieces) <= S
             assert [p[2] for p in pieces] == [1] + [3] * (len(pieces) - 2) + [2]
             assert [p[3] for p in pieces] == list(range(len(pieces)))
             assert all(p[1] - p[0] >= 4 for p in pieces)
-    # global item order: [encoder items][early first pieces][checksum tiles][whole tiles][late first pieces][2nd pieces]...;
+    # global item order: [early first pieces][checksum tiles][whole tiles][late first pieces][2nd pieces]...;
     # every unit's list follows it (regular expression P* C* W* P* then later pieces by piece index), checksum and whole
     # tiles in raster order; the circular-wait simulation below is the actual safety check
     import re
@@ -121,9 +97,8 @@ def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms, enc_m
     for s_ in segs:
         per_unit.setdefault(s_["unit"], []).append(s_)
     for lst in per_unit.values():
-        word = "".join("C" if s_["is_chk"] else "WPFMET"[s_["kind"]] for s_ in lst)
-        # encoder tiles / items are a prefix (the ENCODE workers rely on it); no checksum item behind an encoder tile
-        assert re.fullmatch(r"(T*P*|E*P*C*)W*P*[FM]*", word), word
+        word = "".join("C" if s_["is_chk"] else "WPFM"[s_["kind"]] for s_ in lst)
+        assert re.fullmatch(r"P*C*W*P*[FM]*", word), word
         later = [s_["slice"] for s_ in lst if s_["kind"] in (2, 3)]
         assert later == sorted(later)
         for cls in ("C", "W"):
@@ -148,7 +123,7 @@ def test_planner_levels_the_units(ft):
         hdr, segs = ft.debug_schedule(kid, n, n, n, 148)
         work = [0.0] * hdr["units"]
         for s in segs:
-            work[s["unit"]] += (1.2 if s["kind"] == 4 else 0.58 if s["is_chk"] else 1.0) * (s["kb_end"] - s["kb_begin"]) / hdr["num_kb"]
+            work[s["unit"]] += (0.58 if s["is_chk"] else 1.0) * (s["kb_end"] - s["kb_begin"]) / hdr["num_kb"]
         return hdr, max(work), sum(work) / hdr["units"]
     hdr, t, ideal = makespan(21, 4096)   # 256 tiles on 74 pairs: 3.46 waves -> 4 waves uncut
     assert hdr["sk_tiles"] > 0 and hdr["sk_slices"] == 2 and t <= 3.7
