@@ -292,9 +292,9 @@ int launch_tc(ftsgemm_handle_t h, const CUtensorMap &tmA, const CUtensorMap &tmB
 // takes ~0.33 us, an item costs ~1.5 us of pipeline fill + drain, and a parked accumulator is back in the next owner's
 // tensor memory ~8 us after the piece's last UMMA.
 template <int BNv, int CGv>
-void chk_costs(const KernelParams &p, std::vector<double> *out) {
+void chk_costs(const KernelParams &p, double floor_cost, std::vector<double> *out) {
   for (int c = 0; c < p.tiles_c; ++c)
-    out->push_back(std::max(0.58, static_cast<double>(chk_tile_width<BNv, CGv>(p, c)) / BNv));
+    out->push_back(std::max(floor_cost, static_cast<double>(chk_tile_width<BNv, CGv>(p, c)) / BNv));
 }
 
 PlanInput make_plan_input(int max_units, int CG, int BN, int K, const KernelParams &p) {
@@ -305,12 +305,19 @@ PlanInput make_plan_input(int max_units, int CG, int BN, int K, const KernelPara
   in.n_data_tiles = p.tiles_m * p.tiles_n;
   in.num_kb = (K + kBK - 1) / kBK;
   in.tiles_m = p.tiles_m;
-  if (BN == 32) chk_costs<32, 1>(p, &in.chk_col_cost);
-  else if (BN == 64) chk_costs<64, 1>(p, &in.chk_col_cost);
-  else if (BN == 128 && CG == 1) chk_costs<128, 1>(p, &in.chk_col_cost);
-  else if (BN == 128) chk_costs<128, 2>(p, &in.chk_col_cost);
-  else if (CG == 1) chk_costs<256, 1>(p, &in.chk_col_cost);
-  else chk_costs<256, 2>(p, &in.chk_col_cost);
+  // operands larger than ~3/4 of the 126 MB L2: keep the units in k-lockstep (plan.h)
+  const long long lock = dbg("lockstep", -2);
+  in.lockstep = lock >= 0 ? static_cast<int>(lock)
+                          : (4.0 * K * (static_cast<double>(p.M) + p.N) > 96.0 * 1024 * 1024 ? 1 : 0);
+  // a checksum item's main loop runs at 0.22 us per k-block whatever the size (round 2 timelines: 0.67-0.69 of a data
+  // tile at 2048 .. 4096, where data tiles take 0.33 us per k-block out of L2; 0.58 where they are HBM-bound)
+  const double chk_floor = static_cast<double>(dbg("chk_cost_permille", in.lockstep ? 580 : 680)) * 1e-3;
+  if (BN == 32) chk_costs<32, 1>(p, chk_floor, &in.chk_col_cost);
+  else if (BN == 64) chk_costs<64, 1>(p, chk_floor, &in.chk_col_cost);
+  else if (BN == 128 && CG == 1) chk_costs<128, 1>(p, chk_floor, &in.chk_col_cost);
+  else if (BN == 128) chk_costs<128, 2>(p, chk_floor, &in.chk_col_cost);
+  else if (CG == 1) chk_costs<256, 1>(p, chk_floor, &in.chk_col_cost);
+  else chk_costs<256, 2>(p, chk_floor, &in.chk_col_cost);
   const double tile_us = in.num_kb * 0.333 * (static_cast<double>(BN) * CG / 512.0 < 0.25 ? 0.25 : static_cast<double>(BN) * CG / 512.0);
   in.item_overhead = static_cast<double>(dbg("item_overhead_ns", 1500)) * 1e-3 / tile_us;
   in.park_latency = static_cast<double>(dbg("park_latency_ns", 8000)) * 1e-3 / tile_us;
@@ -320,10 +327,6 @@ PlanInput make_plan_input(int max_units, int CG, int BN, int K, const KernelPara
   in.force_slices = force > 1 ? static_cast<int>(force) : 0;
   in.slab_bytes = static_cast<size_t>(CG) * kBM * BN * sizeof(float);
   in.full_search = dbg("plan_full_search", 0) != 0 ? 1 : 0;
-  // operands larger than ~3/4 of the 126 MB L2: keep the units in k-lockstep (plan.h)
-  const long long lock = dbg("lockstep", -2);
-  in.lockstep = lock >= 0 ? static_cast<int>(lock)
-                          : (4.0 * K * (static_cast<double>(p.M) + p.N) > 96.0 * 1024 * 1024 ? 1 : 0);
   return in;
 }
 
@@ -445,6 +448,10 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
       const int grid = static_cast<int>(dbg("enc_blocks_per_sm", 4)) * h->num_sms;
       const bool small_items = dbg("enc_kr", 8) == 4;
       const bool chain = dbg("pdl_chain", 1) != 0;
+      // B larger than ~half of L2: read it with evict-first loads (it cannot stay resident for the GEMM anyway)
+      const long long sb = dbg("enc_stream", -2);
+      const bool stream_b = sb > 0;  // measured at 8192^3: 1550 vs 1480 us per step -- the tail of B the pre-pass leaves in L2 is
+                                     // worth more to the GEMM's first wave than the residue it evicts: off by default
 #define FT_ENC(bn)                                                                                                          \
   if (BN == bn) {                                                                                                           \
     cudaLaunchConfig_t ec;                                                                                                  \
@@ -460,8 +467,9 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     const float *eb = dB;                                                                                                   \
     float *eo = h->d_chk;                                                                                                   \
     int en = N, ek = K, el = chk_ld, er = rounding, et = p.tiles_n;                                                         \
-    if (small_items) FT_CUDA(h, cudaLaunchKernelEx(&ec, encode_b_kernel<bn, 4>, eb, en, ek, en, eo, el, er, et));           \
-    else FT_CUDA(h, cudaLaunchKernelEx(&ec, encode_b_kernel<bn, 8>, eb, en, ek, en, eo, el, er, et));                       \
+    if (small_items) FT_CUDA(h, cudaLaunchKernelEx(&ec, encode_b_kernel<bn, 4, false>, eb, en, ek, en, eo, el, er, et));    \
+    else if (stream_b) FT_CUDA(h, cudaLaunchKernelEx(&ec, encode_b_kernel<bn, 8, true>, eb, en, ek, en, eo, el, er, et));   \
+    else FT_CUDA(h, cudaLaunchKernelEx(&ec, encode_b_kernel<bn, 8, false>, eb, en, ek, en, eo, el, er, et));                \
   }
       FT_ENC(32) FT_ENC(64) FT_ENC(128) FT_ENC(256)
 #undef FT_ENC

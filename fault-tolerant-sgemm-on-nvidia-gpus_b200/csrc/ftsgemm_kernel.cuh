@@ -597,7 +597,21 @@ struct TransposeReduce {
 
 // One warp encodes items (column block t, KR consecutive k-rows), item = gw, gw + nw, ...; t fastest, so that warps
 // running side by side read neighbouring 1 KiB segments of the same rows of B.
-template <int BN, int KRQ>
+// 16-byte read-only load; STREAM: evict-first in L2 (B larger than L2: the pre-pass must not push the GEMM's working set
+// -- the tails of A, B, C the previous launch left there -- out of the cache for data it will not find again anyway)
+template <bool STREAM>
+__device__ __forceinline__ float4 ld_b16(const float4 *p) {
+  if (!STREAM) return __ldg(p);
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(policy));
+  return v;
+}
+
+template <int BN, int KRQ, bool STREAM = false>
 __device__ __forceinline__ void encode_b_warp(const float *__restrict__ B, int N, int K, int ldb, float *__restrict__ chk,
                                               int chk_ld, int rounding, int tiles_n, int gw, int nw, int lane) {
   constexpr int J = BN >= 128 ? BN / 128 : 0;   // float4 loads per lane and k-row
@@ -616,7 +630,7 @@ __device__ __forceinline__ void encode_b_warp(const float *__restrict__ B, int N
       for (int u = 0; u < KR; ++u)
 #pragma unroll
         for (int jj = 0; jj < J; ++jj)
-          x[u][jj] = __ldg(reinterpret_cast<const float4 *>(B + static_cast<size_t>(k0 + u) * ldb + n0) + lane + 32 * jj);
+          x[u][jj] = ld_b16<STREAM>(reinterpret_cast<const float4 *>(B + static_cast<size_t>(k0 + u) * ldb + n0) + lane + 32 * jj);
 #pragma unroll
       for (int u = 0; u < KR; ++u) {
         float e = 0.0f, w = 0.0f;
@@ -980,7 +994,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       } else if (FT && tc.is_chk) {
         // checksum tile-column: publish R = A * [e, w]^T for these 128 rows, then raise the slab flag
         const int n_hi = min(p.n_chk_cols, n0 + chk_cols_per_tile(BN));  // columns beyond belong to the next item
-        store_tile<BN>(taddr, p.chk_out + m, m < p.M, n0, n_hi, p.M, 1.0f, 0.0f);
+        store_tile<BN>(taddr, p.chk_out + m, m < p.M, n0, n_hi, p.M, 1.0f, 0.0f, 0, (n_hi - n0 + 31) / 32);
         __threadfence();
         __syncwarp();
         if (lane == 0) atomicExch(p.chk_flags + ((m0_cta >> 5) + q) * p.tiles_c + tc.n_blk, p.chk_epoch);
@@ -1146,13 +1160,13 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kEncWarps = 8;
 
-template <int BN, int KRQ>
+template <int BN, int KRQ, bool STREAM = false>
 __global__ void __launch_bounds__(kEncWarps * 32, 2)
 encode_b_kernel(const float *__restrict__ B, int N, int K, int ldb, float *__restrict__ chk, int chk_ld, int rounding,
                 int tiles_n) {
   ptx::pdl_wait();               // (a programmatic dependent itself: the predecessor may still be reading the old vectors)
   ptx::pdl_launch_dependents();  // the GEMM kernel may start on SMs as they drain (its checksum items wait for this grid)
-  encode_b_warp<BN, KRQ>(B, N, K, ldb, chk, chk_ld, rounding, tiles_n, blockIdx.x * kEncWarps + (threadIdx.x >> 5),
+  encode_b_warp<BN, KRQ, STREAM>(B, N, K, ldb, chk, chk_ld, rounding, tiles_n, blockIdx.x * kEncWarps + (threadIdx.x >> 5),
                     gridDim.x * kEncWarps, threadIdx.x & 31);
 }
 

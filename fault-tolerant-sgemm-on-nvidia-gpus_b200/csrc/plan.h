@@ -171,6 +171,7 @@ inline double schedule(const PlanInput &in, const Cut &c, Plan *out) {
   return makespan;
 }
 
+
 inline void add_unique(std::vector<int> *v, int x, int lo, int hi) {
   if (x >= lo && x <= hi && std::find(v->begin(), v->end(), x) == v->end()) v->push_back(x);
 }
