@@ -9,8 +9,13 @@ BASELINE.json configs[1]: M=N=K=4096, alpha=1, beta=-1.5 (the reference's timing
 input distribution (utils/utils.cu:23-31).  Inputs are resident in HBM for `value`; `e2e` runs the same step through
 the host-buffer C-ABI call (ftsgemm_run_host) with H2D/D2H inside the timed region.  At N>1 every rank (one process per
 GPU, torchrun) owns one C block of a 2-D block-sharded product (A row-panel x B row-panel -> no operand traffic) and the
-ranks all-reduce their checksum/fault counters over NCCL every step: weak scaling, value = aggregate GFLOPS over the
-max-over-ranks time.
+ranks exchange their device-side fault verdict vectors (ftsgemm_stats_device -> NCCL all-gather, asynchronous, joined
+before the timed region ends) every step: weak scaling, value = aggregate GFLOPS over the max-over-ranks time.
+
+The JSON line also carries: `sweep` (N=1: fused ABFT / own plain kernel / cuBLAS-TF32 for M=N=K=1024..16384, the same
+number of launches per cell, engines interleaved), `strong` (BASELINE.json configs[4]: ONE 32768^3 product on the P x Q
+rank grid, incl. the verdict exchange), `id16` (configs[1] literally: the 128x128x8 tile), `parity` (sampled rows of the
+bench's own result against the CPU oracle, outside the timed regions).
 
 --impl reference times the reference's own CPU SGEMM (cpu_gemm, utils/utils.cu:79-89, compiled unmodified into
 oracle/_ref/libref_utils.so; falls back to the OpenMP oracle port) on the host cores; rank 0 only.
@@ -222,19 +227,35 @@ def _emit(obj):
         os.write(_JSON_FD, line)
 
 
+def fill_ref_dist(t, gen):
+    """Reference input distribution (utils/utils.cu:23-31: magnitude (rand()%10)*0.1, random sign), in place and chunked
+    so that multi-GiB operands need no multi-GiB temporaries."""
+    import torch
+    n = t.numel()
+    step = 1 << 26
+    for i in range(0, n, step):
+        v = t[i:i + step]
+        v.copy_(torch.randint(0, 10, (v.numel(),), generator=gen, device=t.device, dtype=torch.int32))
+        v.mul_(0.1)
+        sgn = torch.randint(0, 2, (v.numel(),), generator=gen, device=t.device, dtype=torch.int32)
+        v.mul_(sgn.float().mul_(2).sub_(1))
+    return t
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--size", type=int, default=4096, help="M=N=K of the block each GPU computes (weak scaling)")
     ap.add_argument("--global-size", type=int, default=0,
-                    help="G > 0: ONE G^3 product sharded over the P x Q rank grid (M = G/P, N = G/Q, K = G per rank; strong "
-                         "scaling, BASELINE.json config 5: --gpus 8 --global-size 32768)")
+                    help="G > 0: the headline itself is ONE G^3 product sharded over the P x Q rank grid (strong scaling)")
+    ap.add_argument("--strong-size", type=int, default=32768,
+                    help="G of the `strong` sub-record (BASELINE.json configs[4]; 0 = skip)")
     ap.add_argument("--id", type=int, default=31, help="fused ABFT kernel id (31 = 256x256 CTA-pair tile, 16 = literal huge 128x128)")
-    ap.add_argument("--sweep", action="store_true", help="also print the README-style table 1024..16384 to stderr")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the 1024..16384 sweep (N=1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -249,38 +270,26 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=dev)
 
-    n = args.size
-    M = N = K = n
+    from importlib import import_module
+    sharding = import_module("ftsgemm_b200.sharding")
+    P, Q = sharding.shard_grid(world)
     alpha, beta = 1.0, -1.5
     W = max(args.warmup, 3)
-    steps = args.steps
-    # 2-D block sharding of a (P*n) x (Q*n) product over the ranks: rank (p,q) owns A row-panel p, B row-panel q, C block
-    # (P x Q from the package's own sharding helper: 1x1, 1x2, 2x2, 2x4)
-    from importlib import import_module
-    P, Q = import_module("ftsgemm_b200.sharding").shard_grid(world)
-    if args.global_size > 0:
-        G = args.global_size
-        if G % (P * 256) or G % (Q * 256):
-            raise SystemExit("--global-size must be a multiple of 256 * the rank grid")
-        M, N, K = G // P, G // Q, G
+    steps = max(1, args.steps)
     g = torch.Generator(device="cuda").manual_seed(1234 + rank)
-
-    def ref_dist(count):
-        return (torch.randint(0, 10, (count,), generator=g, device="cuda").float() * 0.1) * \
-               (torch.randint(0, 2, (count,), generator=g, device="cuda").float() * 2 - 1)
-
-    dA, dB = ref_dist(M * K), ref_dist(N * K)
-    dC = torch.zeros(M * N, device="cuda")
     ft = pkg.FtSgemm()
     stream = torch.cuda.current_stream().cuda_stream
     opts = pkg.make_opts(stream=stream)
     opts_reuse = pkg.make_opts(stream=stream, reuse_b_checksums=True)
-    stat_vec = torch.zeros(4, device="cuda", dtype=torch.float64)
+    o_cmp = pkg.make_opts(stream=stream, baseline_host_sync=True)
+    names = {k["id"]: k for k in pkg.kernel_table()}
+    launches = {"n": 0}
 
     def sync_all():
         torch.cuda.synchronize()
@@ -288,12 +297,15 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, nsteps):
+    def timed(fn, nsteps, after=None):
+        """nsteps calls between two CUDA events on the launching stream, barrier + synchronize on both sides, MAX over ranks."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync_all()
         e0.record()
         for _ in range(nsteps):
             fn()
+        if after is not None:
+            after()
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -304,76 +316,196 @@ def main():
             dist.barrier()
         return ms
 
-    def step_ft():
-        ft.run(args.id, M, N, K, dA, dB, dC, alpha, beta, opts)
-        if dist is not None:  # the one exchange step of the sharded path: agree on the fault verdict
-            dist.all_reduce(stat_vec)
+    def gflops(M, N, K, ms):
+        return 2.0 * M * N * K / (ms * 1e-3) / 1e9
 
-    def reset_c():
-        dC.zero_()
+    class Problem:
+        """Operands of one block resident in HBM + the engines timed on them."""
+        def __init__(self, M, N, K):
+            self.M, self.N, self.K = M, N, K
+            self.dA = fill_ref_dist(torch.empty(M * K, device="cuda"), g)
+            self.dB = fill_ref_dist(torch.empty(N * K, device="cuda"), g)
+            self.dC = torch.zeros(M * N, device="cuda")
 
-    plain_id = {31: 21, 32: 22}.get(args.id, args.id - 10)
-    o_cmp = pkg.make_opts(stream=stream, baseline_host_sync=True)
+        def run(self, kid, o):
+            ft.run(kid, self.M, self.N, self.K, self.dA, self.dB, self.dC, alpha, beta, o)
 
-    def run_cmp(kid, nsteps):
-        reset_c()
-        for _ in range(2):
-            ft.run(kid, M, N, K, dA, dB, dC, alpha, beta, o_cmp)
-        ms = timed(lambda: ft.run(kid, M, N, K, dA, dB, dC, alpha, beta, o_cmp), nsteps) / nsteps
-        return flops_per_step / (ms * 1e-3) / 1e9
+        def time_engine(self, kid, nsteps, o=None, warm=2):
+            o = o or o_cmp
+            self.dC.zero_()
+            for _ in range(warm):
+                self.run(kid, o)
+            ms = timed(lambda: self.run(kid, o), nsteps) / nsteps
+            return gflops(self.M, self.N, self.K, ms)
 
+    # ------------------------------------------------------------------ headline problem
+    n = args.size
+    M = N = K = n
+    if args.global_size > 0:
+        G = args.global_size
+        if G % (P * 256) or G % (Q * 256):
+            raise SystemExit("--global-size must be a multiple of 256 * the rank grid")
+        M, N, K = G // P, G // Q, G
+    prob = Problem(M, N, K)
     flops_per_step = 2.0 * M * N * K
-    # ---- the bar, measured with the same number of steps right BEFORE and right AFTER the headline region: the GPU is
-    #      power-limited in long runs (SM clock 1.9 -> 1.4-1.7 GHz after ~0.1 s), so a ratio is only meaningful between
-    #      runs of the same length in the same thermal state
+    plain_id = {31: 21, 32: 22}.get(args.id, args.id - 10)
+
+    # the one exchange step of the sharded path: every rank's device-side verdict vector to every rank
+    exch = sharding.VerdictExchange(lambda buf: ft.stats_device(buf, stream), dist, dev) if dist is not None else None
+
+    def step_ft():
+        prob.run(args.id, opts)
+        if exch is not None:
+            exch.step()
+
     comp = {}
-    cublas_before = run_cmp(7, steps)
-    # ---- warm-up + the timed region of the headline number
-    for _ in range(W):
-        step_ft()
-    reset_c()
+    cublas_before = prob.time_engine(7, steps)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
+    prob.dC.zero_()
+    for _ in range(W):  # warm-up directly in front of the timed region (the clocks ramp down during any idle gap)
+        step_ft()
+    if exch is not None:
+        exch.join()
+    ft.stats()  # counters from here on belong to the timed region
     t_wall0 = time.time()
-    ms_total = timed(step_ft, steps)
+    ms_total = timed(step_ft, steps, after=(exch.join if exch is not None else None))
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    verdict = exch.verdict() if exch is not None else None
     st = ft.stats()
     ms_step = ms_total / steps
-    flops = flops_per_step
-    value = world * flops / (ms_step * 1e-3) / 1e9
-    comp["plain"] = run_cmp(plain_id, steps)
-    cublas_after = run_cmp(7, steps)
+    value = world * flops_per_step / (ms_step * 1e-3) / 1e9
+    comp["plain"] = prob.time_engine(plain_id, steps)
+    cublas_after = prob.time_engine(7, steps)
     comp["cublas_tf32"] = 0.5 * (cublas_before + cublas_after)
-    comp["cublas_tf32_before_after"] = [round(cublas_before, 1), round(cublas_after, 1)]
-
-    # ---- dominant kernel alone (checksum panel reused -> no encode launch), same event method
-    reset_c()
-    k_steps = steps
-    k_ms = timed(lambda: ft.run(args.id, M, N, K, dA, dB, dC, alpha, beta, opts_reuse), k_steps) / k_steps
-    # ---- further comparators on the same buffers: non-fused baseline, cuBLAS FP32 (short runs: 20-40x slower engines)
+    # dominant kernel alone (checksum vectors reused -> no encode launch), same event method
+    k_gf = prob.time_engine(args.id, steps, o=opts_reuse)
+    k_ms = flops_per_step / (k_gf * 1e9) * 1e3
     for name, kid, reps in (("cublas_fp32", 0, 5), ("abft_baseline_tf32", 30, 2), ("abft_baseline", 10, 2)):
-        comp[name] = run_cmp(kid, reps)
+        comp[name] = prob.time_engine(kid, reps, warm=1)
+    ft.stats()
+    expected_rows = steps * M * (-(-N // names[args.id]["tile"][1]))
+    if st["rows_checked"] != expected_rows:
+        raise SystemExit(f"rank {rank}: rows_checked {st['rows_checked']} != {expected_rows}: the ABFT check did not run on every tile")
+    if verdict is not None and verdict["rows_checked"] != world * expected_rows:
+        raise SystemExit(f"verdict exchange: world-summed rows_checked {verdict['rows_checked']} != {world * expected_rows}")
+
+    # ------------------------------------------------------------------ BASELINE.json configs[1] literally: id 16 (128x128x8)
+    id16 = None
+    if args.id != 16 and args.global_size == 0:
+        s16 = min(steps, 50)
+        id16 = {"abft_kernel_huge_gflops": round(prob.time_engine(16, s16, o=opts), 1),
+                "kernel_sgemm_huge_gflops": round(prob.time_engine(6, s16), 1), "steps": s16,
+                "note": "BASELINE.json configs[1] literally (tile 128x128, one CTA per tile); the headline uses the CTA-pair tile 256x256"}
+        id16["overhead_pct_vs_cublas_tf32"] = round(100.0 * (comp["cublas_tf32"] / id16["abft_kernel_huge_gflops"] - 1.0), 2)
+        ft.stats()
+
+    # ------------------------------------------------------------------ parity of the bench's own result (outside timing)
+    parity = None
+    if rank == 0:
+        from oracle import oracle as O
+        hA, hB = prob.dA.cpu().numpy(), prob.dB.cpu().numpy()
+        prob.dC.zero_()
+        ft.run(args.id, M, N, K, prob.dA, prob.dB, prob.dC, 1.0, 0.0, opts)
+        got = prob.dC.cpu().numpy().reshape(N, M).T  # column-major M x N -> [m, n]
+        rows = np.linspace(0, M - 1, 24 if K <= 8192 else 6).astype(np.int32)
+        want = O.sgemm_nt_rows(M, N, K, 1.0, hA, hB, 0.0, None, rows)
+        num = float(np.sum((want.astype(np.float64) - got[rows].astype(np.float64)) ** 2))
+        den = float(np.sum(want.astype(np.float64) ** 2))
+        parity = {"rel_fro": float(np.sqrt(num / den)), "rows": int(len(rows)), "cols": int(N), "K": int(K), "tolerance": 1e-3,
+                  "oracle": "oracle_sgemm_nt_rows (port of cpu_gemm, utils/utils.cu:79-89: sequential-k fp32)",
+                  "ok": bool(np.sqrt(num / den) < 1e-3)}
+        if not parity["ok"]:
+            raise SystemExit(f"parity check failed: {parity}")
+        del hA, hB
     ft.stats()
 
-    # ---- e2e: the host-buffer C-ABI call, pinned host memory, H2D(A,B,C) + kernel + D2H(C) inside the timed region
-    hA = torch.empty(M * K, dtype=torch.float32).pin_memory(); hA.copy_(dA)
-    hB = torch.empty(N * K, dtype=torch.float32).pin_memory(); hB.copy_(dB)
+    # ------------------------------------------------------------------ e2e: host buffers through the C ABI
+    hA = torch.empty(M * K, dtype=torch.float32).pin_memory(); hA.copy_(prob.dA)
+    hB = torch.empty(N * K, dtype=torch.float32).pin_memory(); hB.copy_(prob.dB)
     hC = torch.zeros(M * N, dtype=torch.float32).pin_memory()
     e2e_steps = max(3, min(steps, 8))
 
     def step_e2e():
         ft.run_host(args.id, M, N, K, hA.data_ptr(), hB.data_ptr(), hC.data_ptr(), alpha, beta, opts)
-        if dist is not None:
-            dist.all_reduce(stat_vec)
+        if exch is not None:
+            exch.step()
 
     step_e2e()
     hC.zero_()
-    e2e_ms = timed(step_e2e, e2e_steps) / e2e_steps
-    e2e_val = world * flops / (e2e_ms * 1e-3) / 1e9
+    e2e_ms = timed(step_e2e, e2e_steps, after=(exch.join if exch is not None else None)) / e2e_steps
+    e2e_val = world * flops_per_step / (e2e_ms * 1e-3) / 1e9
     result_ok = bool(torch.isfinite(hC).all())
+    del hA, hB, hC
+    ft.stats()
+
+    # ------------------------------------------------------------------ sweep 1024..16384 (N = 1)
+    sweep = None
+    if world == 1 and not args.no_sweep and args.global_size == 0:
+        del prob
+        torch.cuda.empty_cache()
+        sweep = []
+        cell = min(steps, 20)
+        big = Problem(16384, 16384, 16384)
+        for s in range(1024, 16385, 1024):
+            sub = Problem.__new__(Problem)
+            sub.M = sub.N = sub.K = s
+            sub.dA, sub.dB, sub.dC = big.dA, big.dB, big.dC
+            res = {"abft": [], "plain": [], "cublas_tf32": []}
+            for _ in range(3):  # engines interleaved, idle gaps in between: every cell in the same clock state
+                for key, kid, o in (("cublas_tf32", 7, o_cmp), ("abft", 31, opts), ("plain", 21, o_cmp)):
+                    time.sleep(0.02)
+                    res[key].append(sub.time_engine(kid, cell, o=o, warm=3))
+            med = {k: statistics.median(v) for k, v in res.items()}
+            sweep.append({"n": s, "abft_id": 31, "steps": cell, "abft_gflops": round(med["abft"], 1),
+                          "plain_gflops": round(med["plain"], 1), "cublas_tf32_gflops": round(med["cublas_tf32"], 1),
+                          "overhead_pct_vs_cublas_tf32": round(100.0 * (med["cublas_tf32"] / med["abft"] - 1.0), 2),
+                          "overhead_pct_vs_own_plain_kernel": round(100.0 * (med["plain"] / med["abft"] - 1.0), 2)})
+        ft.stats()
+        del big, sub
+        torch.cuda.empty_cache()
+    else:
+        del prob
+        torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ strong: ONE G^3 product on the P x Q rank grid
+    strong = None
+    G = args.strong_size
+    if G > 0 and G % (P * 256) == 0 and G % (Q * 256) == 0 and args.global_size == 0:
+        Ms, Ns, Ks = G // P, G // Q, G
+        need = 4.0 * (Ms * Ks + Ns * Ks + Ms * Ns)
+        if need < 0.8 * torch.cuda.get_device_properties(local_rank).total_memory:
+            sp = Problem(Ms, Ns, Ks)
+            s_steps = 3
+
+            def step_strong():
+                sp.run(args.id, opts)
+                if exch is not None:
+                    exch.step()
+
+            ft.stats()
+            cb = sp.time_engine(7, s_steps, warm=1)
+            sp.dC.zero_()
+            step_strong()
+            s_ms = timed(step_strong, s_steps, after=(exch.join if exch is not None else None)) / s_steps
+            sv = exch.verdict() if exch is not None else None
+            s_st = ft.stats()
+            s_plain = sp.time_engine(plain_id, s_steps, warm=1)
+            ca = sp.time_engine(7, s_steps, warm=1)
+            s_val = 2.0 * G ** 3 / (s_ms * 1e-3) / 1e9
+            cub = 0.5 * (cb + ca)
+            strong = {"global_size": G, "grid": [P, Q], "block": [Ms, Ns, Ks], "steps": s_steps, "ms_per_step": round(s_ms, 3),
+                      "value": round(s_val, 1), "unit": "GFLOPS", "per_gpu_gflops": round(s_val / world, 1),
+                      "cublas_tf32_gflops_same_block": round(cub, 1), "plain_kernel_gflops_same_block": round(s_plain, 1),
+                      "overhead_pct_vs_cublas_tf32": round(100.0 * (cub / (s_val / world) - 1.0), 2),
+                      "roofline_frac": round(s_val / world / 1e3 / (_peaks()["bf16_tflops"] / 2.0), 4),
+                      "rows_checked": (sv or s_st)["rows_checked"], "detected": (sv or s_st)["detected"],
+                      "includes": "encode pre-pass + GEMM" + (" + verdict exchange (NCCL all-gather of the device-side vectors)" if world > 1 else "")}
+            del sp
+            torch.cuda.empty_cache()
 
     if rank != 0:
         if dist is not None:
@@ -381,8 +513,12 @@ def main():
         return
     peaks = _peaks()
     tf32_peak = peaks["bf16_tflops"] / 2.0  # kind::tf32 issues at half the kind::f16 rate on tcgen05
-    achieved = flops / (k_ms * 1e-3) / 1e12
-    info = [k for k in pkg.kernel_table() if k["id"] == args.id][0]
+    achieved = flops_per_step / (k_ms * 1e-3) / 1e12
+    info = names[args.id]
+    region_ms = ms_total
+    capped = bool(clocks and "sw_power_cap" in (clocks.get("reasons") or []))
+    at_boost = bool(clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"])
+    regime = "power-capped (sw_power_cap sampled)" if capped else ("boost clocks, no throttle reason sampled" if at_boost else "below boost clocks")
     out = {
         "metric": METRIC if (n == 4096 and args.global_size == 0) else
                   METRIC.replace("M=N=K=4096", f"one {args.global_size}^3 product" if args.global_size > 0 else f"M=N=K={n}"),
@@ -393,13 +529,16 @@ def main():
         "config": {"workload": f"fused ABFT SGEMM id {args.id} ({info['name']}, tile {info['tile'][0]}x{info['tile'][1]}), "
                                + (f"one {args.global_size}^3 product, block M={M} N={N} K={K} per GPU" if args.global_size > 0 else f"M=N=K={n} per GPU")
                                + ", alpha=1, beta=-1.5 (sgemm.cu:22,234), reference input distribution",
-                   "sharding": f"{P}x{Q} C-block grid, A/B row-panels resident per GPU, NCCL all-reduce of fault counters per step" if world > 1 else "single GPU",
+                   "sharding": (f"{P}x{Q} C-block grid, A/B row-panels resident per GPU; per step every rank's device-side verdict "
+                                f"vector (ftsgemm_stats_device) is all-gathered over NCCL, asynchronously, joined inside the timed region")
+                               if world > 1 else "single GPU",
                    "l2": (f"inputs {4 * (M * K + N * K + M * N) / 2**20:.0f} MiB per step vs 126 MB L2: larger than L2, no flush needed"
                           if 4 * (M * K + N * K + M * N) > 160e6 else "L2-resident working set (small size)"),
                    "baseline_note": "vs_baseline = per-GPU value / 4005 GFLOPS (README.md:53 abft_kernel_huge @4096, GPU unspecified)"},
         "abft": {"overhead_pct_vs_cublas_tf32": round(100.0 * (comp["cublas_tf32"] / (value / world) - 1.0), 2),
                  "overhead_pct_vs_own_plain_kernel": round(100.0 * (comp["plain"] / (value / world) - 1.0), 2),
-                 "cublas_tf32_gflops": round(comp["cublas_tf32"], 1), "cublas_tf32_gflops_before_after": comp["cublas_tf32_before_after"],
+                 "cublas_tf32_gflops": round(comp["cublas_tf32"], 1),
+                 "cublas_tf32_gflops_before_after": [round(cublas_before, 1), round(cublas_after, 1)],
                  "comparator_steps": steps, "cublas_fp32_gflops": round(comp["cublas_fp32"], 1),
                  "plain_kernel_gflops": round(comp["plain"], 1), "abft_baseline_gflops": round(comp["abft_baseline"], 1),
                  "abft_baseline_tf32_gflops": round(comp["abft_baseline_tf32"], 1),
@@ -408,42 +547,34 @@ def main():
                  "max_abs_residual": st["max_abs_residual"], "max_rel_residual": st["max_rel_residual"]},
         "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
                      "frac": round(achieved / tf32_peak, 4), "traffic": None,
-                     "peak_sustained": round(peaks["bf16_tflops_sustained"] / 2.0, 1),
-                     "frac_of_sustained": round(achieved / (peaks["bf16_tflops_sustained"] / 2.0), 4),
-                     "note": f"kernel ftsgemm_tc_kernel alone (encode reused), 2*M*N*K per launch / CUDA-event mean over {k_steps} "
-                             f"back-to-back launches; peak = bf16 burst {peaks['bf16_tflops']} / 2 (kind::tf32 issues at half the "
-                             f"kind::f16 rate), {peaks['src']}; the launches run in the power-limited regime, for which the "
-                             f"sustained figure {peaks['bf16_tflops_sustained']} / 2 is the like-for-like bound (frac_of_sustained)"},
+                     "regime": regime, "timed_region_ms": round(region_ms, 3),
+                     "note": f"kernel ftsgemm_tc_kernel alone (checksum vectors reused: no encode launch), 2*M*N*K per launch / "
+                             f"CUDA-event mean over {steps} back-to-back launches; peak = bf16 burst {peaks['bf16_tflops']} / 2 "
+                             f"(kind::tf32 issues at half the kind::f16 rate; no TF32 peak is measured), {peaks['src']}; "
+                             f"clocks during the headline region: {regime}"},
         "e2e": {"value": round(e2e_val, 1), "unit": "GFLOPS", "h2d_bytes_per_step": 4 * (M * K + N * K + M * N), "d2h_bytes_per_step": 4 * M * N,
                 "steps": e2e_steps, "finite": result_ok},
-        "gpu_launches": 2 * steps,  # encode_b_kernel + ftsgemm_tc_kernel per step
+        "gpu_launches": (2 + (1 if world > 1 else 0)) * steps,  # encode_b_kernel + ftsgemm_tc_kernel (+ stats_vector_kernel) per step
         "clocks": clocks,
+        "parity": parity,
     }
+    if verdict is not None:
+        out["verdict"] = {k: verdict[k] for k in ("tiles", "rows_checked", "detected", "corrected", "uncorrectable", "clean")}
+    if id16 is not None:
+        out["id16"] = id16
+    if sweep is not None:
+        out["sweep"] = sweep
+    if strong is not None:
+        out["strong"] = strong
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
         try:
-            out["roofline"]["traffic"] = json.loads(tp.read_text()).get(str(args.id))
+            t = json.loads(tp.read_text()).get(str(args.id))
+            out["roofline"]["traffic"] = t.get(str(n)) if isinstance(t, dict) else (t if n == 4096 else None)
         except Exception:
             pass
-    if not args.no_cpu and world >= 1:
+    if not args.no_cpu and world == 1:  # (rank 0 at N = 1 only: torchrun pins OMP_NUM_THREADS=1)
         out["cpu_baseline"] = _cpu_port_baseline(n if n <= 4096 else 4096)
-    if args.sweep:
-        sizes = [s for s in range(1024, 16385, 1024) if 3 * 4 * s * s < 60e9]
-        ids = [0, 7, 2, 6, 5, 21, 12, 16, 15, 31]
-        sys.stderr.write("Matrix Size         |" + "".join(f"{s:8d}|" for s in sizes) + "\n")
-        names = {k["id"]: k["name"] for k in pkg.kernel_table()}
-        big = max(sizes)
-        bA, bB, bC = ref_dist(big * big), ref_dist(big * big), torch.zeros(big * big, device="cuda")
-        for kid in ids:
-            row = f"{names[kid]:<20s}|"
-            for s in sizes:
-                bC.zero_()
-                for _ in range(2):
-                    ft.run(kid, s, s, s, bA, bB, bC, alpha, beta, opts)
-                reps = 10 if s <= 4096 else 3
-                ms = timed(lambda: ft.run(kid, s, s, s, bA, bB, bC, alpha, beta, opts), reps) / reps
-                row += f"{2.0 * s ** 3 / ms / 1e6:8.0f}|"
-            sys.stderr.write(row + "\n")
     _emit(out)
     if dist is not None:
         dist.destroy_process_group()

@@ -81,7 +81,7 @@ EXPORTED_SYMBOLS = [
     "ftsgemm_create", "ftsgemm_destroy", "ftsgemm_abi_version", "ftsgemm_error_string", "ftsgemm_last_cuda_error",
     "ftsgemm_default_opts", "ftsgemm_kernel_table", "ftsgemm_kernel_lookup", "ftsgemm_run", "ftsgemm_get_stats",
     "ftsgemm_run_host", "ftsgemm_baseline", "ftsgemm_verify", "ftsgemm_debug_set", "ftsgemm_debug_schedule",
-    "ftsgemm_verify_bad_count", "ftsgemm_debug_trace",
+    "ftsgemm_verify_bad_count", "ftsgemm_debug_trace", "ftsgemm_stats_device",
 ]
 
 _lib = None
@@ -116,6 +116,7 @@ def lib():
         L.ftsgemm_run.argtypes = [vp, ip, ip, ip, ip, vp, vp, vp, fp, fp, C.POINTER(Opts)]
         L.ftsgemm_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.ftsgemm_run_host.argtypes = [vp, ip, ip, ip, ip, vp, vp, vp, fp, fp, C.POINTER(Opts)]
+        L.ftsgemm_stats_device.argtypes = [vp, vp, vp]
         L.ftsgemm_baseline.argtypes = [vp, ip, ip, ip, vp, vp, vp, fp, fp, ip, C.POINTER(Opts), vp]
         L.ftsgemm_verify.argtypes = [vp, vp, vp, ip, ip, C.POINTER(C.c_longlong), C.POINTER(C.c_double), vp]
         L.ftsgemm_debug_set.argtypes = [C.c_char_p, C.c_longlong]
@@ -247,6 +248,10 @@ class FtSgemm:
         s = Stats()
         self._run_checked(lib().ftsgemm_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def stats_device(self, d_out8, stream=None) -> None:
+        """Device-side verdict vector (8 doubles, see include/ftsgemm.h), asynchronous on `stream`, counters not reset."""
+        self._run_checked(lib().ftsgemm_stats_device(self._h, _ptr(d_out8), stream))
 
     def debug_trace(self):
         """Timeline of the last launch made under debug_set("trace", 1): list (per unit) of item dicts, times in ns."""

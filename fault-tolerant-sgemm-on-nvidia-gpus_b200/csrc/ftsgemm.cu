@@ -645,6 +645,20 @@ __global__ void fill_kernel(float *p, float v, size_t n) {
   if (i < n) p[i] = v;
 }
 
+// fault verdict of the launches since the last ftsgemm_get_stats, as 8 doubles in device memory (ftsgemm_stats_device)
+__global__ void stats_vector_kernel(const DeviceStats *st, double *out) {
+  if (threadIdx.x == 0) {
+    out[0] = static_cast<double>(st->tiles);
+    out[1] = static_cast<double>(st->rows_checked);
+    out[2] = static_cast<double>(st->detected);
+    out[3] = static_cast<double>(st->corrected);
+    out[4] = static_cast<double>(st->uncorrectable);
+    out[5] = static_cast<double>(st->checksum_faults);
+    out[6] = static_cast<double>(__uint_as_float(st->max_abs_bits));
+    out[7] = static_cast<double>(__uint_as_float(st->max_rel_bits));
+  }
+}
+
 // verify_matrix (utils/utils.cu:61-77) on the device: smallest failing index + Frobenius sums
 __global__ void verify_kernel(const float *ref, const float *x, size_t n, unsigned long long *first_bad, double *num,
                               double *den, unsigned long long *bad_count) {
@@ -888,6 +902,16 @@ int ftsgemm_get_stats(ftsgemm_handle_t h, ftsgemm_stats *out) {
     out->events[i].corrected_value = ds.events[i].corrected_value;
     out->events[i].status = ds.events[i].status;
   }
+  return FTSGEMM_OK;
+}
+
+int ftsgemm_stats_device(ftsgemm_handle_t h, double *d_out8, void *stream_v) {
+  if (!h) return FTSGEMM_ERR_NO_DEVICE;
+  if (!d_out8) return FTSGEMM_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  stats_vector_kernel<<<1, 32, 0, stream>>>(h->d_stats, d_out8);
+  FT_CUDA(h, cudaGetLastError());
   return FTSGEMM_OK;
 }
 

@@ -4,9 +4,11 @@ reference is single-GPU: sgemm.cu:34).
 Output tiles are independent in the reference (every CTA owns one C tile and its checksums,
 ft_sgemm_huge.cuh:37-41,573-574), so C is split into a P x Q grid of blocks: rank (p, q) keeps the A row-panel
 A[I_p, :] (M/P x K), the B row-panel B[J_q, :] (N/Q x K) and its C block resident; no operand moves during the
-product.  The one exchange step is a small all-reduce (NCCL on GPUs, gloo in the CPU tests) of the fault verdict:
-[tiles, rows_checked, detected, corrected, uncorrectable, checksum_faults] summed and the residual maxima max-ed,
-so that every rank agrees whether the distributed product is clean.
+product.  The one exchange step is the fault verdict: [tiles, rows_checked, detected, corrected, uncorrectable,
+checksum_faults] summed and the residual maxima max-ed over the ranks, so that every rank agrees whether the
+distributed product is clean.  Two forms: `allreduce_verdict` (host dicts, synchronous) and `VerdictExchange`
+(the device-side vectors of ftsgemm_stats_device, one asynchronous all-gather per step: NCCL on GPUs, gloo in the CPU
+tests), which keeps the collective off the GEMM's critical path.
 """
 from __future__ import annotations
 
@@ -56,3 +58,52 @@ def allreduce_verdict(stats: dict, dist, device=None) -> dict:
     out.update({k: float(v) for k, v in zip(STAT_KEYS_MAX, m.tolist())})
     out["clean"] = out["detected"] == out["corrected"] and out["uncorrectable"] == 0
     return out
+
+
+class VerdictExchange:
+    """Per-step exchange of every rank's device-side verdict vector (8 doubles, include/ftsgemm.h:
+    ftsgemm_stats_device): `step()` snapshots the local counters into a slot (on the launching stream, right behind the
+    GEMM it reports on) and starts ONE all-gather of that slot, asynchronously -- the collective runs on the backend's
+    own stream behind the snapshot, the next GEMM is not ordered after it; `join()` makes the launching stream wait for
+    every outstanding exchange (called before a timed region ends); `verdict()` reduces the last gathered vectors on the
+    host: counters summed, residual maxima max-ed.
+
+    fill(buf) writes the local vector into `buf` (a float64 tensor of 8): FtSgemm.stats_device on GPUs, any callable in
+    the CPU tests."""
+
+    SLOTS = 4
+
+    def __init__(self, fill, dist, device=None):
+        import torch
+        self.fill, self.dist = fill, dist
+        self.world = dist.get_world_size()
+        self.local = [torch.zeros(8, dtype=torch.float64, device=device) for _ in range(self.SLOTS)]
+        self.gathered = [torch.zeros(self.world * 8, dtype=torch.float64, device=device) for _ in range(self.SLOTS)]
+        self.work = [None] * self.SLOTS
+        self.n = 0
+        self.last = None
+
+    def step(self):
+        s = self.n % self.SLOTS
+        if self.work[s] is not None:  # the slot's previous exchange (SLOTS steps ago) must be over before it is rewritten
+            self.work[s].wait()
+        self.fill(self.local[s])
+        self.work[s] = self.dist.all_gather_into_tensor(self.gathered[s], self.local[s], async_op=True)
+        self.last = s
+        self.n += 1
+
+    def join(self):
+        for w in self.work:
+            if w is not None:
+                w.wait()
+        self.work = [None] * self.SLOTS
+
+    def verdict(self) -> dict:
+        """Reduced verdict of the most recent exchange (join() first)."""
+        self.join()
+        v = self.gathered[self.last].reshape(self.world, 8).cpu()
+        out = {k: int(v[:, i].sum().item()) for i, k in enumerate(STAT_KEYS_SUM)}
+        out.update({k: float(v[:, 6 + i].max().item()) for i, k in enumerate(STAT_KEYS_MAX)})
+        out["clean"] = out["detected"] == out["corrected"] and out["uncorrectable"] == 0
+        out["per_rank_rows_checked"] = [int(x) for x in v[:, 1].tolist()]
+        return out

@@ -155,6 +155,13 @@ int ftsgemm_run(ftsgemm_handle_t h, int kernel_id, int M, int N, int K, const fl
 /* Counters of all FT launches since the previous call (synchronises the handle's last stream, then resets). */
 int ftsgemm_get_stats(ftsgemm_handle_t h, ftsgemm_stats *out);
 
+/* The same counters as a device-side vector, asynchronously on `stream` and WITHOUT resetting them: d_out8 (device
+ * memory, 8 doubles) = {tiles, rows_checked, detected, corrected, uncorrectable, checksum_faults, max_abs_residual,
+ * max_rel_residual} of all FT launches since the previous ftsgemm_get_stats.  This is the vector the tile-sharded
+ * multi-GPU path exchanges (NCCL all-gather / all-reduce on the same stream) so that every rank agrees on the fault
+ * verdict of a distributed product without a host round trip (new work: the reference is single-GPU, sgemm.cu:34). */
+int ftsgemm_stats_device(ftsgemm_handle_t h, double *d_out8, void *stream);
+
 /* Same contract with HOST buffers: H2D of A, B (and C when beta != 0), the kernel, D2H of C, synchronous.
  * This is the call the e2e benchmark times.  Device staging buffers are cached on the handle. */
 int ftsgemm_run_host(ftsgemm_handle_t h, int kernel_id, int M, int N, int K, const float *hA, const float *hB,

@@ -56,6 +56,21 @@ def _worker(rank, world, port, q):
     stats = {"tiles": (mb // 128) * (nb // 128), "rows_checked": mb * (nb // 128), "detected": rank, "corrected": rank,
              "uncorrectable": 0, "checksum_faults": 0, "max_abs_residual": 1e-4 * (rank + 1), "max_rel_residual": 1e-7}
     verdict = sh.allreduce_verdict(stats, dist)
+    # the per-step device-vector form (CPU tensors + gloo here; ftsgemm_stats_device + NCCL on GPUs)
+    vec = [float(stats[k]) for k in sh.STAT_KEYS_SUM] + [float(stats[k]) for k in sh.STAT_KEYS_MAX]
+    steps_done = {"n": 0}
+
+    def fill(buf):
+        steps_done["n"] += 1
+        buf.copy_(torch.tensor(vec, dtype=torch.float64) * torch.tensor([steps_done["n"]] * 6 + [1, 1], dtype=torch.float64))
+
+    ex = sh.VerdictExchange(fill, dist)
+    for _ in range(6):  # more steps than slots: slots are recycled
+        ex.step()
+    v2 = ex.verdict()
+    assert v2["rows_checked"] == 6 * verdict["rows_checked"] and v2["detected"] == 6 * verdict["detected"]
+    assert abs(v2["max_abs_residual"] - verdict["max_abs_residual"]) < 1e-15 and v2["clean"] == verdict["clean"]
+    assert len(v2["per_rank_rows_checked"]) == world
     blocks = [None] * world
     dist.all_gather_object(blocks, (e, Cb))
     if rank == 0:
