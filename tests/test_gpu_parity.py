@@ -54,7 +54,7 @@ def _rand(rng, count):
 
 # ------------------------------------------------------------------ golden fixtures (reference inputs, END = n)
 @pytest.mark.parametrize("n", [256, 512, 1024])
-@pytest.mark.parametrize("name", ["small", "medium", "large", "tall", "wide", "huge"])
+@pytest.mark.parametrize("name", ["small", "medium", "large", "tall", "wide", "huge", "giant", "pair128"])
 def test_reference_inputs_vs_golden_and_oracle(cuda, ft, dev, oracle, n, name):
     import hashlib
     A, B, C0 = oracle.make_inputs(n)
@@ -72,7 +72,7 @@ def test_reference_inputs_vs_golden_and_oracle(cuda, ft, dev, oracle, n, name):
         scale = float(np.sqrt(np.mean(want.astype(np.float64) ** 2)))
         for idx, v in GOLD[str(n)]["C_sel"].items():
             assert abs(float(got[int(idx)]) - v) < 5e-3 * scale
-    if name == "huge":  # fault-free FT run must not flag anything
+    if name in ("huge", "giant"):  # fault-free FT run must not flag anything
         st = dev.stats()
         assert st["detected"] == 0 and st["rows_checked"] > 0
 
@@ -283,6 +283,45 @@ def test_unsupported_and_invalid_args(cuda, ft, dev):
     with pytest.raises(ft.FtsgemmError) as e:
         dev.run(16, 64, 64, 0, t, t, t)
     assert e.value.code == -1
+    # options: a zero-initialised struct (struct_size 0) is rejected, not read as "all defaults on the default stream";
+    # negative self-test coordinates are rejected instead of indexing outside the tile's tensor-memory columns
+    o = ft.Opts()
+    with pytest.raises(ft.FtsgemmError) as e:
+        dev.run(16, 64, 64, 64, t, t, t, 1.0, 0.0, o)
+    assert e.value.code == -1
+    for sel in ((10000.0, -1, 0), (10000.0, 0, -5)):
+        with pytest.raises(ft.FtsgemmError) as e:
+            dev.run(16, 64, 64, 64, t, t, t, 1.0, 0.0, ft.make_opts(selftest=sel))
+        assert e.value.code == -1
+    dev.run(16, 64, 64, 64, t, t, t, 1.0, 0.0, ft.make_opts(selftest=(10000.0, 17, 5)))  # (valid options still run)
+    cuda.cuda.synchronize()
+    dev.stats()
+
+
+def test_handle_is_bound_to_its_device_and_scaled_inputs(cuda, ft, dev, oracle):
+    """(1) A second handle (its own workspace, shared-memory attribute cached per handle) gives the same result.
+    (2) Detection threshold and operand scale: thr = tau_abs + tau_rel * sum|acc| with tau_abs calibrated for operands of
+    magnitude ~1 (include/ftsgemm.h); for operands scaled by s the caller scales tau_abs by s^2 -- with that, an upset of
+    the same RELATIVE size is detected and repaired at 1e-3 and 1e3 times the reference magnitude."""
+    rng = np.random.default_rng(77)
+    M, N, K = 512, 512, 512
+    A, B = _rand(rng, M * K), _rand(rng, N * K)
+    C0 = np.zeros(M * N, np.float32)
+    base = _run(cuda, dev, 31, M, N, K, A, B, C0)
+    h2 = ft.FtSgemm()
+    try:
+        assert np.array_equal(_run(cuda, h2, 31, M, N, K, A, B, C0), base)
+    finally:
+        h2.close()
+    for s in (1e-3, 1e3):
+        As, Bs = (A * np.float32(s)).astype(np.float32), (B * np.float32(s)).astype(np.float32)
+        clean = _run(cuda, dev, 31, M, N, K, As, Bs, C0, opts=ft.make_opts(tau_abs=1e-3 * s * s))
+        dev.stats()
+        fixed = _run(cuda, dev, 31, M, N, K, As, Bs, C0,
+                     opts=ft.make_opts(tau_abs=1e-3 * s * s, faults=[{"row": 100, "col": 200, "add": 50.0 * s * s}]))
+        st = dev.stats()
+        assert st["detected"] == 1 and st["corrected"] == 1, (s, st)
+        assert np.allclose(fixed, clean, rtol=0, atol=2e-3 * s * s)
 
 
 # ------------------------------------------------------------------ cuBLAS rows and the non-fused baseline
@@ -401,7 +440,7 @@ def test_run_host_matches_device_path(cuda, ft, dev, oracle):
 
 
 # ------------------------------------------------------------------ BASELINE.json full sizes: properties
-@pytest.mark.parametrize("n,kid", [(4096, 16), (4096, 15), (8192, 16)])
+@pytest.mark.parametrize("n,kid", [(4096, 16), (4096, 15), (8192, 16), (4096, 31), (8192, 31), (16384, 31), (16384, 16)])
 def test_full_size_properties(cuda, ft, dev, oracle, n, kid):
     """Size-independent checks at the metric's sizes: (1) sampled rows against the CPU oracle, (2) the checksum of
     checksums e^T C e = (e^T A)(B^T e) in float64, (3) linearity in alpha, (4) injected faults are repaired in place."""
@@ -417,18 +456,21 @@ def test_full_size_properties(cuda, ft, dev, oracle, n, kid):
     torch.cuda.synchronize()
     st = dev.stats()
     assert st["detected"] == 0 and st["rows_checked"] >= n * (n // 256)
-    # (1) 16 sampled rows x all columns on the host cores
-    rows = np.random.default_rng(n).choice(n, 16, replace=False)
+    # (1) sampled rows x all columns on the host cores (the kernel the bench times, ids 31 / 21, included; 16384 runs the
+    #     wave re-synchronisation path that is on by default from 24 waves)
+    rows = np.random.default_rng(n).choice(n, 16 if n <= 8192 else 8, replace=False)
     A, B = dA.cpu().numpy(), dB.cpu().numpy()
     want = oracle.sgemm_nt_rows(n, n, n, 1.0, A, B, 0.0, None, rows)
     got = dC.view(n, n).t()[torch.from_numpy(rows).cuda()].cpu().numpy()  # C is column-major
     assert np.linalg.norm(want - got) / np.linalg.norm(want) < TOL_NORM
     # (2) checksum of checksums (TF32-truncated operands, float64 reference)
-    At = (dA.view(torch.int32) & -8192).view(torch.float32).double().view(n, n)  # [k][m]
-    Bt = (dB.view(torch.int32) & -8192).view(torch.float32).double().view(n, n)  # [k][n]
-    ref_total = float((At.sum(1) * Bt.sum(1)).sum())
-    got_total = float(dC.double().sum())
-    denom = float((At.abs().sum(1) * Bt.abs().sum(1)).sum())
+    At = (dA.view(torch.int32) & -8192).view(torch.float32).view(n, n)  # [k][m]
+    Bt = (dB.view(torch.int32) & -8192).view(torch.float32).view(n, n)  # [k][n]
+    sa, sb = At.sum(1, dtype=torch.float64), Bt.sum(1, dtype=torch.float64)
+    ref_total = float((sa * sb).sum())
+    got_total = float(dC.sum(dtype=torch.float64))
+    denom = float((At.abs().sum(1, dtype=torch.float64) * Bt.abs().sum(1, dtype=torch.float64)).sum())
+    del At, Bt
     assert abs(ref_total - got_total) / denom < 1e-6
     # (3) linearity: alpha = 2 gives exactly twice the result (power-of-two scaling is exact in FP32)
     dC2 = torch.zeros(n * n, device="cuda")

@@ -97,3 +97,56 @@ def test_world2_gloo_sharded_product_and_verdict(ft):
     assert ok
     assert verdict["tiles"] == 4 and verdict["detected"] == 1 and verdict["corrected"] == 1 and verdict["clean"]
     assert abs(verdict["max_abs_residual"] - 2e-4) < 1e-12
+
+
+def _nccl_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    from importlib import import_module
+    pkg = ge.load_package()
+    sh = import_module("ftsgemm_b200.sharding")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    ft = pkg.FtSgemm()
+    n = 1024
+    g = torch.Generator(device="cuda").manual_seed(5 + rank)
+    dA = torch.randint(-9, 10, (n * n,), generator=g, device="cuda").float() * 0.1
+    dB = torch.randint(-9, 10, (n * n,), generator=g, device="cuda").float() * 0.1
+    dC = torch.zeros(n * n, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    ex = sh.VerdictExchange(lambda buf: ft.stats_device(buf, stream), dist, dev)
+    # rank 1 injects one fault per step: the distributed verdict must show it on every rank
+    faults = [{"row": 3, "col": 700, "xor": 1 << 30}] if rank == 1 else None
+    for _ in range(5):
+        ft.run(31, n, n, n, dA, dB, dC, 1.0, 0.0, pkg.make_opts(stream=stream, faults=faults))
+        ex.step()
+    v = ex.verdict()
+    local = ft.stats()
+    q.put((rank, v, local["rows_checked"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_world2_nccl_device_verdict_exchange(cuda, ft):
+    """The multi-GPU exchange step on real GPUs: two ranks, NCCL all-gather of the device-side verdict vectors."""
+    if cuda.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, v, local_rows in res:
+        assert v["detected"] == 5 and v["corrected"] == 5 and v["clean"], v
+        assert v["rows_checked"] == 2 * local_rows == 2 * 5 * 1024 * 4
+        assert v["per_rank_rows_checked"] == [local_rows, local_rows]
