@@ -121,6 +121,8 @@ struct ftsgemm_handle_s {
   int trace_units = 0;
   float *d_stage[3] = {nullptr, nullptr, nullptr};  // run_host staging A, B, C
   size_t stage_bytes[3] = {0, 0, 0};
+  cudaStream_t s_in = nullptr, s_out = nullptr;     // run_host: upload / download streams of the panel pipeline
+  cudaEvent_t ev_in[16] = {}, ev_done[16] = {};
   double *d_verify = nullptr;   // {first_bad (as long long), num, den}
   std::map<int, int> max_units;     // per kernel instantiation (BN * 8 + FT * 4 + CG): co-resident CTAs / CTA pairs
   cudaStream_t last_stream = nullptr;
@@ -836,6 +838,14 @@ int ftsgemm_destroy(ftsgemm_handle_t h) {
   cudaFree(h->d_aux);
   cudaFree(h->d_verify);
   for (int i = 0; i < 3; ++i) cudaFree(h->d_stage[i]);
+  if (h->s_in) {
+    cudaStreamDestroy(h->s_in);
+    cudaStreamDestroy(h->s_out);
+    for (int i = 0; i < 16; ++i) {
+      cudaEventDestroy(h->ev_in[i]);
+      cudaEventDestroy(h->ev_done[i]);
+    }
+  }
   delete h;
   return FTSGEMM_OK;
 }
@@ -919,6 +929,10 @@ int ftsgemm_run_host(ftsgemm_handle_t h, int kernel_id, int M, int N, int K, con
                      float *hC, float alpha, float beta, const ftsgemm_opts *opts) {
   if (!h) return FTSGEMM_ERR_NO_DEVICE;
   if (!hA || !hB || !hC || M <= 0 || N <= 0 || K <= 0) return FTSGEMM_ERR_INVALID_ARG;
+  ftsgemm_opts o;
+  const int orc = load_opts(opts, &o);
+  if (orc) return orc;
+  DeviceGuard guard(h);
   const size_t bytes[3] = {sizeof(float) * M * static_cast<size_t>(K), sizeof(float) * N * static_cast<size_t>(K),
                            sizeof(float) * M * static_cast<size_t>(N)};
   for (int i = 0; i < 3; ++i)
@@ -929,18 +943,63 @@ int ftsgemm_run_host(ftsgemm_handle_t h, int kernel_id, int M, int N, int K, con
       FT_CUDA(h, cudaMalloc(&h->d_stage[i], bytes[i]));
       h->stage_bytes[i] = bytes[i];
     }
-  ftsgemm_opts o;
-  const int orc = load_opts(opts, &o);
-  if (orc) return orc;
-  DeviceGuard guard(h);
   cudaStream_t stream = static_cast<cudaStream_t>(o.stream);
-  FT_CUDA(h, cudaMemcpyAsync(h->d_stage[0], hA, bytes[0], cudaMemcpyHostToDevice, stream));
-  FT_CUDA(h, cudaMemcpyAsync(h->d_stage[1], hB, bytes[1], cudaMemcpyHostToDevice, stream));
-  if (beta != 0.0f) FT_CUDA(h, cudaMemcpyAsync(h->d_stage[2], hC, bytes[2], cudaMemcpyHostToDevice, stream));
+  // Column panels of C pipeline the three phases (the PCIe link is full duplex and the GEMM of a panel takes a few per
+  // cent of its transfer time): upload stream  A, B_0, C_0, B_1, C_1, ...;  compute stream  GEMM_j after (A, B_j, C_j);
+  // download stream  C_j after GEMM_j.  Panel widths are multiples of the widest tile (256), so every element is
+  // accumulated exactly as in the one-shot device path (bit-identical, tests/test_gpu_parity.py).  B_j is a row block of
+  // the N x K column-major operand: a 2-D copy into a compact (ld = N_j) staging panel.
+  const int max_panels = static_cast<int>(sizeof(h->ev_in) / sizeof(h->ev_in[0]));
+  int panels = static_cast<int>(dbg("host_panels", 0));
+  if (panels <= 0) panels = N >= 4096 ? 4 : (N >= 2048 ? 2 : 1);
+  if (panels > max_panels) panels = max_panels;
+  int pw = ((N + panels - 1) / panels + 255) / 256 * 256;  // panel width
+  if (pw >= N) {
+    pw = N;
+    panels = 1;
+  } else {
+    panels = (N + pw - 1) / pw;
+  }
+  if (!h->s_in) {
+    FT_CUDA(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    FT_CUDA(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < max_panels; ++i) {
+      FT_CUDA(h, cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+      FT_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+  }
+  float *dA = h->d_stage[0], *dBs = h->d_stage[1], *dC = h->d_stage[2];
+  FT_CUDA(h, cudaMemcpyAsync(dA, hA, bytes[0], cudaMemcpyHostToDevice, h->s_in));
+  for (int j = 0; j < panels; ++j) {
+    const int n0 = j * pw, nj = (N - n0) < pw ? (N - n0) : pw;
+    float *dBj = dBs + static_cast<size_t>(n0) * K;
+    if (panels == 1)
+      FT_CUDA(h, cudaMemcpyAsync(dBj, hB, bytes[1], cudaMemcpyHostToDevice, h->s_in));
+    else
+      FT_CUDA(h, cudaMemcpy2DAsync(dBj, sizeof(float) * nj, hB + n0, sizeof(float) * N, sizeof(float) * nj, K,
+                                   cudaMemcpyHostToDevice, h->s_in));
+    if (beta != 0.0f)
+      FT_CUDA(h, cudaMemcpyAsync(dC + static_cast<size_t>(n0) * M, hC + static_cast<size_t>(n0) * M,
+                                 sizeof(float) * M * static_cast<size_t>(nj), cudaMemcpyHostToDevice, h->s_in));
+    FT_CUDA(h, cudaEventRecord(h->ev_in[j], h->s_in));
+  }
   o.reuse_b_checksums = 0;  // the staging buffer content changed
-  int rc = ftsgemm_run(h, kernel_id, M, N, K, h->d_stage[0], h->d_stage[1], h->d_stage[2], alpha, beta, &o);
-  if (rc) return rc;
-  FT_CUDA(h, cudaMemcpyAsync(hC, h->d_stage[2], bytes[2], cudaMemcpyDeviceToHost, stream));
+  for (int j = 0; j < panels; ++j) {
+    const int n0 = j * pw, nj = (N - n0) < pw ? (N - n0) : pw;
+    FT_CUDA(h, cudaStreamWaitEvent(stream, h->ev_in[j], 0));
+    const int rc = ftsgemm_run(h, kernel_id, M, nj, K, dA, dBs + static_cast<size_t>(n0) * K, dC + static_cast<size_t>(n0) * M,
+                               alpha, beta, &o);
+    if (rc) {
+      cudaStreamSynchronize(h->s_in);
+      cudaStreamSynchronize(h->s_out);
+      return rc;
+    }
+    FT_CUDA(h, cudaEventRecord(h->ev_done[j], stream));
+    FT_CUDA(h, cudaStreamWaitEvent(h->s_out, h->ev_done[j], 0));
+    FT_CUDA(h, cudaMemcpyAsync(hC + static_cast<size_t>(n0) * M, dC + static_cast<size_t>(n0) * M,
+                               sizeof(float) * M * static_cast<size_t>(nj), cudaMemcpyDeviceToHost, h->s_out));
+  }
+  FT_CUDA(h, cudaStreamSynchronize(h->s_out));
   FT_CUDA(h, cudaStreamSynchronize(stream));
   return check_abort_flag(h);
 }

@@ -162,8 +162,10 @@ int ftsgemm_get_stats(ftsgemm_handle_t h, ftsgemm_stats *out);
  * verdict of a distributed product without a host round trip (new work: the reference is single-GPU, sgemm.cu:34). */
 int ftsgemm_stats_device(ftsgemm_handle_t h, double *d_out8, void *stream);
 
-/* Same contract with HOST buffers: H2D of A, B (and C when beta != 0), the kernel, D2H of C, synchronous.
- * This is the call the e2e benchmark times.  Device staging buffers are cached on the handle. */
+/* Same contract with HOST buffers, synchronous: the call the e2e benchmark times.  The transfers are pipelined over
+ * column panels of C (upload A, then per panel B_j (+ C_j when beta != 0) | GEMM_j | download C_j on three streams), so
+ * the step costs about the upload time of A, B, C (PCIe is full duplex); pass page-locked host memory for that to
+ * hold.  Results are bit-identical to the device path.  Staging buffers / streams are cached on the handle. */
 int ftsgemm_run_host(ftsgemm_handle_t h, int kernel_id, int M, int N, int K, const float *hA, const float *hB,
                      float *hC, float alpha, float beta, const ftsgemm_opts *opts);
 

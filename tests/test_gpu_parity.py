@@ -437,6 +437,28 @@ def test_run_host_matches_device_path(cuda, ft, dev, oracle):
     hC = C0.copy()
     dev.run_host(16, n, n, n, A, B, hC, 1.0, -1.5, None)
     assert np.array_equal(hC, want)
+    # the panel pipeline (4 column panels from N = 4096 on; forced here on a ragged N): upload | GEMM | download per panel,
+    # bit-identical to the one-shot device path, with and without the C upload (beta = 0), pinned and pageable memory
+    rng = np.random.default_rng(3)
+    M, N, K = 512, 1000, 320
+    A, B = _rand(rng, M * K), _rand(rng, N * K)
+    C0 = rng.standard_normal(M * N).astype(np.float32)
+    for kid in (31, 16):
+        for beta in (-1.5, 0.0):
+            want = _run(cuda, dev, kid, M, N, K, A, B, C0, 0.5, beta)
+            for panels in (3, 4, 1):
+                try:
+                    ft.debug_set("host_panels", panels)
+                    hC = C0.copy()
+                    dev.run_host(kid, M, N, K, A, B, hC, 0.5, beta, None)
+                    assert np.array_equal(hC, want), (kid, beta, panels)
+                    pA, pB = cuda.from_numpy(A).pin_memory(), cuda.from_numpy(B).pin_memory()
+                    pC = cuda.from_numpy(C0.copy()).pin_memory()
+                    dev.run_host(kid, M, N, K, pA, pB, pC, 0.5, beta, None)
+                    assert np.array_equal(pC.numpy(), want), (kid, beta, panels, "pinned")
+                finally:
+                    ft.debug_set("host_panels", -1)
+    assert dev.stats()["detected"] == 0
 
 
 # ------------------------------------------------------------------ BASELINE.json full sizes: properties
