@@ -52,7 +52,7 @@ class Opts(C.Structure):
                 ("selftest_value", C.c_float), ("selftest_row", C.c_int), ("selftest_col", C.c_int),
                 ("n_faults", C.c_int), ("faults", Fault * MAX_FAULTS), ("tau_abs", C.c_float),
                 ("tau_rel", C.c_float), ("detect_only", C.c_int), ("reuse_b_checksums", C.c_int),
-                ("baseline_host_sync", C.c_int)]
+                ("baseline_host_sync", C.c_int), ("no_recompute", C.c_int)]
 
 
 class Event(C.Structure):
@@ -64,11 +64,11 @@ class Stats(C.Structure):
     _fields_ = [("tiles", C.c_ulonglong), ("rows_checked", C.c_ulonglong), ("detected", C.c_ulonglong),
                 ("corrected", C.c_ulonglong), ("uncorrectable", C.c_ulonglong), ("checksum_faults", C.c_ulonglong),
                 ("max_abs_residual", C.c_float), ("max_rel_residual", C.c_float), ("n_events", C.c_int),
-                ("events", Event * MAX_EVENTS)]
+                ("events", Event * MAX_EVENTS), ("recomputed", C.c_ulonglong)]
 
     def as_dict(self):
         return {"tiles": self.tiles, "rows_checked": self.rows_checked, "detected": self.detected,
-                "corrected": self.corrected, "uncorrectable": self.uncorrectable,
+                "corrected": self.corrected, "uncorrectable": self.uncorrectable, "recomputed": self.recomputed,
                 "checksum_faults": self.checksum_faults, "max_abs_residual": self.max_abs_residual,
                 "max_rel_residual": self.max_rel_residual,
                 "events": [{"row": e.row, "col": e.col, "residual": e.residual,
@@ -150,7 +150,7 @@ def default_opts() -> Opts:
 
 
 def make_opts(stream=None, selftest=None, faults=None, tau_abs=0.0, tau_rel=0.0, detect_only=False,
-              reuse_b_checksums=False, baseline_host_sync=True) -> Opts:
+              reuse_b_checksums=False, baseline_host_sync=True, no_recompute=False) -> Opts:
     """selftest: None | (value, tile_row, tile_col)  -> the reference's always-on injector (ft_sgemm_huge.cuh:324-327)
     faults: list of dicts {row, col, add=float} or {row, col, xor=int}"""
     o = default_opts()
@@ -172,6 +172,7 @@ def make_opts(stream=None, selftest=None, faults=None, tau_abs=0.0, tau_rel=0.0,
     o.detect_only = int(detect_only)
     o.reuse_b_checksums = int(reuse_b_checksums)
     o.baseline_host_sync = int(baseline_host_sync)
+    o.no_recompute = int(no_recompute)
     return o
 
 

@@ -188,8 +188,8 @@ int main(int argc, char **argv) {
     if (ftsgemm_kernel_lookup(run_id, &info) == FTSGEMM_OK && info.fault_tolerant && info.engine == 1) {
       ftsgemm_stats st;
       if (ftsgemm_get_stats(h, &st) == FTSGEMM_OK)
-        fprintf(stderr, "[abft] kernel %d: tiles %llu detected %llu corrected %llu uncorrectable %llu max_resid %.3e rel_fro_vs_cublas %.3e\n",
-                id, st.tiles, st.detected, st.corrected, st.uncorrectable, st.max_abs_residual, rel);
+        fprintf(stderr, "[abft] kernel %d: tiles %llu detected %llu corrected %llu uncorrectable %llu recomputed %llu max_resid %.3e rel_fro_vs_cublas %.3e\n",
+                id, st.tiles, st.detected, st.corrected, st.uncorrectable, st.recomputed, st.max_abs_residual, rel);
     }
     if (cpu_verify) {
       CUDA_OR_DIE(cudaMemcpy(Cm.data(), dC, count * sizeof(float), cudaMemcpyDeviceToHost));

@@ -385,6 +385,11 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
   p.tau_abs = o.tau_abs > 0 ? o.tau_abs : 1e-3f;
   p.tau_rel = o.tau_rel > 0 ? o.tau_rel : 1e-5f;  // 13x the measured fault-free floor at K = 8192 (7.6e-7)
   p.detect_only = o.detect_only;
+  p.recompute = o.no_recompute ? 0 : 1;
+  p.A = dA;
+  p.B = dB;
+  p.lda = M;
+  p.ldb = N;
   p.inject_mode = ft ? o.inject_mode : 0;
   p.selftest_value = o.selftest_value;
   p.selftest_row = o.selftest_row & (kBM - 1);  // (>= 0: validated by load_opts)
@@ -902,6 +907,7 @@ int ftsgemm_get_stats(ftsgemm_handle_t h, ftsgemm_stats *out) {
   out->corrected = ds.corrected;
   out->uncorrectable = ds.uncorrectable;
   out->checksum_faults = ds.checksum_faults;
+  out->recomputed = ds.recomputed;
   memcpy(&out->max_abs_residual, &ds.max_abs_bits, 4);
   memcpy(&out->max_rel_residual, &ds.max_rel_bits, 4);
   out->n_events = ds.n_events < FTSGEMM_MAX_EVENTS ? ds.n_events : FTSGEMM_MAX_EVENTS;

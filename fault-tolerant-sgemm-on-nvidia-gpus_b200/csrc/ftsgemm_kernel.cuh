@@ -65,6 +65,7 @@ struct DeviceStats {
   unsigned int max_abs_bits, max_rel_bits;
   int n_events;
   DeviceEvent events[kMaxEvents];
+  unsigned long long recomputed;  // rows that were detected but not cleanly correctable and were recomputed on CUDA cores
 };
 
 struct KernelParams {
@@ -116,6 +117,13 @@ struct KernelParams {
                         //    that only the launch latency and the prologue overlap the predecessor's tail
   float tau_abs, tau_rel;
   int detect_only;
+  // Fallback for rows that are flagged but cannot be repaired from the two checksums (upset too small to locate, two
+  // upsets in one row, second checksum disagrees): the row segment of this tile is RECOMPUTED from A and B on CUDA cores
+  // (TF32-truncated operands, FP32 accumulate) and written straight to C; the store pass skips it.  Nothing that was
+  // detected is stored as computed.  (The reference only ever adds the residual, ft_sgemm_huge.cuh:422-485.)
+  int recompute;
+  const float *A, *B;   // the operands in global memory (lda = M, ldb = N)
+  int lda, ldb;
   int inject_mode;
   float selftest_value;
   int selftest_row, selftest_col;
@@ -340,7 +348,7 @@ __device__ __forceinline__ void try_prefetch_expected(const KernelParams &p, int
 
 template <int BN>
 __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr, int q, int lane, int m, int m0_cta,
-                                           int n0, int n_blk, int &fix_col, float &fix_val, ExpectedChk &xp,
+                                           int n0, int n_blk, int &fix_col, float &fix_val, bool &redo, ExpectedChk &xp,
                                            int c_mid = BN / 32, uint32_t xchg = 0u, int pair_bar = 0) {
   // ---- fault injection into the TMEM accumulator (reference: ft_sgemm_huge.cuh:324-327) ----
   if (p.inject_mode == 1) {
@@ -487,15 +495,18 @@ __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr
     status = (fabsf(e2) <= tol) ? 1 : 3;
   }
   if (status == 1 && p.detect_only) status = 2;
+  if (status == 3 && p.recompute && !p.detect_only && m < p.M) status = 5;
   if (status == 1) {
     fix_col = j;
     fix_val = vc;
   }
+  redo = status == 5;
   if (p.stats) {
     atomicAdd(&p.stats->detected, 1ull);
     if (status == 1) atomicAdd(&p.stats->corrected, 1ull);
     if (status == 3) atomicAdd(&p.stats->uncorrectable, 1ull);
     if (status == 4) atomicAdd(&p.stats->checksum_faults, 1ull);
+    if (status == 5) atomicAdd(&p.stats->recomputed, 1ull);
     const int slot = atomicAdd(&p.stats->n_events, 1);
     if (slot < kMaxEvents) {
       DeviceEvent ev;
@@ -505,6 +516,42 @@ __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr
       ev.corrected_value = vc;
       ev.status = status;
       p.stats->events[slot] = ev;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Recompute fallback (rare): one warp recomputes row m of the tile's BN columns from global memory -- the values the
+// tensor core would have produced up to FP32 accumulation order (TF32-truncated operands: every product is exact in
+// FP32) -- and writes C = alpha * acc + beta * C directly.  K iterations of 1 broadcast + BN/32 coalesced loads.
+// ------------------------------------------------------------------------------------------------------------
+// (scalars by value: a reference to the __grid_constant__ parameter block would force a local copy of all of it)
+template <int BN>
+__device__ __noinline__ void recompute_row(const float *A, const float *B, float *C, int lda, int ldb, int ldc, int N, int K,
+                                           float alpha, float beta, int m, int n0, int lane) {
+  constexpr int J = BN / 32;
+  float acc[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) acc[j] = 0.0f;
+  const float *a = A + m;
+  const float *b = B + n0 + lane;
+#pragma unroll 2
+  for (int k = 0; k < K; ++k) {
+    const float av = u2f(f2u(__ldg(a + static_cast<size_t>(k) * lda)) & 0xFFFFE000u);
+    const float *bk = b + static_cast<size_t>(k) * ldb;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const float bv = (n0 + lane + 32 * j < N) ? u2f(f2u(__ldg(bk + 32 * j)) & 0xFFFFE000u) : 0.0f;
+      acc[j] = fmaf(av, bv, acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int n = n0 + lane + 32 * j;
+    if (n < N) {
+      float *dst = C + m + static_cast<size_t>(n) * ldc;
+      const float o = (beta == 0.0f) ? 0.0f : beta * (*dst);
+      *dst = alpha * acc[j] + o;
     }
   }
 }
@@ -1004,8 +1051,12 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int c_mid = assist ? kMid : BN / 32;
         int fix_col = -1;
         float fix_val = 0.0f;
+        bool redo = false;
         if (FT && !(p.dbg_flags & 1))
-          abft_check<BN>(p, taddr, q, lane, m, m0_cta, n0, tc.n_blk, fix_col, fix_val, xp, c_mid, xchg_base(q), 4 + q);
+          abft_check<BN>(p, taddr, q, lane, m, m0_cta, n0, tc.n_blk, fix_col, fix_val, redo, xp, c_mid, xchg_base(q), 4 + q);
+        // rows to recompute are skipped by both store passes (the helper reads the mask after the pair barrier below)
+        const unsigned redo_mask = FT ? __ballot_sync(0xffffffffu, redo) : 0u;
+        if (FT && assist && !(p.dbg_flags & 1) && lane == 0) ptx::st_shared_u32(xchg_base(q), redo_mask);
         if (tracer) trace_put(p, unit, item_idx, 5, globaltimer_ns());
         if (FT) {
           // rare: write the recomputed elements back into the accumulator (one lane = one row at a time, like the
@@ -1028,7 +1079,15 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           ptx::tc_fence_before();
           ptx::named_bar_sync(4 + q, 64);
         }
-        store_tile<BN>(taddr, p.C + m, m < p.M, n0, p.N, p.ldc, p.alpha, p.beta, 0, c_mid);
+        store_tile<BN>(taddr, p.C + m, m < p.M && !redo, n0, p.N, p.ldc, p.alpha, p.beta, 0, c_mid);
+        if (FT && redo_mask != 0u) {  // rare, warp-uniform: recompute the flagged rows from global memory
+          unsigned rm = redo_mask;
+          while (rm != 0u) {
+            const int r = __ffs(rm) - 1;
+            rm &= rm - 1u;
+            recompute_row<BN>(p.A, p.B, p.C, p.lda, p.ldb, p.ldc, p.N, p.K, p.alpha, p.beta, m0_cta + q * 32 + r, n0, lane);
+          }
+        }
         if (assist) {  // both halves are out of tensor memory
           ptx::tc_fence_before();
           ptx::named_bar_sync(4 + q, 64);
@@ -1075,6 +1134,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a_acc * BN;
         const int m0_cta = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;
         const int m = m0_cta + row;
+        uint32_t skip = 0u;
         if (FT && !(p.dbg_flags & 1)) {
           if (p.inject_mode != 0) {
             ptx::named_bar_sync(4 + q, 64);  // injected
@@ -1088,8 +1148,9 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           ptx::named_bar_sync(4 + q, 64);  // partial sums handed over
           ptx::named_bar_sync(4 + q, 64);  // verdict reached, corrections written to tensor memory
           ptx::tc_fence_after();
+          skip = (ptx::ld_acquire_shared_u32(xchg_base(q)) >> lane) & 1u;  // rows the epilogue warp recomputes
         }
-        store_tile<BN>(taddr, p.C + m, m < p.M, tc.n_blk * BN, p.N, p.ldc, p.alpha, p.beta, kMid, BN / 32);
+        store_tile<BN>(taddr, p.C + m, m < p.M && !skip, tc.n_blk * BN, p.N, p.ldc, p.alpha, p.beta, kMid, BN / 32);
         ptx::tc_fence_before();
         ptx::named_bar_sync(4 + q, 64);  // both halves are out of tensor memory
       };

@@ -56,7 +56,7 @@ def allreduce_verdict(stats: dict, dist, device=None) -> dict:
     dist.all_reduce(m, op=dist.ReduceOp.MAX)
     out = {k: int(v) for k, v in zip(STAT_KEYS_SUM, s.tolist())}
     out.update({k: float(v) for k, v in zip(STAT_KEYS_MAX, m.tolist())})
-    out["clean"] = out["detected"] == out["corrected"] and out["uncorrectable"] == 0
+    out["clean"] = out["uncorrectable"] == 0  # (everything else that was detected was corrected or recomputed)
     return out
 
 
@@ -104,6 +104,6 @@ class VerdictExchange:
         v = self.gathered[self.last].reshape(self.world, 8).cpu()
         out = {k: int(v[:, i].sum().item()) for i, k in enumerate(STAT_KEYS_SUM)}
         out.update({k: float(v[:, 6 + i].max().item()) for i, k in enumerate(STAT_KEYS_MAX)})
-        out["clean"] = out["detected"] == out["corrected"] and out["uncorrectable"] == 0
+        out["clean"] = out["uncorrectable"] == 0  # (everything else that was detected was corrected or recomputed)
         out["per_rank_rows_checked"] = [int(x) for x in v[:, 1].tolist()]
         return out

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FTSGEMM_ABI_VERSION 1
+#define FTSGEMM_ABI_VERSION 2
 
 enum {
   FTSGEMM_OK = 0,
@@ -105,6 +105,11 @@ typedef struct ftsgemm_opts {
                             (no encoder items in this launch) */
   int baseline_host_sync;/* id 10/30: 1 = host-synchronise between stages like the reference
                             (baseline_ft_sgemm.cuh:7,19,26,30); 0 = stream-ordered */
+  /* ---- ABI version 2 ---- */
+  int no_recompute;      /* 0 (default): a row that is flagged but cannot be repaired from its two checksums (upset too
+                            small to locate, two upsets in one row) is RECOMPUTED from A and B on CUDA cores and counted
+                            in stats.recomputed -- nothing detected is stored as computed; 1: leave such rows as computed
+                            and count them in stats.uncorrectable (round-1 behaviour) */
 } ftsgemm_opts;
 /* sizeof(ftsgemm_opts) of ABI version 1: the smallest struct_size the library accepts (a zero-initialised struct is
  * rejected with FTSGEMM_ERR_INVALID_ARG instead of silently meaning "all defaults on the default stream"). */
@@ -114,7 +119,8 @@ typedef struct ftsgemm_event {
   int row, col;          /* global element that was located (col = -1 if not locatable) */
   float residual;        /* expected - actual row checksum */
   float corrected_value; /* accumulator value after correction */
-  int status;            /* 1 corrected, 2 detected only (detect_only), 3 uncorrectable, 4 checksum-column fault */
+  int status;            /* 1 corrected, 2 detected only (detect_only), 3 uncorrectable, 4 checksum-column fault,
+                            5 row recomputed */
 } ftsgemm_event;
 
 typedef struct ftsgemm_stats {
@@ -122,12 +128,15 @@ typedef struct ftsgemm_stats {
   unsigned long long rows_checked; /* row checksums tested */
   unsigned long long detected;     /* rows whose residual exceeded the threshold */
   unsigned long long corrected;    /* single-element corrections applied */
-  unsigned long long uncorrectable;/* detected but not locatable (multi-error row / ambiguous) */
+  unsigned long long uncorrectable;/* detected, not locatable (multi-error row / ambiguous) AND left as computed
+                                      (only with opts.no_recompute or detect_only) */
   unsigned long long checksum_faults; /* residual explained by a fault in the checksum column itself */
   float max_abs_residual;          /* max |expected - actual| over all fault-free rows */
   float max_rel_residual;          /* max |expected - actual| / sum_n|acc| over all fault-free rows */
   int n_events;
   ftsgemm_event events[FTSGEMM_MAX_EVENTS];
+  /* ---- ABI version 2 ---- */
+  unsigned long long recomputed;   /* rows detected but not correctable from the checksums, recomputed on CUDA cores */
 } ftsgemm_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------- */

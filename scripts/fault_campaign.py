@@ -43,7 +43,7 @@ out = {"n": n, "kernel": info["name"], "tile": [TM, TN], "fault_free": {k: base_
        ("tiles", "rows_checked", "detected", "max_abs_residual", "max_rel_residual")}, "bits": {}}
 dC = torch.zeros(n * n, device="cuda")
 for bit in range(31, -1, -1):
-    inj = det = cor = unc = located = 0
+    inj = det = cor = unc = located = rec = 0
     worst_left = 0.0
     for _ in range(trials):
         faults, seen = [], set()
@@ -62,10 +62,11 @@ for bit in range(31, -1, -1):
         det += st["detected"]
         cor += st["corrected"]
         unc += st["uncorrectable"]
+        rec += st["recomputed"]
         want = {(f["row"], f["col"]) for f in faults}
         located += sum(1 for e in st["events"] if (e["row"], e["col"]) in want)
         worst_left = max(worst_left, float((dC - clean).abs().max()))
-    out["bits"][str(bit)] = {"injected": inj, "detected": det, "corrected": cor, "uncorrectable": unc,
+    out["bits"][str(bit)] = {"injected": inj, "detected": det, "corrected": cor, "recomputed": rec, "uncorrectable": unc,
                              "located_ok": located, "max_abs_error_left": worst_left,
                              "max_abs_error_left_over_maxC": worst_left / scale}
     print(bit, out["bits"][str(bit)], flush=True)

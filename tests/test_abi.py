@@ -18,7 +18,7 @@ def test_header_symbols_all_exported(ft):
     lib = C.CDLL(str(ft.LIB_PATH))
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.ftsgemm_abi_version() == 1
+    assert lib.ftsgemm_abi_version() == 2
 
 
 def test_header_cites_reference_interfaces():

@@ -416,16 +416,81 @@ def test_low_order_flip_below_threshold_is_harmless(cuda, ft, dev):
     assert np.abs(got - clean).max() < 1e-4  # an undetected flip is below the rounding floor by construction
 
 
-def test_two_faults_in_one_row_reported_uncorrectable(cuda, ft, dev):
+def test_two_faults_in_one_row_are_recomputed(cuda, ft, dev):
+    """Two upsets in one row of one tile cannot be repaired from the two checksums.  Default: the row segment is recomputed
+    from A and B on CUDA cores (status 5) -- nothing detected is stored as computed; opts.no_recompute restores the
+    round-1 behaviour (reported uncorrectable, left as computed).  All tile shapes, alpha / beta, helper-assisted halves."""
     rng = np.random.default_rng(11)
-    M = N = 256
-    K = 512
+    M, N, K = 512, 768, 512
     A, B = _rand(rng, M * K), _rand(rng, N * K)
-    C0 = np.zeros(M * N, np.float32)
-    _run(cuda, dev, 16, M, N, K, A, B, C0,
-         opts=ft.make_opts(faults=[{"row": 40, "col": 10, "add": 100.0}, {"row": 40, "col": 90, "add": -37.0}]))
-    st = dev.stats()
-    assert st["detected"] == 1 and st["corrected"] == 0 and st["uncorrectable"] == 1
+    C0 = rng.standard_normal(M * N).astype(np.float32)
+    for kid in (16, 31, 15, 12, 32):
+        clean = _run(cuda, dev, kid, M, N, K, A, B, C0, 0.75, -1.5)
+        faults = [{"row": 40, "col": 10, "add": 100.0}, {"row": 40, "col": 25, "add": -37.0},     # same row, same tile
+                  {"row": 300, "col": 520, "xor": 1 << 30}, {"row": 300, "col": 530, "xor": 1 << 28},
+                  {"row": 511, "col": 767, "add": 55.0}]                                        # (a single one: corrected)
+        dev.stats()
+        got = _run(cuda, dev, kid, M, N, K, A, B, C0, 0.75, -1.5, opts=ft.make_opts(faults=faults))
+        st = dev.stats()
+        assert st["detected"] == 3 and st["corrected"] == 1 and st["recomputed"] == 2 and st["uncorrectable"] == 0, (kid, st)
+        assert sorted(e["status"] for e in st["events"]) == [1, 5, 5]
+        scale = float(np.abs(clean).max())
+        assert np.abs(got - clean).max() <= 1e-4 * scale, (kid, np.abs(got - clean).max(), scale)
+        # only the two recomputed row segments and the corrected element may differ from the fault-free run at all
+        diff = np.flatnonzero(got != clean)
+        rows = set((diff % M).tolist())
+        assert rows <= {40, 300, 511}, (kid, rows)
+        got2 = _run(cuda, dev, kid, M, N, K, A, B, C0, 0.75, -1.5, opts=ft.make_opts(faults=faults[:2], no_recompute=True))
+        st = dev.stats()
+        assert st["detected"] == 1 and st["corrected"] == 0 and st["uncorrectable"] == 1 and st["recomputed"] == 0
+        assert np.abs(got2 - clean).max() > 10.0  # (left as computed)
+
+
+def test_fault_campaign_floors(cuda, ft, dev):
+    """BASELINE.json configs[3] in miniature at the real size (M=N=K=8192, the bench kernel id 31): single-bit flips of
+    tensor-memory accumulators.  Floors: bits >= 22 (exponent, sign, top mantissa bit) detected 100 % and repaired
+    (corrected or recomputed) 100 %, error left <= 1e-4 * max|C|; lower bits: whatever is detected is repaired -- no
+    detected fault is stored as computed -- and what stays undetected is below the detection threshold
+    (tau_abs + tau_rel * sum|acc| ~ 0.05 at K = 8192, i.e. < 5e-4 * max|C|)."""
+    torch = cuda
+    n, kid = 8192, 31
+    g = torch.Generator(device="cuda").manual_seed(7)
+    dA = (torch.randint(0, 10, (n * n,), generator=g, device="cuda").float() * 0.1) * \
+        (torch.randint(0, 2, (n * n,), generator=g, device="cuda").float() * 2 - 1)
+    dB = (torch.randint(0, 10, (n * n,), generator=g, device="cuda").float() * 0.1) * \
+        (torch.randint(0, 2, (n * n,), generator=g, device="cuda").float() * 2 - 1)
+    clean = torch.zeros(n * n, device="cuda")
+    dev.stats()
+    dev.run(kid, n, n, n, dA, dB, clean, 1.0, 0.0, None)
+    torch.cuda.synchronize()
+    assert dev.stats()["detected"] == 0
+    scale = float(clean.abs().max())
+    rng = np.random.default_rng(0)
+    dC = torch.zeros(n * n, device="cuda")
+    for bit in (31, 30, 29, 27, 25, 23, 22, 21, 20, 19, 18, 17, 16, 14, 10):
+        inj = det = rep = 0
+        worst = 0.0
+        for _ in range(2):
+            faults, seen = [], set()
+            while len(faults) < ft.MAX_FAULTS:
+                r, c = int(rng.integers(n)), int(rng.integers(n))
+                if (r, c // 256) in seen:
+                    continue
+                seen.add((r, c // 256))
+                faults.append({"row": r, "col": c, "xor": 1 << bit})
+            dC.zero_()
+            dev.run(kid, n, n, n, dA, dB, dC, 1.0, 0.0, ft.make_opts(faults=faults))
+            torch.cuda.synchronize()
+            st = dev.stats()
+            inj += len(faults)
+            det += st["detected"]
+            rep += st["corrected"] + st["recomputed"]
+            assert st["uncorrectable"] == 0 and st["checksum_faults"] == 0, (bit, st)
+            worst = max(worst, float((dC - clean).abs().max()))
+        assert rep == det, (bit, det, rep)
+        assert worst <= 5e-4 * scale, (bit, worst, scale)
+        if bit >= 22:
+            assert det == inj and worst <= 1e-4 * scale, (bit, det, inj, worst, scale)
 
 
 # ------------------------------------------------------------------ host-buffer (e2e) entry point
