@@ -26,6 +26,7 @@ MAX_EVENTS = 16
 
 # kernel ids (include/ftsgemm.h; reference sgemm.cu:235-237)
 ID_CUBLAS, ID_CUBLAS_TF32, ID_ABFT_BASELINE, ID_ABFT_BASELINE_TF32 = 0, 7, 10, 30
+ID_SGEMM_AUTO, ID_ABFT_AUTO = 20, 40  # per-shape choice among the tcgen05 variants (select_kernel)
 SGEMM_IDS = {"small": 1, "medium": 2, "large": 3, "tall": 4, "wide": 5, "huge": 6, "giant": 21, "pair128": 22}
 ABFT_IDS = {"small": 11, "medium": 12, "large": 13, "tall": 14, "wide": 15, "huge": 16, "giant": 31, "pair128": 32}
 
@@ -52,7 +53,7 @@ class Opts(C.Structure):
                 ("selftest_value", C.c_float), ("selftest_row", C.c_int), ("selftest_col", C.c_int),
                 ("n_faults", C.c_int), ("faults", Fault * MAX_FAULTS), ("tau_abs", C.c_float),
                 ("tau_rel", C.c_float), ("detect_only", C.c_int), ("reuse_b_checksums", C.c_int),
-                ("baseline_host_sync", C.c_int), ("no_recompute", C.c_int)]
+                ("baseline_host_sync", C.c_int), ("precision", C.c_int), ("no_recompute", C.c_int)]
 
 
 class Event(C.Structure):
@@ -81,7 +82,7 @@ EXPORTED_SYMBOLS = [
     "ftsgemm_create", "ftsgemm_destroy", "ftsgemm_abi_version", "ftsgemm_error_string", "ftsgemm_last_cuda_error",
     "ftsgemm_default_opts", "ftsgemm_kernel_table", "ftsgemm_kernel_lookup", "ftsgemm_run", "ftsgemm_get_stats",
     "ftsgemm_run_host", "ftsgemm_baseline", "ftsgemm_verify", "ftsgemm_debug_set", "ftsgemm_debug_schedule",
-    "ftsgemm_verify_bad_count", "ftsgemm_debug_trace", "ftsgemm_stats_device",
+    "ftsgemm_verify_bad_count", "ftsgemm_debug_trace", "ftsgemm_stats_device", "ftsgemm_select_kernel",
 ]
 
 _lib = None
@@ -117,6 +118,7 @@ def lib():
         L.ftsgemm_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.ftsgemm_run_host.argtypes = [vp, ip, ip, ip, ip, vp, vp, vp, fp, fp, C.POINTER(Opts)]
         L.ftsgemm_stats_device.argtypes = [vp, vp, vp]
+        L.ftsgemm_select_kernel.argtypes = [ip, ip, ip, ip]
         L.ftsgemm_baseline.argtypes = [vp, ip, ip, ip, vp, vp, vp, fp, fp, ip, C.POINTER(Opts), vp]
         L.ftsgemm_verify.argtypes = [vp, vp, vp, ip, ip, C.POINTER(C.c_longlong), C.POINTER(C.c_double), vp]
         L.ftsgemm_debug_set.argtypes = [C.c_char_p, C.c_longlong]
@@ -143,6 +145,14 @@ def kernel_table():
             for k in arr]
 
 
+def select_kernel(M: int, N: int, K: int, fault_tolerant: bool) -> int:
+    """The concrete kernel id the AUTO ids (20 / 40) resolve to for this shape."""
+    r = lib().ftsgemm_select_kernel(M, N, K, 1 if fault_tolerant else 0)
+    if r < 0:
+        _check(r)
+    return r
+
+
 def default_opts() -> Opts:
     o = Opts()
     lib().ftsgemm_default_opts(C.byref(o))
@@ -150,7 +160,7 @@ def default_opts() -> Opts:
 
 
 def make_opts(stream=None, selftest=None, faults=None, tau_abs=0.0, tau_rel=0.0, detect_only=False,
-              reuse_b_checksums=False, baseline_host_sync=True, no_recompute=False) -> Opts:
+              reuse_b_checksums=False, baseline_host_sync=True, no_recompute=False, precision=0) -> Opts:
     """selftest: None | (value, tile_row, tile_col)  -> the reference's always-on injector (ft_sgemm_huge.cuh:324-327)
     faults: list of dicts {row, col, add=float} or {row, col, xor=int}"""
     o = default_opts()
@@ -173,6 +183,7 @@ def make_opts(stream=None, selftest=None, faults=None, tau_abs=0.0, tau_rel=0.0,
     o.reuse_b_checksums = int(reuse_b_checksums)
     o.baseline_host_sync = int(baseline_host_sync)
     o.no_recompute = int(no_recompute)
+    o.precision = int(precision)  # 0 = single-pass TF32, 1 = 3xTF32 (FP32-grade)
     return o
 
 

@@ -32,31 +32,35 @@ struct Variant {
   int cg;  // 1 = one CTA per tile (UMMA M = 128), 2 = CTA pair per tile (cta_group::2, UMMA M = 256)
 };
 
-// Reference tiles from code_gen/main.py:8-16; sm_100a tiles: UMMA M is 128 per CTA, so the reference's "tall"
-// (128x32) and "huge" (128x128) shapes are literal, the others map to the nearest UMMA-legal shape with the same
-// role (fewer/larger CTAs).  "giant" (ids 21/31) is the B200-only CTA-pair tile 256x256.  tile_k = K extent of one
-// shared-memory stage (4 UMMA k-steps of 8).
+// Reference tiles from code_gen/main.py:8-16.  sm_100a tiles: UMMA M is 128 per CTA (256 for a CTA pair), so the
+// reference's "tall" (128x32) and "huge" (128x128) shapes are literal; the four others map, in the reference's order of
+// size, onto the remaining UMMA-legal shapes -- six names, six DISTINCT binaries (round 1 aliased small = tall and
+// large = huge):   small 128x64   medium 256x64 (pair)   large 256x128 (pair)   tall 128x32   wide 128x256   huge 128x128.
+// "giant" (ids 21/31) is the B200-only CTA-pair tile 256x256, "pair128" (22/32) an alias of large kept for round-1
+// callers; ids 20 / 40 pick per shape (select_variant).  tile_k = K extent of one shared-memory stage (4 UMMA k-steps).
 const Variant kVariants[] = {
     {{0, "cublas", 0, 0, 0, 0, 0, 0, 0, 0}, 0, 0},
-    {{1, "kernel_sgemm_small", 0, 1, 16, 16, 16, 128, 32, 32}, 32, 1},
-    {{2, "kernel_sgemm_medium", 0, 1, 32, 32, 8, 128, 64, 32}, 64, 1},
-    {{3, "kernel_sgemm_large", 0, 1, 64, 64, 8, 128, 128, 32}, 128, 1},
+    {{1, "kernel_sgemm_small", 0, 1, 16, 16, 16, 128, 64, 32}, 64, 1},
+    {{2, "kernel_sgemm_medium", 0, 1, 32, 32, 8, 256, 64, 32}, 64, 2},
+    {{3, "kernel_sgemm_large", 0, 1, 64, 64, 8, 256, 128, 32}, 128, 2},
     {{4, "kernel_sgemm_tall", 0, 1, 128, 32, 8, 128, 32, 32}, 32, 1},
     {{5, "kernel_sgemm_wide", 0, 1, 32, 128, 8, 128, 256, 32}, 256, 1},
     {{6, "kernel_sgemm_huge", 0, 1, 128, 128, 8, 128, 128, 32}, 128, 1},
     {{7, "cublas_tf32", 0, 0, 0, 0, 0, 0, 0, 0}, 0, 0},
     {{10, "abft_baseline", 1, 2, 0, 0, 256, 0, 0, 256}, 0, 0},
-    {{11, "abft_kernel_small", 1, 1, 16, 16, 16, 128, 32, 32}, 32, 1},
-    {{12, "abft_kernel_medium", 1, 1, 32, 32, 8, 128, 64, 32}, 64, 1},
-    {{13, "abft_kernel_large", 1, 1, 64, 64, 8, 128, 128, 32}, 128, 1},
+    {{11, "abft_kernel_small", 1, 1, 16, 16, 16, 128, 64, 32}, 64, 1},
+    {{12, "abft_kernel_medium", 1, 1, 32, 32, 8, 256, 64, 32}, 64, 2},
+    {{13, "abft_kernel_large", 1, 1, 64, 64, 8, 256, 128, 32}, 128, 2},
     {{14, "abft_kernel_tall", 1, 1, 128, 32, 8, 128, 32, 32}, 32, 1},
     {{15, "abft_kernel_wide", 1, 1, 32, 128, 8, 128, 256, 32}, 256, 1},
     {{16, "abft_kernel_huge", 1, 1, 128, 128, 8, 128, 128, 32}, 128, 1},
+    {{20, "kernel_sgemm_auto", 0, 1, 0, 0, 0, 0, 0, 32}, 0, 0},
     {{21, "kernel_sgemm_giant", 0, 1, 0, 0, 0, 256, 256, 32}, 256, 2},
     {{22, "kernel_sgemm_pair128", 0, 1, 0, 0, 0, 256, 128, 32}, 128, 2},
     {{30, "abft_baseline_tf32", 1, 2, 0, 0, 256, 0, 0, 256}, 0, 0},
     {{31, "abft_kernel_giant", 1, 1, 0, 0, 0, 256, 256, 32}, 256, 2},
     {{32, "abft_kernel_pair128", 1, 1, 0, 0, 0, 256, 128, 32}, 128, 2},
+    {{40, "abft_kernel_auto", 1, 1, 0, 0, 0, 0, 0, 32}, 0, 0},
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
@@ -65,6 +69,16 @@ const Variant *find_variant(int id) {
   for (int i = 0; i < kNumVariants; ++i)
     if (kVariants[i].info.id == id) return &kVariants[i];
   return nullptr;
+}
+
+// Per-shape choice of the tcgen05 variant (replaces the reference's manual id choice, sgemm.cu:110-199).
+// Measured on B200 (profiles/r02_sweep_small_ids.jsonl, 20-launch bursts): from ~40 tiles of 256x256 on (2048^2 and up)
+// the CTA-pair tile 256x256 wins for both engines (2048^3: 37 us vs 42 us for 256x128 with ABFT); below that the 74 CTA
+// pairs are mostly idle with 256x256 tiles and the 256x128 pair tile is ahead (1024^3 plain: 15.3 vs 18.8 us).
+int select_variant(int M, int N, bool ft) {
+  const long long tiles256 = (static_cast<long long>(M) + 255) / 256 * ((static_cast<long long>(N) + 255) / 256);
+  if (tiles256 >= 40) return ft ? FTSGEMM_ID_ABFT_GIANT : FTSGEMM_ID_SGEMM_GIANT;
+  return ft ? FTSGEMM_ID_ABFT_LARGE : FTSGEMM_ID_SGEMM_LARGE;
 }
 
 // slab flags of the checksum tile-columns live in front of the expected-checksum matrix (one int per 32-row slab and
@@ -99,6 +113,8 @@ struct ftsgemm_handle_s {
   size_t chk_out_bytes = 0;
   const float *chk_for_b = nullptr;  // B pointer / shape the panel was encoded from
   int chk_n = 0, chk_k = 0, chk_bn = 0;
+  float *d_lo = nullptr;        // 3xTF32: A_lo | B_lo
+  size_t lo_bytes = 0;
   float *d_aux = nullptr;       // baseline vectors
   size_t aux_floats = 0;
   struct CachedPlan {
@@ -315,7 +331,8 @@ PlanInput make_plan_input(int max_units, int CG, int BN, int K, const KernelPara
   // tile at 2048 .. 4096, where data tiles take 0.33 us per k-block out of L2; 0.58 where they are HBM-bound)
   const double chk_floor = static_cast<double>(dbg("chk_cost_permille", in.lockstep ? 580 : 680)) * 1e-3;
   if (BN == 32) chk_costs<32, 1>(p, chk_floor, &in.chk_col_cost);
-  else if (BN == 64) chk_costs<64, 1>(p, chk_floor, &in.chk_col_cost);
+  else if (BN == 64 && CG == 1) chk_costs<64, 1>(p, chk_floor, &in.chk_col_cost);
+  else if (BN == 64) chk_costs<64, 2>(p, chk_floor, &in.chk_col_cost);
   else if (BN == 128 && CG == 1) chk_costs<128, 1>(p, chk_floor, &in.chk_col_cost);
   else if (BN == 128) chk_costs<128, 2>(p, chk_floor, &in.chk_col_cost);
   else if (CG == 1) chk_costs<256, 1>(p, chk_floor, &in.chk_col_cost);
@@ -511,7 +528,7 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     int qrc = FTSGEMM_ERR_UNSUPPORTED;
 #define FT_QUERY(bn, cg) \
   if (BN == bn && CG == cg) qrc = ft ? query_max_units<bn, true, cg>(h, &max_units) : query_max_units<bn, false, cg>(h, &max_units);
-    FT_QUERY(32, 1) FT_QUERY(64, 1) FT_QUERY(128, 1) FT_QUERY(256, 1) FT_QUERY(128, 2) FT_QUERY(256, 2)
+    FT_QUERY(32, 1) FT_QUERY(64, 1) FT_QUERY(128, 1) FT_QUERY(256, 1) FT_QUERY(64, 2) FT_QUERY(128, 2) FT_QUERY(256, 2)
 #undef FT_QUERY
     if (qrc) return qrc;
     if (max_units < 1) return FTSGEMM_ERR_UNSUPPORTED;  // not a single CTA (pair) of this kernel fits on the device partition
@@ -630,6 +647,7 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
   FT_DISPATCH(64, 1)
   FT_DISPATCH(128, 1)
   FT_DISPATCH(256, 1)
+  FT_DISPATCH(64, 2)
   FT_DISPATCH(128, 2)
   FT_DISPATCH(256, 2)
 #undef FT_DISPATCH
@@ -652,8 +670,23 @@ __global__ void fill_kernel(float *p, float v, size_t n) {
   if (i < n) p[i] = v;
 }
 
+// 3xTF32: lo = x - tf32(x) (exact in FP32; the tensor core truncates lo to its own 11 significant bits when it reads it)
+__global__ void split_lo_kernel(const float4 *__restrict__ x, float4 *__restrict__ lo, size_t n4) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(x + i);
+    float4 r;
+    r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    lo[i] = r;
+  }
+}
+
 // fault verdict of the launches since the last ftsgemm_get_stats, as 8 doubles in device memory (ftsgemm_stats_device)
 __global__ void stats_vector_kernel(const DeviceStats *st, double *out) {
+  ptx::pdl_wait();  // launched as a programmatic dependent: the GEMM in front of it must have completed
+  ptx::pdl_launch_dependents();
   if (threadIdx.x == 0) {
     out[0] = static_cast<double>(st->tiles);
     out[1] = static_cast<double>(st->rows_checked);
@@ -733,6 +766,11 @@ int ftsgemm_kernel_table(ftsgemm_kernel_info *out, int cap) {
   return kNumVariants;
 }
 
+int ftsgemm_select_kernel(int M, int N, int K, int fault_tolerant) {
+  if (M <= 0 || N <= 0 || K <= 0) return FTSGEMM_ERR_INVALID_ARG;
+  return select_variant(M, N, fault_tolerant != 0);
+}
+
 int ftsgemm_kernel_lookup(int kernel_id, ftsgemm_kernel_info *out) {
   const Variant *v = find_variant(kernel_id);
   if (!v) return FTSGEMM_ERR_INVALID_ARG;
@@ -746,6 +784,7 @@ int ftsgemm_kernel_lookup(int kernel_id, ftsgemm_kernel_info *out) {
 int ftsgemm_debug_schedule(int kernel_id, int M, int N, int K, int num_sms, int *hdr, int *rows, int cap) {
   const Variant *v = find_variant(kernel_id);
   if (!v || v->info.engine != 1 || M <= 0 || N <= 0 || K <= 0 || num_sms <= 0) return FTSGEMM_ERR_INVALID_ARG;
+  if (v->bn == 0) v = find_variant(select_variant(M, N, v->info.fault_tolerant != 0));
   KernelParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
@@ -841,6 +880,7 @@ int ftsgemm_destroy(ftsgemm_handle_t h) {
     cudaFree(kv.second.d_wave_target);
   }
   cudaFree(h->d_aux);
+  cudaFree(h->d_lo);
   cudaFree(h->d_verify);
   for (int i = 0; i < 3; ++i) cudaFree(h->d_stage[i]);
   if (h->s_in) {
@@ -865,7 +905,7 @@ static int load_opts(const ftsgemm_opts *opts, ftsgemm_opts *o) {
   if (opts->struct_size < FTSGEMM_OPTS_V1_SIZE) return FTSGEMM_ERR_INVALID_ARG;
   memcpy(o, opts, opts->struct_size < sizeof(*o) ? opts->struct_size : sizeof(*o));
   o->struct_size = sizeof(*o);
-  if (o->inject_mode < 0 || o->inject_mode > 2 || o->selftest_row < 0 || o->selftest_col < 0 || o->n_faults < 0 ||
+  if (o->precision < 0 || o->precision > 1 || o->inject_mode < 0 || o->inject_mode > 2 || o->selftest_row < 0 || o->selftest_col < 0 || o->n_faults < 0 ||
       o->n_faults > FTSGEMM_MAX_FAULTS)
     return FTSGEMM_ERR_INVALID_ARG;
   return FTSGEMM_OK;
@@ -882,6 +922,36 @@ int ftsgemm_run(ftsgemm_handle_t h, int kernel_id, int M, int N, int K, const fl
   if (orc) return orc;
   DeviceGuard guard(h);
   cudaStream_t stream = static_cast<cudaStream_t>(o.stream);
+  if (v->info.engine == 1 && v->bn == 0) {  // ids 20 / 40: per-shape choice
+    v = find_variant(select_variant(M, N, v->info.fault_tolerant != 0));
+    if (!v) return FTSGEMM_ERR_UNSUPPORTED;
+  }
+  if (v->info.engine == 1 && o.precision == 1) {
+    // 3xTF32 (FP32-grade accuracy, the reference's kernels are true FP32 FFMA, ft_sgemm_huge.cuh:228-323): with
+    // x = hi + lo (hi = the 11 significant bits the tensor core reads, lo = x - hi exactly),
+    //   A B^T ~= A_lo B_hi^T + A_hi B_lo^T + A_hi B_hi^T       (A_lo B_lo^T ~ 2^-22 relative is dropped)
+    // as three launches of the same kernel, smallest terms first, each accumulating into C -- every one of them a
+    // complete fault-tolerant GEMM with its own checksum vectors, so ABFT covers the whole 3-pass product.
+    if ((static_cast<size_t>(M) * K) % 4 || (static_cast<size_t>(N) * K) % 4) return FTSGEMM_ERR_UNSUPPORTED;
+    const size_t need = (static_cast<size_t>(M) + N) * K * sizeof(float);
+    int rc = ensure_buf(h, &h->d_lo, &h->lo_bytes, need);
+    if (rc) return rc;
+    float *dAlo = h->d_lo, *dBlo = h->d_lo + static_cast<size_t>(M) * K;
+    split_lo_kernel<<<h->num_sms * 8, 256, 0, stream>>>(reinterpret_cast<const float4 *>(dA), reinterpret_cast<float4 *>(dAlo),
+                                                        static_cast<size_t>(M) * K / 4);
+    split_lo_kernel<<<h->num_sms * 8, 256, 0, stream>>>(reinterpret_cast<const float4 *>(dB), reinterpret_cast<float4 *>(dBlo),
+                                                        static_cast<size_t>(N) * K / 4);
+    FT_CUDA(h, cudaGetLastError());
+    ftsgemm_opts o3 = o;
+    o3.reuse_b_checksums = 0;
+    o3.precision = 0;
+    ftsgemm_opts o_quiet = o3;  // injected faults belong to the main product only
+    o_quiet.inject_mode = 0;
+    rc = run_tc(h, *v, M, N, K, dAlo, dB, dC, alpha, beta, o_quiet, stream);
+    if (!rc) rc = run_tc(h, *v, M, N, K, dA, dBlo, dC, alpha, 1.0f, o_quiet, stream);
+    if (!rc) rc = run_tc(h, *v, M, N, K, dA, dB, dC, alpha, 1.0f, o3, stream);
+    return rc;
+  }
   switch (v->info.engine) {
     case 0: return run_cublas(h, v->info.id == 7, M, N, K, dA, dB, dC, alpha, beta, stream);
     case 1: return run_tc(h, *v, M, N, K, dA, dB, dC, alpha, beta, o, stream);
@@ -926,8 +996,20 @@ int ftsgemm_stats_device(ftsgemm_handle_t h, double *d_out8, void *stream_v) {
   if (!d_out8) return FTSGEMM_ERR_INVALID_ARG;
   DeviceGuard guard(h);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  stats_vector_kernel<<<1, 32, 0, stream>>>(h->d_stats, d_out8);
-  FT_CUDA(h, cudaGetLastError());
+  // a programmatic dependent of the GEMM it reports on, and a programmatic primary of the next launch: the launch chain
+  // of back-to-back steps is not broken by the snapshot
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(1);
+  cfg.blockDim = dim3(32);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = dbg("pdl_chain", 1) != 0 ? 1 : 0;
+  const DeviceStats *st = h->d_stats;
+  FT_CUDA(h, cudaLaunchKernelEx(&cfg, stats_vector_kernel, st, d_out8));
   return FTSGEMM_OK;
 }
 

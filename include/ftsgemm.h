@@ -54,11 +54,13 @@ enum {
   FTSGEMM_ID_ABFT_BASELINE = 10,
   FTSGEMM_ID_ABFT_SMALL = 11, FTSGEMM_ID_ABFT_MEDIUM = 12, FTSGEMM_ID_ABFT_LARGE = 13,
   FTSGEMM_ID_ABFT_TALL = 14, FTSGEMM_ID_ABFT_WIDE = 15, FTSGEMM_ID_ABFT_HUGE = 16,
+  FTSGEMM_ID_SGEMM_AUTO = 20,        /* plain tcgen05 kernel, variant chosen per shape (ftsgemm_select_kernel)  (B200 extra) */
   FTSGEMM_ID_SGEMM_GIANT = 21,       /* 256 x 256 tile on a CTA pair (cta_group::2), plain  (B200 extra) */
-  FTSGEMM_ID_SGEMM_PAIR128 = 22,     /* 256 x 128 tile on a CTA pair, plain  (B200 extra) */
+  FTSGEMM_ID_SGEMM_PAIR128 = 22,     /* 256 x 128 tile on a CTA pair, plain: alias of "large" (id 3) */
   FTSGEMM_ID_ABFT_BASELINE_TF32 = 30,/* non-fused baseline with TF32 tensor-op math */
   FTSGEMM_ID_ABFT_GIANT = 31,        /* 256 x 256 CTA-pair tile, fused ABFT: the bench configuration (B200 extra) */
-  FTSGEMM_ID_ABFT_PAIR128 = 32       /* 256 x 128 CTA-pair tile, fused ABFT (B200 extra) */
+  FTSGEMM_ID_ABFT_PAIR128 = 32,      /* 256 x 128 CTA-pair tile, fused ABFT: alias of "large" (id 13) */
+  FTSGEMM_ID_ABFT_AUTO = 40          /* fused ABFT, variant chosen per shape (ftsgemm_select_kernel)  (B200 extra) */
 };
 
 typedef struct ftsgemm_handle_s *ftsgemm_handle_t;
@@ -106,6 +108,10 @@ typedef struct ftsgemm_opts {
   int baseline_host_sync;/* id 10/30: 1 = host-synchronise between stages like the reference
                             (baseline_ft_sgemm.cuh:7,19,26,30); 0 = stream-ordered */
   /* ---- ABI version 2 ---- */
+  int precision;         /* 0 (default): single-pass TF32 (operands truncated to 11 significant bits by the tensor core,
+                            FP32 accumulate; norm-wise 1e-3 against FP32) | 1: 3xTF32 -- hi/lo split of A and B, three
+                            fault-tolerant passes A_lo*B + A*B_lo + A*B: FP32-grade, element-wise parity with the
+                            reference's FP32 FFMA kernels (ft_sgemm_huge.cuh:228-323) at ~1/3 of the throughput */
   int no_recompute;      /* 0 (default): a row that is flagged but cannot be repaired from its two checksums (upset too
                             small to locate, two upsets in one row) is RECOMPUTED from A and B on CUDA cores and counted
                             in stats.recomputed -- nothing detected is stored as computed; 1: leave such rows as computed
@@ -152,6 +158,9 @@ void ftsgemm_default_opts(ftsgemm_opts *o);
 /* ---- kernel-variant table  (replaces sgemm.cu:235-237 + code_gen/main.py:8-16) --------------------------- */
 int ftsgemm_kernel_table(ftsgemm_kernel_info *out, int cap); /* returns number of rows (fills min(cap, rows)) */
 int ftsgemm_kernel_lookup(int kernel_id, ftsgemm_kernel_info *out);
+/* The concrete tcgen05 kernel id that ids 20 / 40 (AUTO) resolve to for this shape (replaces the reference's manual
+ * choice of a variant per run, sgemm.cu:110-199).  Returns the id (> 0) or a negative error code. */
+int ftsgemm_select_kernel(int M, int N, int K, int fault_tolerant);
 
 /* ---- the kernel contract  (replaces `kernel<<<grid,block>>>(M,N,K,dA,dB,dC,alpha,beta)` selected by id,
  *      sgemm.cu:110-199, and cublasSgemm at sgemm.cu:108,198,260) ---------------------------------------------

@@ -46,17 +46,29 @@ def test_kernel_table_matches_reference_ids(ft):
         assert tab[ft.SGEMM_IDS[nm]]["tile"] == tab[ft.ABFT_IDS[nm]]["tile"]  # FT and non-FT share the tiling
     # config 2 of BASELINE.json: the huge tile is literally 128 x 128 with UMMA K = 8 steps
     assert tab[16]["tile"][:2] == (128, 128) and tab[14]["tile"][:2] == (128, 32)
+    # six names, six DISTINCT sm_100a tiles (round 1 aliased small = tall and large = huge)
+    tiles = {nm: tab[ft.SGEMM_IDS[nm]]["tile"][:2] for nm in ref_tiles}
+    assert len(set(tiles.values())) == 6, tiles
+    assert tiles == {"small": (128, 64), "medium": (256, 64), "large": (256, 128), "tall": (128, 32), "wide": (128, 256),
+                     "huge": (128, 128)}
     # UMMA legality of every tcgen05 tile: M = 128 (cta_group::1) or 256 (cta_group::2), N % 16 == 0, 16 <= N <= 256
     for k in tab.values():
-        if k["engine"] == 1:
+        if k["engine"] == 1 and k["id"] not in (ft.ID_SGEMM_AUTO, ft.ID_ABFT_AUTO):
             m, n, kk = k["tile"]
             assert m in (128, 256) and n % 16 == 0 and 16 <= n <= 256 and kk % 8 == 0
+    # AUTO ids resolve per shape to a concrete variant of the right kind (no GPU needed)
+    for (M, N) in ((1024, 1024), (2048, 2048), (4096, 4096), (256, 16384), (16384, 16384)):
+        a, b = ft.select_kernel(M, N, 1024, False), ft.select_kernel(M, N, 1024, True)
+        assert tab[a]["engine"] == 1 and not tab[a]["fault_tolerant"] and tab[b]["fault_tolerant"]
+        assert tab[a]["tile"] == tab[b]["tile"]
+    assert ft.select_kernel(4096, 4096, 4096, True) == 31 and ft.select_kernel(1024, 1024, 1024, False) == 3
 
 
 def test_opts_struct_layout(ft):
     o = ft.default_opts()
     assert o.struct_size == C.sizeof(ft.Opts)
     assert o.selftest_value == 10000.0 and o.inject_mode == 0 and o.baseline_host_sync == 1
+    assert o.precision == 0 and o.no_recompute == 0
     o = ft.make_opts(faults=[{"row": 1, "col": 2, "xor": 1 << 30}, {"row": 3, "col": 4, "add": 2.5}])
     assert o.inject_mode == 2 and o.n_faults == 2 and o.faults[0].xor_mask == 1 << 30 and o.faults[1].add_value == 2.5
 

@@ -493,6 +493,53 @@ def test_fault_campaign_floors(cuda, ft, dev):
             assert det == inj and worst <= 1e-4 * scale, (bit, det, inj, worst, scale)
 
 
+# ------------------------------------------------------------------ 3xTF32: FP32-grade accuracy mode
+def test_3xtf32_elementwise_fp32_parity(cuda, ft, dev, oracle):
+    """opts.precision = 1: hi/lo split of A and B, three fault-tolerant passes.  ELEMENT-wise parity with the FP32
+    oracle (the reference's kernels are true FP32 FFMA): |got - want| <= 1e-3 * |want| + 1e-5 * rms(want) for every
+    element, zero failures of the reference's own comparator, norm-wise < 5e-6 (measured 2.7e-6; single-pass TF32: 6e-4); alpha / beta;
+    an injected fault in the main pass is still detected and repaired."""
+    for n in (512, 1024):
+        A, B, C0 = oracle.make_inputs(n)
+        want = oracle.sgemm_nt(n, n, n, 1.0, A, B, 0.0, C0.copy())
+        rms = float(np.sqrt(np.mean(want.astype(np.float64) ** 2)))
+        for kid in (31, 16, 21, ft.ID_ABFT_AUTO):
+            dev.stats()
+            got = _run(cuda, dev, kid, n, n, n, A, B, C0, opts=ft.make_opts(precision=1))
+            d = np.abs(got.astype(np.float64) - want.astype(np.float64))
+            assert np.all(d <= 1e-3 * np.abs(want) + 1e-5 * rms), (kid, n, float(d.max()))
+            assert oracle.verify_matrix(want, got, n, n) == -1
+            assert oracle.error_metrics(want, got)["rel_fro"] < 5e-6, (kid, oracle.error_metrics(want, got))
+            if kid != 21:
+                st = dev.stats()
+                assert st["detected"] == 0 and st["rows_checked"] >= 3 * n * (n // 256)  # three checked passes
+    rng = np.random.default_rng(2)
+    M, N, K = 384, 640, 1000
+    A, B = rng.standard_normal(M * K).astype(np.float32), rng.standard_normal(N * K).astype(np.float32)
+    C0 = rng.standard_normal(M * N).astype(np.float32)
+    want = oracle.sgemm_nt(M, N, K, 0.75, A, B, -1.5, C0.copy())
+    dev.stats()
+    got = _run(cuda, dev, 31, M, N, K, A, B, C0, 0.75, -1.5,
+               opts=ft.make_opts(precision=1, faults=[{"row": 100, "col": 300, "xor": 1 << 30}]))
+    st = dev.stats()
+    assert st["detected"] == 1 and st["corrected"] + st["recomputed"] == 1, st
+    assert oracle.error_metrics(want, got)["rel_fro"] < 5e-6
+    x1 = _run(cuda, dev, 31, M, N, K, A, B, C0, 0.75, -1.5)
+    assert oracle.error_metrics(want, x1)["rel_fro"] > 1e-4  # (single-pass TF32 for comparison)
+
+
+def test_auto_ids_resolve_and_run(cuda, ft, dev, oracle):
+    """ids 20 / 40 pick the variant per shape (ftsgemm_select_kernel) and give bit-for-bit the result of that variant."""
+    rng = np.random.default_rng(4)
+    for (M, N, K) in ((512, 768, 256), (2304, 2304, 128)):
+        A, B = _rand(rng, M * K), _rand(rng, N * K)
+        C0 = np.zeros(M * N, np.float32)
+        for auto, is_ft in ((ft.ID_SGEMM_AUTO, False), (ft.ID_ABFT_AUTO, True)):
+            kid = ft.select_kernel(M, N, K, is_ft)
+            assert np.array_equal(_run(cuda, dev, auto, M, N, K, A, B, C0), _run(cuda, dev, kid, M, N, K, A, B, C0))
+    assert dev.stats()["detected"] == 0
+
+
 # ------------------------------------------------------------------ host-buffer (e2e) entry point
 def test_run_host_matches_device_path(cuda, ft, dev, oracle):
     n = 384

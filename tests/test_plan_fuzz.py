@@ -4,17 +4,17 @@ tests/test_schedule.py, which enumerates fixed shapes)."""
 import pytest
 from hypothesis import HealthCheck, given, settings, strategies as st
 
-from test_schedule import TILE_N, _simulate
+from test_schedule import PAIR_IDS, TILE_N, _simulate
 
 
 @settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
-@given(kid=st.sampled_from([1, 2, 6, 5, 21, 22, 11, 12, 16, 15, 31, 32]),
+@given(kid=st.sampled_from([1, 2, 3, 4, 6, 5, 21, 22, 11, 12, 13, 14, 16, 15, 31, 32]),
        m4=st.integers(1, 3000), n4=st.integers(1, 3000), K=st.integers(1, 20000),
        sms=st.sampled_from([148, 132, 20, 8, 2]), splitk=st.sampled_from([-1, 0, 2, 3, 4]))
 def test_random_plans(ft, kid, m4, n4, K, sms, splitk):
     M, N = 4 * m4, 4 * n4
     bn = TILE_N[kid]
-    cg = 2 if kid in (21, 22, 31, 32) else 1
+    cg = 2 if kid in PAIR_IDS else 1
     if (-(-M // (128 * cg))) * (-(-N // bn)) > 20000:   # keep one example cheap
         M = min(M, 128 * cg * 100)
         N = min(N, bn * 100)

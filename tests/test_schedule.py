@@ -9,7 +9,9 @@ import itertools
 
 import pytest
 
-TILE_N = {1: 32, 2: 64, 6: 128, 5: 256, 21: 256, 22: 128, 11: 32, 12: 64, 16: 128, 15: 256, 31: 256, 32: 128}
+TILE_N = {1: 64, 2: 64, 3: 128, 4: 32, 6: 128, 5: 256, 21: 256, 22: 128, 11: 64, 12: 64, 13: 128, 14: 32, 16: 128, 15: 256, 31: 256,
+          32: 128}
+PAIR_IDS = (2, 3, 12, 13, 21, 22, 31, 32)  # CTA-pair tiles (cta_group::2)
 
 
 def _simulate(hdr, segs, acc_stages):
@@ -58,7 +60,7 @@ def _simulate(hdr, segs, acc_stages):
     return all(epi_done[u] == len(per_unit[u]) for u in range(units))
 
 
-@pytest.mark.parametrize("kid", [1, 6, 5, 21, 22, 12, 16, 15, 31, 32])
+@pytest.mark.parametrize("kid", [1, 4, 6, 5, 21, 22, 12, 13, 14, 16, 15, 31, 32])
 @pytest.mark.parametrize("shape", [(4096, 4096, 4096), (2048, 2048, 2048), (1024, 1024, 1024), (8192, 8192, 512),
                                    (1536, 2560, 1000), (256, 256, 64), (128, 4096, 32), (5120, 384, 4096),
                                    (16384, 16384, 1024), (32768, 1024, 256)])
@@ -110,7 +112,7 @@ def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms):
     # checksum tiles: n_chk_tiles of them, 8 columns per N-tile
     chk = {(s["m_blk"], s["n_blk"]) for s in segs if s["is_chk"]}
     assert len(chk) == hdr["n_chk_tiles"]
-    if kid in (11, 12, 16, 15, 31, 32):
+    if kid in (11, 12, 13, 14, 16, 15, 31, 32):
         tiles_n = -(-N // TILE_N[kid])
         assert hdr["n_chk_tiles"] == -(-M // (128 * hdr["cta_group"])) * -(-(tiles_n * 4) // TILE_N[kid])
     acc_stages = 2 if 2 * TILE_N[kid] <= 512 else 1
