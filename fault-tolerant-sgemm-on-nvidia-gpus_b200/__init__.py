@@ -82,7 +82,7 @@ EXPORTED_SYMBOLS = [
     "ftsgemm_create", "ftsgemm_destroy", "ftsgemm_abi_version", "ftsgemm_error_string", "ftsgemm_last_cuda_error",
     "ftsgemm_default_opts", "ftsgemm_kernel_table", "ftsgemm_kernel_lookup", "ftsgemm_run", "ftsgemm_get_stats",
     "ftsgemm_run_host", "ftsgemm_baseline", "ftsgemm_verify", "ftsgemm_debug_set", "ftsgemm_debug_schedule",
-    "ftsgemm_verify_bad_count", "ftsgemm_debug_trace", "ftsgemm_stats_device", "ftsgemm_select_kernel",
+    "ftsgemm_verify_bad_count", "ftsgemm_debug_trace", "ftsgemm_stats_device", "ftsgemm_select_kernel", "ftsgemm_launch_count",
 ]
 
 _lib = None
@@ -119,6 +119,8 @@ def lib():
         L.ftsgemm_run_host.argtypes = [vp, ip, ip, ip, ip, vp, vp, vp, fp, fp, C.POINTER(Opts)]
         L.ftsgemm_stats_device.argtypes = [vp, vp, vp]
         L.ftsgemm_select_kernel.argtypes = [ip, ip, ip, ip]
+        L.ftsgemm_launch_count.argtypes = [vp]
+        L.ftsgemm_launch_count.restype = C.c_ulonglong
         L.ftsgemm_baseline.argtypes = [vp, ip, ip, ip, vp, vp, vp, fp, fp, ip, C.POINTER(Opts), vp]
         L.ftsgemm_verify.argtypes = [vp, vp, vp, ip, ip, C.POINTER(C.c_longlong), C.POINTER(C.c_double), vp]
         L.ftsgemm_debug_set.argtypes = [C.c_char_p, C.c_longlong]
@@ -260,6 +262,10 @@ class FtSgemm:
         s = Stats()
         self._run_checked(lib().ftsgemm_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def launch_count(self) -> int:
+        """Kernels of this library launched through the handle so far (include/ftsgemm.h)."""
+        return int(lib().ftsgemm_launch_count(self._h))
 
     def stats_device(self, d_out8, stream=None) -> None:
         """Device-side verdict vector (8 doubles, see include/ftsgemm.h), asynchronous on `stream`, counters not reset."""

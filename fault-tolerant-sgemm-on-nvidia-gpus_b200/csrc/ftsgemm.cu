@@ -113,6 +113,8 @@ struct ftsgemm_handle_s {
   size_t chk_out_bytes = 0;
   const float *chk_for_b = nullptr;  // B pointer / shape the panel was encoded from
   int chk_n = 0, chk_k = 0, chk_bn = 0;
+  int *d_enc_done = nullptr;    // front-phase encode: warps done, monotonic over launches
+  int enc_done_value = 0;
   float *d_lo = nullptr;        // 3xTF32: A_lo | B_lo
   size_t lo_bytes = 0;
   float *d_aux = nullptr;       // baseline vectors
@@ -142,6 +144,7 @@ struct ftsgemm_handle_s {
   double *d_verify = nullptr;   // {first_bad (as long long), num, den}
   std::map<int, int> max_units;     // per kernel instantiation (BN * 8 + FT * 4 + CG): co-resident CTAs / CTA pairs
   cudaStream_t last_stream = nullptr;
+  unsigned long long launch_count = 0;  // kernels of THIS library launched through the handle (ftsgemm_launch_count)
   int last_cuda_error = 0;
   unsigned long long last_verify_bad = 0;
 };
@@ -422,6 +425,7 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
   p.stats = h->d_stats;
 
   CUtensorMap tmA, tmB, tmC;
+  bool enc_front = false;
   const bool allow3d = dbg("tma3d", 1) != 0;
   int rc;
   if (allow3d && M % kAtomMN == 0) {
@@ -464,7 +468,18 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     p.chk_epoch = ++h->chk_epoch;
     p.dbg_flags = static_cast<int>(dbg("ft_dbg", 0)) & 1;
     const bool reuse = o.reuse_b_checksums && h->chk_for_b == dB && h->chk_n == N && h->chk_k == K && h->chk_bn == BN;
-    if (!reuse) {
+    // Default: the encode is a FRONT PHASE of the GEMM kernel (KernelParams::enc_front) -- one launch per fused GEMM, like
+    // the reference (sgemm.cu:191-192).  Measured equal to the stand-alone pre-pass within noise from 2048^3 to 12288^3
+    // (profiles/r02_front_phase_vs_prepass.jsonl: 200.0 vs 200.6 us at 4096^3, 1437 vs 1442 at 8192^3, -2.6 us at 2560^3);
+    // only below ~8 MB of B (1024^3: 23.0 vs 22.1 us) the two-launch form is kept.
+    const long long ef = dbg("enc_front", -2);
+    enc_front = !reuse && (ef >= 0 ? ef != 0 : 4.0 * N * static_cast<double>(K) >= static_cast<double>(dbg("enc_front_min_mb", 8)) * 1048576.0);
+    if (enc_front) {
+      p.enc_front = 1;
+      p.enc_out = h->d_chk;
+      p.enc_ld = chk_ld;
+    }
+    if (!reuse && !enc_front) {
       // stand-alone pre-pass in the caller's stream
       const int rounding = static_cast<int>(dbg("enc_rounding", 0));
       // grid-stride over (column block, k-row group) items.  Item size (8 / 4 KiB) and grid (2 / 4 blocks per SM) make no
@@ -496,6 +511,7 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     else FT_CUDA(h, cudaLaunchKernelEx(&ec, encode_b_kernel<bn, 8, false>, eb, en, ek, en, eo, el, er, et));                \
   }
       FT_ENC(32) FT_ENC(64) FT_ENC(128) FT_ENC(256)
+      ++h->launch_count;
 #undef FT_ENC
       FT_CUDA(h, cudaGetLastError());
       // The GEMM launch below becomes a programmatic dependent of this kernel: its CTAs start on SMs as they drain, and
@@ -574,6 +590,20 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     cp.uploaded = true;
   }
   const int units = cp.plan.units;
+  if (enc_front) {
+    const int inc = units * CG * (kThreads / 32);
+    if (h->d_enc_done == nullptr) {
+      FT_CUDA(h, cudaMalloc(&h->d_enc_done, sizeof(int)));
+      FT_CUDA(h, cudaMemsetAsync(h->d_enc_done, 0, sizeof(int), stream));
+      h->enc_done_value = 0;
+    } else if (h->enc_done_value > (1 << 30) - inc) {
+      FT_CUDA(h, cudaMemsetAsync(h->d_enc_done, 0, sizeof(int), stream));
+      h->enc_done_value = 0;
+    }
+    h->enc_done_value += inc;
+    p.enc_done = h->d_enc_done;
+    p.enc_target = h->enc_done_value;
+  }
   p.plan = cp.d_items;
   p.plan_off = cp.d_off;
   p.sk_tiles = cp.plan.sk_tiles;
@@ -638,6 +668,7 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
   // thread executes griddepcontrol.wait before the first global access.
   if (p.pdl_wait == 0 && dbg("pdl_chain", 1) != 0) p.pdl_wait = 2;
   h->last_stream = stream;
+  ++h->launch_count;
   int lrc = FTSGEMM_ERR_UNSUPPORTED;
 #define FT_DISPATCH(bn, cg)                                                          \
   if (BN == bn && CG == cg)                                                          \
@@ -881,6 +912,7 @@ int ftsgemm_destroy(ftsgemm_handle_t h) {
   }
   cudaFree(h->d_aux);
   cudaFree(h->d_lo);
+  cudaFree(h->d_enc_done);
   cudaFree(h->d_verify);
   for (int i = 0; i < 3; ++i) cudaFree(h->d_stage[i]);
   if (h->s_in) {
@@ -896,6 +928,8 @@ int ftsgemm_destroy(ftsgemm_handle_t h) {
 }
 
 int ftsgemm_last_cuda_error(ftsgemm_handle_t h) { return h ? h->last_cuda_error : 0; }
+
+unsigned long long ftsgemm_launch_count(ftsgemm_handle_t h) { return h ? h->launch_count : 0ull; }
 
 // Copies the caller's options over the defaults.  struct_size is the caller's sizeof(ftsgemm_opts): anything smaller
 // than the first published layout (e.g. 0 from a zero-initialised struct) is an error, not "all defaults".
@@ -942,6 +976,7 @@ int ftsgemm_run(ftsgemm_handle_t h, int kernel_id, int M, int N, int K, const fl
     split_lo_kernel<<<h->num_sms * 8, 256, 0, stream>>>(reinterpret_cast<const float4 *>(dB), reinterpret_cast<float4 *>(dBlo),
                                                         static_cast<size_t>(N) * K / 4);
     FT_CUDA(h, cudaGetLastError());
+    h->launch_count += 2;
     ftsgemm_opts o3 = o;
     o3.reuse_b_checksums = 0;
     o3.precision = 0;
@@ -1010,6 +1045,7 @@ int ftsgemm_stats_device(ftsgemm_handle_t h, double *d_out8, void *stream_v) {
   cfg.numAttrs = dbg("pdl_chain", 1) != 0 ? 1 : 0;
   const DeviceStats *st = h->d_stats;
   FT_CUDA(h, cudaLaunchKernelEx(&cfg, stats_vector_kernel, st, d_out8));
+  ++h->launch_count;
   return FTSGEMM_OK;
 }
 

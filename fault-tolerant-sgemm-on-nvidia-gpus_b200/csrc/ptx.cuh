@@ -131,6 +131,8 @@ __device__ __forceinline__ uint32_t ld_acquire_shared_u32(uint32_t addr) {
 
 // Orders preceding generic-proxy memory operations (e.g. an acquire load that observed another kernel's writes) before
 // subsequent async-proxy operations (TMA loads of that data).
+// release / acquire fence at GPU scope (MEMBAR.ALL.GPU; __threadfence() is the sequentially consistent MEMBAR.SC.GPU)
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------- TMA

@@ -153,6 +153,10 @@ int ftsgemm_destroy(ftsgemm_handle_t h);
 int ftsgemm_abi_version(void);
 const char *ftsgemm_error_string(int code);
 int ftsgemm_last_cuda_error(ftsgemm_handle_t h); /* cudaError_t / CUresult of the last failure, 0 if none */
+/* Number of kernels of THIS library (fused GEMM, encode pre-pass, hi/lo split, verdict snapshot; not cuBLAS') launched
+ * through the handle since it was created: a fused ABFT GEMM is 1 launch (the encode is a front phase of the kernel),
+ * 2 below ~8 MB of B (separate pre-pass) -- what bench.py reports as gpu_launches. */
+unsigned long long ftsgemm_launch_count(ftsgemm_handle_t h);
 void ftsgemm_default_opts(ftsgemm_opts *o);
 
 /* ---- kernel-variant table  (replaces sgemm.cu:235-237 + code_gen/main.py:8-16) --------------------------- */
