@@ -24,9 +24,10 @@ OUT = ROOT / "gpurun_out"
 KEY = ("UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "STTM", "UTCBAR", "UTCCP", "UTMAPF", "SYNCS", "HMMA",
        "FFMA", "LDG", "STG", "LDS", "STS", "SHFL", "BAR", "MEMBAR", "ATOM", "RED", "DADD", "ELECT")
 # kernel id -> (template instantiation, role) : one id per distinct binary
-IDS = {1: "32,plain,cg1 (small / tall)", 2: "64,plain,cg1 (medium)", 6: "128,plain,cg1 (large / huge)", 5: "256,plain,cg1 (wide)",
-       22: "128,plain,cg2 (pair128)", 21: "256,plain,cg2 (giant)", 11: "32,abft,cg1", 12: "64,abft,cg1", 16: "128,abft,cg1",
-       15: "256,abft,cg1", 32: "128,abft,cg2", 31: "256,abft,cg2 (bench)"}
+IDS = {1: "128x64 plain cg1 (small)", 2: "256x64 plain cg2 (medium)", 3: "256x128 plain cg2 (large / pair128)", 4: "128x32 plain cg1 (tall)",
+       5: "128x256 plain cg1 (wide)", 6: "128x128 plain cg1 (huge)", 21: "256x256 plain cg2 (giant)",
+       11: "128x64 abft cg1", 12: "256x64 abft cg2", 13: "256x128 abft cg2", 14: "128x32 abft cg1", 15: "128x256 abft cg1",
+       16: "128x128 abft cg1 (config 2 literal)", 31: "256x256 abft cg2 (bench)"}
 
 
 def demangle(name):
@@ -84,7 +85,12 @@ def ncu(n):
     # the encode pre-pass of the bench kernel
     rep = OUT / f"r02_ncu_encode_{n}"
     subprocess.run(["ncu", "--set", "full", "--clock-control", "none", "-k", "regex:encode_b_kernel", "-s", "2", "-c", "1", "-f", "-o",
-                    str(rep), sys.executable, str(ROOT / "scripts" / "run_one.py"), "31", str(n), "3"], capture_output=True, text=True)
+                    str(rep), sys.executable, str(ROOT / "scripts" / "run_one.py"), "31", str(n), "3", "enc_front=0"], capture_output=True, text=True)
+    # gpurun brings back at most 64 MiB: summarise on the box, keep only the reports of the bench kernel and its plain twin
+    summarize()
+    for rep in OUT.glob("r02_ncu_*.ncu-rep"):
+        if not re.search(r"id(31|21)_", rep.name):
+            rep.unlink()
 
 
 METRICS = {"gpu__time_duration.sum": "duration_us", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pipe_pct_of_active",
@@ -92,7 +98,11 @@ METRICS = {"gpu__time_duration.sum": "duration_us", "sm__pipe_tensor_cycles_acti
            "sm__inst_executed_pipe_tensor.sum": "tensor_inst", "dram__bytes_read.sum": "dram_read_bytes", "dram__bytes_write.sum": "dram_write_bytes",
            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct_of_peak", "lts__t_sector_hit_rate.pct": "l2_hit_pct",
            "launch__registers_per_thread": "registers", "launch__grid_size": "grid", "sm__cycles_elapsed.avg.per_second": "sm_hz"}
-UNIT = {"nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+UNIT = {"nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0, "msecond": 1e3, "ms": 1e3, "second": 1e6, "s": 1e6, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def mode_is_ncu():
+    return len(sys.argv) > 1 and sys.argv[1] == "ncu"
 
 
 def summarize():
@@ -112,14 +122,18 @@ def summarize():
                     continue
                 rec[METRICS[h]] = v * UNIT.get(units[i], 1.0) if units[i] in UNIT else v
         key = rep.stem.replace("r02_ncu_", "")
+        m0 = re.match(r"id(\d+)_", key)
+        if m0 and int(m0.group(1)) in IDS:
+            rec["variant"] = IDS[int(m0.group(1))]
         if "dram_read_bytes" in rec:
             rec["dram_bytes"] = rec["dram_read_bytes"] + rec.get("dram_write_bytes", 0.0)
         out[key] = rec
         m = re.match(r"id(\d+)_(\d+)", key)
         if m and "dram_bytes" in rec:
             traffic.setdefault(m.group(1), {})[m.group(2)] = int(rec["dram_bytes"])
-    (PROF / "r02_ncu_summary.json").write_text(json.dumps(out, indent=1, sort_keys=True))
-    tp = PROF / "traffic.json"
+    dest = OUT if mode_is_ncu() else PROF
+    (dest / "r02_ncu_summary.json").write_text(json.dumps(out, indent=1, sort_keys=True))
+    tp = dest / "traffic.json"
     old = {}
     if tp.exists():
         try:
