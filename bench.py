@@ -458,11 +458,13 @@ def main():
             sub.dA, sub.dB, sub.dC = big.dA, big.dB, big.dC
             res = {"abft": [], "plain": [], "cublas_tf32": []}
             for _ in range(3):  # engines interleaved, idle gaps in between: every cell in the same clock state
-                for key, kid, o in (("cublas_tf32", 7, o_cmp), ("abft", 31, opts), ("plain", 21, o_cmp)):
+                # ids 40 / 20: the library's per-shape choice (ftsgemm_select_kernel): 256x256 pair tile from 1536 / 2048 on
+                for key, kid, o in (("cublas_tf32", 7, o_cmp), ("abft", pkg.ID_ABFT_AUTO, opts), ("plain", pkg.ID_SGEMM_AUTO, o_cmp)):
                     time.sleep(0.02)
                     res[key].append(sub.time_engine(kid, cell, o=o, warm=3))
             med = {k: statistics.median(v) for k, v in res.items()}
-            sweep.append({"n": s, "abft_id": 31, "steps": cell, "abft_gflops": round(med["abft"], 1),
+            sweep.append({"n": s, "abft_id": pkg.select_kernel(s, s, s, True), "plain_id": pkg.select_kernel(s, s, s, False),
+                          "steps": cell, "abft_gflops": round(med["abft"], 1),
                           "plain_gflops": round(med["plain"], 1), "cublas_tf32_gflops": round(med["cublas_tf32"], 1),
                           "overhead_pct_vs_cublas_tf32": round(100.0 * (med["cublas_tf32"] / med["abft"] - 1.0), 2),
                           "overhead_pct_vs_own_plain_kernel": round(100.0 * (med["plain"] / med["abft"] - 1.0), 2)})

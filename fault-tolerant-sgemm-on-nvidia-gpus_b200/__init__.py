@@ -191,7 +191,7 @@ def make_opts(stream=None, selftest=None, faults=None, tau_abs=0.0, tau_rel=0.0,
 
 def debug_schedule(kernel_id: int, M: int, N: int, K: int, num_sms: int = 148):
     """Work decomposition of one launch, enumerated on the host (no GPU needed): (header dict, list of segment dicts)."""
-    hdr = (C.c_int * 7)()
+    hdr = (C.c_int * 8)()
     n = lib().ftsgemm_debug_schedule(kernel_id, M, N, K, num_sms, hdr, None, 0)
     if n < 0:
         _check(n)
@@ -199,7 +199,7 @@ def debug_schedule(kernel_id: int, M: int, N: int, K: int, num_sms: int = 148):
     lib().ftsgemm_debug_schedule(kernel_id, M, N, K, num_sms, hdr, rows, n)
     keys = ("unit", "tile", "is_chk", "m_blk", "n_blk", "kb_begin", "kb_end", "kind", "slice")
     segs = [dict(zip(keys, rows[9 * i:9 * i + 9])) for i in range(n)]
-    return dict(zip(("units", "num_tiles", "n_chk_tiles", "sk_tiles", "num_kb", "cta_group", "sk_slices"), hdr)), segs
+    return dict(zip(("units", "num_tiles", "n_chk_tiles", "sk_tiles", "num_kb", "cta_group", "sk_slices", "chk_slices"), hdr)), segs
 
 
 def debug_set(key: str, value: int) -> None:

@@ -72,12 +72,13 @@ const Variant *find_variant(int id) {
 }
 
 // Per-shape choice of the tcgen05 variant (replaces the reference's manual id choice, sgemm.cu:110-199).
-// Measured on B200 (profiles/r02_sweep_small_ids.jsonl, 20-launch bursts): from ~40 tiles of 256x256 on (2048^2 and up)
-// the CTA-pair tile 256x256 wins for both engines (2048^3: 37 us vs 42 us for 256x128 with ABFT); below that the 74 CTA
-// pairs are mostly idle with 256x256 tiles and the 256x128 pair tile is ahead (1024^3 plain: 15.3 vs 18.8 us).
+// Measured on B200 (profiles/r02_sweep_small_all_variants.jsonl, r02_small_slices_*.jsonl; 20-launch bursts, us per
+// launch): with few tiles the 74 CTA pairs are mostly idle with 256x256 tiles and the 256x128 pair tile ("large") is ahead --
+//   plain: 1024^3 12.4 vs 17.0, 1536^3 16.4 vs 21.9, 2048^3 32.7 vs 27.8  -> giant from 49 tiles of 256x256 on;
+//   ABFT:  1024^3 18.6 vs 22.2, 1536^3 33.8 vs 28.2                          -> giant from 25 tiles on.
 int select_variant(int M, int N, bool ft) {
   const long long tiles256 = (static_cast<long long>(M) + 255) / 256 * ((static_cast<long long>(N) + 255) / 256);
-  if (tiles256 >= 40) return ft ? FTSGEMM_ID_ABFT_GIANT : FTSGEMM_ID_SGEMM_GIANT;
+  if (tiles256 >= (ft ? 25 : 49)) return ft ? FTSGEMM_ID_ABFT_GIANT : FTSGEMM_ID_SGEMM_GIANT;
   return ft ? FTSGEMM_ID_ABFT_LARGE : FTSGEMM_ID_SGEMM_LARGE;
 }
 
@@ -322,7 +323,8 @@ PlanInput make_plan_input(int max_units, int CG, int BN, int K, const KernelPara
   PlanInput in;
   long long units = dbg("grid", 0);
   in.units = (units > 0 && units <= max_units) ? static_cast<int>(units) : max_units;
-  in.n_chk_tiles = p.tiles_c * p.tiles_m;
+  in.chk_slices = p.chk_slices > 1 ? p.chk_slices : 1;
+  in.n_chk_tiles = p.tiles_c * p.tiles_m * in.chk_slices;
   in.n_data_tiles = p.tiles_m * p.tiles_n;
   in.num_kb = (K + kBK - 1) / kBK;
   in.tiles_m = p.tiles_m;
@@ -350,6 +352,24 @@ PlanInput make_plan_input(int max_units, int CG, int BN, int K, const KernelPara
   in.slab_bytes = static_cast<size_t>(CG) * kBM * BN * sizeof(float);
   in.full_search = dbg("plan_full_search", 0) != 0 ? 1 : 0;
   return in;
+}
+
+// K-slices of the checksum items (KernelParams::chk_slices): only where units would otherwise idle -- all data tiles and
+// all slices run concurrently in one wave -- and a slice keeps at least 8 k-blocks.  Measured at 1024^3 (id 13): the
+// checksum item's K loop (7 us, after the encode) + its epilogue were the critical path of a 19.5 us step.
+int choose_chk_slices(const KernelParams &p, int units, int K) {
+  const long long forced = dbg("chk_slices", -2);
+  const int num_kb = (K + kBK - 1) / kBK;
+  if (p.tiles_c != 1) return 1;
+  int s = 1;
+  if (forced >= 1) s = static_cast<int>(forced);
+  else {
+    const int spare = units - p.tiles_m * p.tiles_n;
+    if (spare >= 2 * p.tiles_m) s = spare / p.tiles_m;
+    if (s > 4) s = 4;
+  }
+  while (s > 1 && num_kb / s < 8) --s;
+  return s < 1 ? 1 : s;
 }
 
 void plan_tiles(int M, int N, int BN, int CG, bool ft, KernelParams *p) {
@@ -549,9 +569,28 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     if (qrc) return qrc;
     if (max_units < 1) return FTSGEMM_ERR_UNSUPPORTED;  // not a single CTA (pair) of this kernel fits on the device partition
   }
+  if (ft) {
+    p.chk_slices = choose_chk_slices(p, max_units, K);
+    const size_t n_flags_s = static_cast<size_t>(p.tiles_m) * CG * (kBM / 32) * p.tiles_c * p.chk_slices;
+    if (p.chk_slices > 1 && n_flags_s * sizeof(int) > kChkFlagBytes) p.chk_slices = 1;
+    if (p.chk_slices > 1) {
+      // one plane of expected checksums per slice
+      const size_t out_floats = static_cast<size_t>(M) * p.n_chk_cols * p.chk_slices;
+      const float *out_before = h->d_chk_out;
+      rc = ensure_buf(h, &h->d_chk_out, &h->chk_out_bytes, kChkFlagBytes + out_floats * sizeof(float));
+      if (rc) return rc;
+      if (h->d_chk_out != out_before) {  // reallocated: fresh flags, restart the epoch
+        FT_CUDA(h, cudaMemsetAsync(h->d_chk_out, 0, kChkFlagBytes, stream));
+        h->chk_epoch = 1;
+        p.chk_epoch = 1;
+      }
+      p.chk_flags = reinterpret_cast<int *>(h->d_chk_out);
+      p.chk_out = h->d_chk_out + kChkFlagBytes / sizeof(float);
+    }
+  }
   const PlanInput pin = make_plan_input(max_units, CG, BN, K, p);
   const std::array<long long, 6> key = {v.info.id, M, N, K, pin.units,
-                                        pin.force_slices * 16 + pin.max_slices + pin.lockstep * 8192 + pin.full_search * 16384};
+                                        pin.force_slices * 16 + pin.max_slices + pin.lockstep * 8192 + pin.full_search * 16384 + pin.chk_slices * 65536};
   ftsgemm_handle_s::CachedPlan &cp = h->plans[key];
   if (!cp.uploaded) {
     if (h->plans.size() > 64) {  // bound the cache: drop everything but this entry
@@ -811,7 +850,7 @@ int ftsgemm_kernel_lookup(int kernel_id, ftsgemm_kernel_info *out) {
 
 // Enumerate the work decomposition of one launch on the HOST (same inline code the device runs): for every work unit,
 // in processing order, rows of 9 ints {unit, tile, is_chk, m_blk, n_blk, kb_begin, kb_end, kind, slice}.  Returns the
-// number of rows (fills min(cap, rows)); hdr[0..6] = {units, num_tiles, n_chk_tiles, sk_tiles, num_kb, cta_group, sk_slices}.
+// number of rows (fills min(cap, rows)); hdr[0..7] = {units, num_tiles, n_chk_tiles, sk_tiles, num_kb, cta_group, sk_slices, chk_slices}.
 int ftsgemm_debug_schedule(int kernel_id, int M, int N, int K, int num_sms, int *hdr, int *rows, int cap) {
   const Variant *v = find_variant(kernel_id);
   if (!v || v->info.engine != 1 || M <= 0 || N <= 0 || K <= 0 || num_sms <= 0) return FTSGEMM_ERR_INVALID_ARG;
@@ -820,11 +859,12 @@ int ftsgemm_debug_schedule(int kernel_id, int M, int N, int K, int num_sms, int 
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
   plan_tiles(M, N, v->bn, v->cg, v->info.fault_tolerant != 0, &p);
+  if (v->info.fault_tolerant) p.chk_slices = choose_chk_slices(p, num_sms / v->cg, K);
   const PlanInput pin = make_plan_input(num_sms / v->cg, v->cg, v->bn, K, p);
   const Plan plan = build_plan(pin);
   if (hdr) {
     hdr[0] = plan.units; hdr[1] = pin.n_chk_tiles + pin.n_data_tiles; hdr[2] = pin.n_chk_tiles; hdr[3] = plan.sk_tiles;
-    hdr[4] = pin.num_kb; hdr[5] = v->cg; hdr[6] = plan.sk_slices;
+    hdr[4] = pin.num_kb; hdr[5] = v->cg; hdr[6] = plan.sk_slices; hdr[7] = pin.chk_slices;
   }
   int n = 0;
   for (int u = 0; u < plan.units; ++u) {

@@ -96,6 +96,10 @@ struct KernelParams {
   int sk_epoch;
   // fault tolerance: checksum tile-columns
   int tiles_c;          // number of BN-wide checksum tile-columns (0 when FT is off)
+  int chk_slices;       // >= 1: every checksum tile is computed as chk_slices independent K-slices (one plan item each, on
+                        // otherwise idle units of small problems, where the checksum item is the critical path: its K loop
+                        // starts after the encode and is as long as a data tile's); slice s publishes its partial expected
+                        // checksums in plane s of chk_out / chk_flags, the check adds the planes in slice order
   int chk_box_bytes;    // bytes one CTA's TMA box of the checksum operand delivers per stage (<= kBBytes: the box is
                         // sized to the checksum columns that exist, so checksum items load less than data tiles)
   int n_chk_cols;       // tiles_n * kChkPerTile
@@ -179,6 +183,7 @@ __device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
 
 struct TileCoord {
   int m_blk, n_blk;  // n_blk indexes checksum tile-columns when is_chk
+  int slice;         // K-slice of a checksum tile (0 otherwise)
   bool is_chk;
 };
 
@@ -187,9 +192,13 @@ struct TileCoord {
 // wave of CTAs shares few A row-panels and few B row-panels in L2.
 __host__ __device__ __forceinline__ TileCoord decode_tile(const KernelParams &p, int t) {
   TileCoord tc;
-  const int n_chk_tiles = p.tiles_c * p.tiles_m;
+  tc.slice = 0;
+  const int per_slice = p.tiles_c * p.tiles_m;
+  const int n_chk_tiles = per_slice * (p.chk_slices > 1 ? p.chk_slices : 1);
   if (t < n_chk_tiles) {
     tc.is_chk = true;
+    tc.slice = t / (per_slice > 0 ? per_slice : 1);
+    t -= tc.slice * per_slice;
     tc.m_blk = t % p.tiles_m;
     tc.n_blk = t / p.tiles_m;
     return tc;
@@ -343,14 +352,25 @@ __device__ __forceinline__ void load_expected(const KernelParams &p, int m, int 
     x.e1 = __ldcg(cp + p.M);
     x.w0 = __ldcg(cp + 2 * static_cast<size_t>(p.M));
     x.w1 = __ldcg(cp + 3 * static_cast<size_t>(p.M));
+    const size_t plane = static_cast<size_t>(p.M) * p.n_chk_cols;
+    for (int sl = 1; sl < p.chk_slices; ++sl) {  // K-slices of the checksum product, added in slice order (deterministic)
+      cp += plane;
+      x.e0 += __ldcg(cp);
+      x.e1 += __ldcg(cp + p.M);
+      x.w0 += __ldcg(cp + 2 * static_cast<size_t>(p.M));
+      x.w1 += __ldcg(cp + 3 * static_cast<size_t>(p.M));
+    }
   }
 }
+// number of flags per 32-row slab: checksum tile-columns x K-slices (flag index = slice * tiles_c + c)
+__device__ __forceinline__ int chk_flags_per_slab(const KernelParams &p) { return p.tiles_c * (p.chk_slices > 1 ? p.chk_slices : 1); }
 __device__ __forceinline__ void try_prefetch_expected(const KernelParams &p, int q, int lane, int m, int m0_cta, int n_blk,
                                                       ExpectedChk &x) {
-  const int *flag = p.chk_flags + ((m0_cta >> 5) + q) * p.tiles_c;
+  const int nf = chk_flags_per_slab(p);
+  const int *flag = p.chk_flags + ((m0_cta >> 5) + q) * nf;
   int ok = 1;
   if (lane == 0)
-    for (int c = 0; c < p.tiles_c; ++c) ok &= (ld_acquire(flag + c) == p.chk_epoch) ? 1 : 0;
+    for (int c = 0; c < nf; ++c) ok &= (ld_acquire(flag + c) == p.chk_epoch) ? 1 : 0;
   ok = __shfl_sync(0xffffffffu, ok, 0);
   x.ready = ok != 0;
   if (x.ready) load_expected(p, m, n_blk, x);
@@ -399,9 +419,10 @@ __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr
   // ---- expected checksums published by the checksum tile-columns (wait for this 32-row slab's flag unless the
   //      prefetch already found it raised) ----
   if (!xp.ready) {
-    const int *flag = p.chk_flags + ((m0_cta >> 5) + q) * p.tiles_c;
+    const int nf = chk_flags_per_slab(p);
+    const int *flag = p.chk_flags + ((m0_cta >> 5) + q) * nf;
     if (lane == 0) {
-      for (int c = 0; c < p.tiles_c; ++c) {
+      for (int c = 0; c < nf; ++c) {
         ptx::Watchdog wd;
         while (ld_acquire(flag + c) != p.chk_epoch) {
           __nanosleep(64);
@@ -1119,10 +1140,12 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       } else if (FT && tc.is_chk) {
         // checksum tile-column: publish R = A * [e, w]^T for these 128 rows, then raise the slab flag
         const int n_hi = min(p.n_chk_cols, n0 + chk_cols_per_tile(BN));  // columns beyond belong to the next item
-        store_tile<BN>(taddr, p.chk_out + m, m < p.M, n0, n_hi, p.M, 1.0f, 0.0f, 0, (n_hi - n0 + 31) / 32);
+        store_tile<BN>(taddr, p.chk_out + static_cast<size_t>(tc.slice) * p.M * p.n_chk_cols + m, m < p.M, n0, n_hi, p.M, 1.0f, 0.0f, 0,
+                       (n_hi - n0 + 31) / 32);
         __threadfence();
         __syncwarp();
-        if (lane == 0) atomicExch(p.chk_flags + ((m0_cta >> 5) + q) * p.tiles_c + tc.n_blk, p.chk_epoch);
+        if (lane == 0)
+          atomicExch(p.chk_flags + ((m0_cta >> 5) + q) * chk_flags_per_slab(p) + tc.slice * p.tiles_c + tc.n_blk, p.chk_epoch);
       } else {
         // final epilogue of a data tile; with epi_assist the helper warp of this quadrant owns the chunks [kMid, BN/32)
         const bool assist = p.epi_assist != 0 && BN >= 64;

@@ -47,7 +47,8 @@ struct Plan {
 
 struct PlanInput {
   int units;            // CTAs or CTA pairs
-  int n_chk_tiles;      // checksum tile-columns x tiles_m (first tiles in decode order)
+  int n_chk_tiles;      // checksum tile-columns x tiles_m x chk_slices (first tiles in decode order)
+  int chk_slices = 1;   // K-slices per checksum tile (tile t belongs to slice t / (n_chk_tiles / chk_slices))
   int n_data_tiles;
   int num_kb;           // k-blocks per tile
   int tiles_m;          // checksum tile t belongs to checksum tile-column t / tiles_m
@@ -131,8 +132,15 @@ inline double schedule(const PlanInput &in, const Cut &c, Plan *out) {
     ready[i] = end + in.park_latency;
   };
   for (int i = 0; i < c.He; ++i) piece(i, 0);
-  for (int t = 0; t < in.n_chk_tiles; ++t)
-    give(PlanItem{t, 0, in.num_kb, 0, 0, -1}, in.chk_col_cost[static_cast<size_t>(t / in.tiles_m)], in.chk_release, false);
+  {
+    const int S = in.chk_slices > 1 ? in.chk_slices : 1, per_slice = in.n_chk_tiles / S;
+    for (int t = 0; t < in.n_chk_tiles; ++t) {
+      const int sl = t / per_slice, r = t - sl * per_slice;
+      const int kb0 = static_cast<int>(static_cast<long long>(in.num_kb) * sl / S);
+      const int kb1 = static_cast<int>(static_cast<long long>(in.num_kb) * (sl + 1) / S);
+      give(PlanItem{t, kb0, kb1, 0, sl, -1}, in.chk_col_cost[static_cast<size_t>(r / in.tiles_m)] / S, in.chk_release, false);
+    }
+  }
   for (int d = 0; d < whole; ++d) give(PlanItem{in.n_chk_tiles + d, 0, in.num_kb, 0, 0, -1}, 1.0, 0.0, true);
   for (int i = c.He; i < H; ++i) piece(i, 0);
   for (int p = 1; p < max_pieces; ++p) {

@@ -215,7 +215,8 @@ long long ftsgemm_verify_bad_count(ftsgemm_handle_t h);
 int ftsgemm_debug_set(const char *key, long long value);
 /* Host-side enumeration of the work decomposition of one launch (split-K head + data-parallel body), for tests:
  * rows of 9 ints {unit, tile, is_chk, m_blk, n_blk, kb_begin, kb_end, kind(0 whole,1 contributor,2 finisher), slice};
- * hdr[7] = {units, num_tiles, n_chk_tiles, sk_tiles, num_kb, cta_group, sk_slices}.  Needs no GPU. */
+ * hdr[8] = {units, num_tiles, n_chk_tiles, sk_tiles, num_kb, cta_group, sk_slices, chk_slices}; checksum tiles carry
+ * their K-slice index in the `slice` column.  Needs no GPU. */
 int ftsgemm_debug_schedule(int kernel_id, int M, int N, int K, int num_sms, int *hdr, int *rows, int cap);
 /* Device timeline of the last tensor-core launch made with ftsgemm_debug_set("trace", 1): per work unit 64 items x 8
  * u64 = %globaltimer ns {producer start, producer end, MMA start, MMA issue end, accumulator complete, check done,

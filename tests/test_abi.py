@@ -60,8 +60,8 @@ def test_kernel_table_matches_reference_ids(ft):
     for (M, N) in ((1024, 1024), (2048, 2048), (4096, 4096), (256, 16384), (16384, 16384)):
         a, b = ft.select_kernel(M, N, 1024, False), ft.select_kernel(M, N, 1024, True)
         assert tab[a]["engine"] == 1 and not tab[a]["fault_tolerant"] and tab[b]["fault_tolerant"]
-        assert tab[a]["tile"] == tab[b]["tile"]
     assert ft.select_kernel(4096, 4096, 4096, True) == 31 and ft.select_kernel(1024, 1024, 1024, False) == 3
+    assert ft.select_kernel(1536, 1536, 1536, True) == 31 and ft.select_kernel(1536, 1536, 1536, False) == 3
 
 
 def test_opts_struct_layout(ft):

@@ -30,8 +30,13 @@ def test_random_plans(ft, kid, m4, n4, K, sms, splitk):
         assert 0 <= s["kb_begin"] < s["kb_end"] <= num_kb and 0 <= s["unit"] < hdr["units"]
         cover.setdefault(s["tile"], []).append((s["kb_begin"], s["kb_end"], s["kind"]))
     assert sorted(cover) == list(range(hdr["num_tiles"]))
-    for pieces in cover.values():
+    S_chk = max(1, hdr["chk_slices"])
+    for t, pieces in cover.items():
         pieces.sort()
+        if t < hdr["n_chk_tiles"] and S_chk > 1:
+            sl = t // (hdr["n_chk_tiles"] // S_chk)
+            assert [p[:2] for p in pieces] == [(num_kb * sl // S_chk, num_kb * (sl + 1) // S_chk)]
+            continue
         assert pieces[0][0] == 0 and pieces[-1][1] == num_kb
         assert all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
         kinds = [p[2] for p in pieces]

@@ -25,7 +25,7 @@ def _simulate(hdr, segs, acc_stages):
     for u, lst in enumerate(per_unit):
         for i, s in enumerate(lst):
             if s["is_chk"]:
-                chk_done[(s["m_blk"], s["n_blk"])] = False
+                chk_done[(s["m_blk"], s["n_blk"], s["slice"])] = False
                 tiles_c = max(tiles_c, s["n_blk"] + 1)
             if s["kind"] in (1, 2, 3):
                 piece_at[(s["tile"], s["slice"])] = (u, i)
@@ -49,13 +49,13 @@ def _simulate(hdr, segs, acc_stages):
                 s = lst[i]
                 ok = True
                 if hdr["n_chk_tiles"] and not s["is_chk"] and s["kind"] in (0, 2):  # parking pieces are not checked
-                    ok = all(chk_done[(s["m_blk"], c)] for c in range(tiles_c))
+                    ok = all(chk_done[(s["m_blk"], c, sl)] for c in range(tiles_c) for sl in range(max(1, hdr.get("chk_slices", 1))))
                 if not ok:
                     break
                 epi_done[u] += 1
                 done_epi.add((u, i))
                 if s["is_chk"]:
-                    chk_done[(s["m_blk"], s["n_blk"])] = True
+                    chk_done[(s["m_blk"], s["n_blk"], s["slice"])] = True
                 progress = True
     return all(epi_done[u] == len(per_unit[u]) for u in range(units))
 
@@ -79,8 +79,13 @@ def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms):
         if s["kind"] in (1, 2, 3):
             assert not s["is_chk"]
     assert sorted(cover) == list(range(hdr["num_tiles"]))
+    S_chk = max(1, hdr["chk_slices"])
     for t, pieces in cover.items():
         pieces.sort()
+        if t < hdr["n_chk_tiles"] and S_chk > 1:  # a K-slice of a checksum tile: one item over its own k range
+            sl = t // (hdr["n_chk_tiles"] // S_chk)
+            assert pieces == [(num_kb * sl // S_chk, num_kb * (sl + 1) // S_chk, 0, sl)], (t, pieces)
+            continue
         assert pieces[0][0] == 0 and pieces[-1][1] == num_kb
         for a, b in zip(pieces, pieces[1:]):
             assert a[1] == b[0]  # contiguous, no overlap
@@ -110,11 +115,13 @@ def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms):
             if s_["is_chk"]:
                 assert s_["tile"] < hdr["n_chk_tiles"]
     # checksum tiles: n_chk_tiles of them, 8 columns per N-tile
-    chk = {(s["m_blk"], s["n_blk"]) for s in segs if s["is_chk"]}
+    chk = {(s["m_blk"], s["n_blk"], s["slice"]) for s in segs if s["is_chk"]}
     assert len(chk) == hdr["n_chk_tiles"]
     if kid in (11, 12, 13, 14, 16, 15, 31, 32):
         tiles_n = -(-N // TILE_N[kid])
-        assert hdr["n_chk_tiles"] == -(-M // (128 * hdr["cta_group"])) * -(-(tiles_n * 4) // TILE_N[kid])
+        assert hdr["n_chk_tiles"] == -(-M // (128 * hdr["cta_group"])) * -(-(tiles_n * 4) // TILE_N[kid]) * S_chk
+        if S_chk > 1:  # slices only where every data tile and every slice get a unit of their own
+            assert hdr["num_tiles"] <= units and num_kb // S_chk >= 8
     acc_stages = 2 if 2 * TILE_N[kid] <= 512 else 1
     assert _simulate(hdr, segs, acc_stages), "circular wait in the schedule"
 
