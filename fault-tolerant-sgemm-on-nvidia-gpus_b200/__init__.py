@@ -53,7 +53,8 @@ class Opts(C.Structure):
                 ("selftest_value", C.c_float), ("selftest_row", C.c_int), ("selftest_col", C.c_int),
                 ("n_faults", C.c_int), ("faults", Fault * MAX_FAULTS), ("tau_abs", C.c_float),
                 ("tau_rel", C.c_float), ("detect_only", C.c_int), ("reuse_b_checksums", C.c_int),
-                ("baseline_host_sync", C.c_int), ("precision", C.c_int), ("no_recompute", C.c_int)]
+                ("baseline_host_sync", C.c_int), ("precision", C.c_int), ("check_segments", C.c_int),
+                ("no_recompute", C.c_int)]
 
 
 class Event(C.Structure):
@@ -162,7 +163,7 @@ def default_opts() -> Opts:
 
 
 def make_opts(stream=None, selftest=None, faults=None, tau_abs=0.0, tau_rel=0.0, detect_only=False,
-              reuse_b_checksums=False, baseline_host_sync=True, no_recompute=False, precision=0) -> Opts:
+              reuse_b_checksums=False, baseline_host_sync=True, no_recompute=False, precision=0, check_segments=0) -> Opts:
     """selftest: None | (value, tile_row, tile_col)  -> the reference's always-on injector (ft_sgemm_huge.cuh:324-327)
     faults: list of dicts {row, col, add=float} or {row, col, xor=int}"""
     o = default_opts()
@@ -186,6 +187,7 @@ def make_opts(stream=None, selftest=None, faults=None, tau_abs=0.0, tau_rel=0.0,
     o.baseline_host_sync = int(baseline_host_sync)
     o.no_recompute = int(no_recompute)
     o.precision = int(precision)  # 0 = single-pass TF32, 1 = 3xTF32 (FP32-grade)
+    o.check_segments = int(check_segments)  # > 1: intra-K checking (K-segments verified one after the other)
     return o
 
 

@@ -979,7 +979,7 @@ static int load_opts(const ftsgemm_opts *opts, ftsgemm_opts *o) {
   if (opts->struct_size < FTSGEMM_OPTS_V1_SIZE) return FTSGEMM_ERR_INVALID_ARG;
   memcpy(o, opts, opts->struct_size < sizeof(*o) ? opts->struct_size : sizeof(*o));
   o->struct_size = sizeof(*o);
-  if (o->precision < 0 || o->precision > 1 || o->inject_mode < 0 || o->inject_mode > 2 || o->selftest_row < 0 || o->selftest_col < 0 || o->n_faults < 0 ||
+  if (o->check_segments < 0 || o->check_segments > 4096 || o->precision < 0 || o->precision > 1 || o->inject_mode < 0 || o->inject_mode > 2 || o->selftest_row < 0 || o->selftest_col < 0 || o->n_faults < 0 ||
       o->n_faults > FTSGEMM_MAX_FAULTS)
     return FTSGEMM_ERR_INVALID_ARG;
   return FTSGEMM_OK;
@@ -999,6 +999,27 @@ int ftsgemm_run(ftsgemm_handle_t h, int kernel_id, int M, int N, int K, const fl
   if (v->info.engine == 1 && v->bn == 0) {  // ids 20 / 40: per-shape choice
     v = find_variant(select_variant(M, N, v->info.fault_tolerant != 0));
     if (!v) return FTSGEMM_ERR_UNSUPPORTED;
+  }
+  if (v->info.engine == 1 && o.check_segments > 1 && v->info.fault_tolerant) {
+    // Intra-K checking (ftsgemm_opts::check_segments): S consecutive K-segments, each a complete fault-tolerant GEMM.  A and
+    // B are column-major with k the slow index, so a segment is a pointer offset; segment boundaries are multiples of the
+    // stage depth (32 k-rows).  Injected faults (tests) go to the first segment only.
+    int S = o.check_segments;
+    const int num_kb = (K + kBK - 1) / kBK;
+    if (S > num_kb) S = num_kb;
+    ftsgemm_opts os = o;
+    os.check_segments = 1;
+    os.reuse_b_checksums = 0;
+    int rc = FTSGEMM_OK;
+    for (int sg = 0; sg < S && !rc; ++sg) {
+      const int k0 = static_cast<int>(static_cast<long long>(num_kb) * sg / S) * kBK;
+      int k1 = static_cast<int>(static_cast<long long>(num_kb) * (sg + 1) / S) * kBK;
+      if (k1 > K) k1 = K;
+      if (sg > 0) os.inject_mode = 0;
+      rc = ftsgemm_run(h, v->info.id, M, N, k1 - k0, dA + static_cast<size_t>(k0) * M, dB + static_cast<size_t>(k0) * N, dC, alpha,
+                       sg == 0 ? beta : 1.0f, &os);
+    }
+    return rc;
   }
   if (v->info.engine == 1 && o.precision == 1) {
     // 3xTF32 (FP32-grade accuracy, the reference's kernels are true FP32 FFMA, ft_sgemm_huge.cuh:228-323): with

@@ -112,6 +112,12 @@ typedef struct ftsgemm_opts {
                             FP32 accumulate; norm-wise 1e-3 against FP32) | 1: 3xTF32 -- hi/lo split of A and B, three
                             fault-tolerant passes A_lo*B + A*B_lo + A*B: FP32-grade, element-wise parity with the
                             reference's FP32 FFMA kernels (ft_sgemm_huge.cuh:228-323) at ~1/3 of the throughput */
+  int check_segments;    /* 0 / 1 (default): one check per tile over the whole K range.  S > 1: intra-K checking -- the product is
+                            formed as S consecutive K-segments (S launches, C += alpha * A[:, seg] * B[:, seg]^T), each a
+                            complete fault-tolerant GEMM whose tiles are verified and repaired before the segment is
+                            committed to C: an upset is caught within K/S of where it happened, and upsets in different
+                            segments of one row are each correctable (the reference checks its register accumulators every
+                            K/20 iterations, ft_sgemm_huge.cuh:324, code_gen.py:333).  Costs S launches and S passes over C. */
   int no_recompute;      /* 0 (default): a row that is flagged but cannot be repaired from its two checksums (upset too
                             small to locate, two upsets in one row) is RECOMPUTED from A and B on CUDA cores and counted
                             in stats.recomputed -- nothing detected is stored as computed; 1: leave such rows as computed

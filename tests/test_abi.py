@@ -68,7 +68,7 @@ def test_opts_struct_layout(ft):
     o = ft.default_opts()
     assert o.struct_size == C.sizeof(ft.Opts)
     assert o.selftest_value == 10000.0 and o.inject_mode == 0 and o.baseline_host_sync == 1
-    assert o.precision == 0 and o.no_recompute == 0
+    assert o.precision == 0 and o.no_recompute == 0 and o.check_segments == 0
     o = ft.make_opts(faults=[{"row": 1, "col": 2, "xor": 1 << 30}, {"row": 3, "col": 4, "add": 2.5}])
     assert o.inject_mode == 2 and o.n_faults == 2 and o.faults[0].xor_mask == 1 << 30 and o.faults[1].add_value == 2.5
 

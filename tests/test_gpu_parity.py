@@ -528,6 +528,35 @@ def test_3xtf32_elementwise_fp32_parity(cuda, ft, dev, oracle):
     assert oracle.error_metrics(want, x1)["rel_fro"] > 1e-4  # (single-pass TF32 for comparison)
 
 
+def test_intra_k_check_segments(cuda, ft, dev, oracle):
+    """opts.check_segments = S: the product is verified K-segment by K-segment (the reference checks its accumulators
+    every K/20 iterations, ft_sgemm_huge.cuh:324).  Same result as the one-shot product up to the FP32 rounding of the S - 1
+    intermediate stores; S x the row checks; an upset is repaired inside its segment; 3xTF32 composes with it."""
+    rng = np.random.default_rng(8)
+    M, N, K = 512, 768, 2048 + 40
+    A, B = _rand(rng, M * K), _rand(rng, N * K)
+    C0 = rng.standard_normal(M * N).astype(np.float32)
+    model = oracle.sgemm_nt_tf32_model(M, N, K, 0.5, A, B, -1.5, C0, "trunc")
+    for kid in (31, 16):
+        one = _run(cuda, dev, kid, M, N, K, A, B, C0, 0.5, -1.5)
+        dev.stats()
+        for S in (4, 20):
+            got = _run(cuda, dev, kid, M, N, K, A, B, C0, 0.5, -1.5, opts=ft.make_opts(check_segments=S))
+            st = dev.stats()
+            tile_n = 256 if kid == 31 else 128
+            assert st["detected"] == 0 and st["rows_checked"] == S * M * (N // tile_n), (kid, S, st)
+            assert oracle.error_metrics(model, got)["rel_fro"] < TOL_MODEL
+            assert np.allclose(got, one, rtol=0, atol=2e-5 * float(np.abs(one).max()))
+        got = _run(cuda, dev, kid, M, N, K, A, B, C0, 0.5, -1.5,
+                   opts=ft.make_opts(check_segments=4, faults=[{"row": 77, "col": 300, "xor": 1 << 30}]))
+        st = dev.stats()
+        assert st["detected"] == 1 and st["corrected"] + st["recomputed"] == 1, st
+        assert np.allclose(got, one, rtol=0, atol=2e-4 * float(np.abs(one).max()))
+    want = oracle.sgemm_nt(M, N, K, 0.5, A, B, -1.5, C0.copy())
+    got = _run(cuda, dev, 31, M, N, K, A, B, C0, 0.5, -1.5, opts=ft.make_opts(check_segments=3, precision=1))
+    assert oracle.error_metrics(want, got)["rel_fro"] < 5e-6
+
+
 def test_auto_ids_resolve_and_run(cuda, ft, dev, oracle):
     """ids 20 / 40 pick the variant per shape (ftsgemm_select_kernel) and give bit-for-bit the result of that variant."""
     rng = np.random.default_rng(4)
