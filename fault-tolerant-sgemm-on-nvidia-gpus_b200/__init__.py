@@ -83,7 +83,8 @@ EXPORTED_SYMBOLS = [
     "ftsgemm_create", "ftsgemm_destroy", "ftsgemm_abi_version", "ftsgemm_error_string", "ftsgemm_last_cuda_error",
     "ftsgemm_default_opts", "ftsgemm_kernel_table", "ftsgemm_kernel_lookup", "ftsgemm_run", "ftsgemm_get_stats",
     "ftsgemm_run_host", "ftsgemm_baseline", "ftsgemm_verify", "ftsgemm_debug_set", "ftsgemm_debug_schedule",
-    "ftsgemm_verify_bad_count", "ftsgemm_debug_trace", "ftsgemm_stats_device", "ftsgemm_select_kernel", "ftsgemm_launch_count",
+    "ftsgemm_verify_bad_count", "ftsgemm_debug_trace", "ftsgemm_stats_device", "ftsgemm_select_kernel", "ftsgemm_launch_count", "ftsgemm_peer_export", "ftsgemm_peer_connect",
+    "ftsgemm_peer_verdict",
 ]
 
 _lib = None
@@ -120,6 +121,9 @@ def lib():
         L.ftsgemm_run_host.argtypes = [vp, ip, ip, ip, ip, vp, vp, vp, fp, fp, C.POINTER(Opts)]
         L.ftsgemm_stats_device.argtypes = [vp, vp, vp]
         L.ftsgemm_select_kernel.argtypes = [ip, ip, ip, ip]
+        L.ftsgemm_peer_export.argtypes = [vp, vp]
+        L.ftsgemm_peer_connect.argtypes = [vp, ip, ip, vp]
+        L.ftsgemm_peer_verdict.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), ip]
         L.ftsgemm_launch_count.argtypes = [vp]
         L.ftsgemm_launch_count.restype = C.c_ulonglong
         L.ftsgemm_baseline.argtypes = [vp, ip, ip, ip, vp, vp, vp, fp, fp, ip, C.POINTER(Opts), vp]
@@ -264,6 +268,22 @@ class FtSgemm:
         s = Stats()
         self._run_checked(lib().ftsgemm_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    # fused multi-GPU verdict exchange (include/ftsgemm.h: ftsgemm_peer_*)
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._run_checked(lib().ftsgemm_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_connect(self, rank: int, world: int, handles) -> None:
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        self._run_checked(lib().ftsgemm_peer_connect(self._h, rank, world, C.create_string_buffer(blob, len(blob))))
+
+    def peer_verdict(self, world: int, timeout_ms: int = 10000):
+        out, per = (C.c_double * 8)(), (C.c_double * (8 * world))()
+        self._run_checked(lib().ftsgemm_peer_verdict(self._h, out, per, timeout_ms))
+        return list(out), [list(per[8 * r:8 * r + 8]) for r in range(world)]
 
     def launch_count(self) -> int:
         """Kernels of this library launched through the handle so far (include/ftsgemm.h)."""

@@ -126,6 +126,9 @@ int main(int argc, char **argv) {
   ftsgemm_opts opts;
   ftsgemm_default_opts(&opts);
   if (inject) opts.inject_mode = 1;  // +10000 into one accumulator of every CTA tile (ft_sgemm_huge.cuh:324-327)
+  // optional modes of the tcgen05 engines (not in the reference's argv: environment only)
+  if (getenv("FTSGEMM_PRECISION") && !strcmp(getenv("FTSGEMM_PRECISION"), "x3")) opts.precision = 1;  // 3xTF32, FP32-grade
+  opts.check_segments = env_int("FTSGEMM_CHECK_SEGMENTS", 0);  // S > 1: intra-K checking, S verified K-segments
 
   if (cpu_verify) {
     Chost.resize(count);

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <ctime>
 #include <cstdlib>
 #include <cstring>
 #include <array>
@@ -114,6 +115,14 @@ struct ftsgemm_handle_s {
   size_t chk_out_bytes = 0;
   const float *chk_for_b = nullptr;  // B pointer / shape the panel was encoded from
   int chk_n = 0, chk_k = 0, chk_bn = 0;
+  // fused verdict exchange (ftsgemm_peer_*): this rank's mailbox (kMaxPeers slots), the peers' mailboxes mapped through
+  // CUDA IPC, the exit counter of the publishing launches and their sequence number
+  double *d_mailbox = nullptr;
+  double *peer_box[kMaxPeers] = {};
+  bool peer_opened[kMaxPeers] = {};
+  int peer_world = 0, peer_rank = 0;
+  unsigned long long peer_seq = 0;
+  unsigned int *d_exit_count = nullptr;
   int *d_enc_done = nullptr;    // front-phase encode: warps done, monotonic over launches
   int enc_done_value = 0;
   float *d_lo = nullptr;        // 3xTF32: A_lo | B_lo
@@ -443,6 +452,13 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     p.faults[i].xor_mask = o.faults[i].xor_mask;
   }
   p.stats = h->d_stats;
+  if (ft && h->peer_world > 0) {  // fused verdict push to every rank's mailbox
+    for (int r = 0; r < h->peer_world; ++r) p.peer_box[r] = h->peer_box[r];
+    p.peer_world = h->peer_world;
+    p.peer_rank = h->peer_rank;
+    p.peer_seq = static_cast<double>(++h->peer_seq);
+    p.exit_count = h->d_exit_count;
+  }
 
   CUtensorMap tmA, tmB, tmC;
   bool enc_front = false;
@@ -953,6 +969,10 @@ int ftsgemm_destroy(ftsgemm_handle_t h) {
   cudaFree(h->d_aux);
   cudaFree(h->d_lo);
   cudaFree(h->d_enc_done);
+  for (int r = 0; r < kMaxPeers; ++r)
+    if (h->peer_opened[r]) cudaIpcCloseMemHandle(h->peer_box[r]);
+  cudaFree(h->d_mailbox);
+  cudaFree(h->d_exit_count);
   cudaFree(h->d_verify);
   for (int i = 0; i < 3; ++i) cudaFree(h->d_stage[i]);
   if (h->s_in) {
@@ -1083,6 +1103,77 @@ int ftsgemm_get_stats(ftsgemm_handle_t h, ftsgemm_stats *out) {
     out->events[i].residual = ds.events[i].residual;
     out->events[i].corrected_value = ds.events[i].corrected_value;
     out->events[i].status = ds.events[i].status;
+  }
+  return FTSGEMM_OK;
+}
+
+int ftsgemm_peer_export(ftsgemm_handle_t h, void *ipc_handle_64) {
+  if (!h) return FTSGEMM_ERR_NO_DEVICE;
+  if (!ipc_handle_64) return FTSGEMM_ERR_INVALID_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  DeviceGuard guard(h);
+  if (!h->d_mailbox) {
+    const size_t bytes = static_cast<size_t>(kMaxPeers) * kPeerSlotDoubles * sizeof(double);
+    FT_CUDA(h, cudaMalloc(&h->d_mailbox, bytes));
+    FT_CUDA(h, cudaMemset(h->d_mailbox, 0, bytes));
+    FT_CUDA(h, cudaMalloc(&h->d_exit_count, sizeof(unsigned int)));
+    FT_CUDA(h, cudaMemset(h->d_exit_count, 0, sizeof(unsigned int)));
+  }
+  cudaIpcMemHandle_t hd;
+  FT_CUDA(h, cudaIpcGetMemHandle(&hd, h->d_mailbox));
+  memcpy(ipc_handle_64, &hd, sizeof(hd));
+  return FTSGEMM_OK;
+}
+
+int ftsgemm_peer_connect(ftsgemm_handle_t h, int rank, int world, const void *ipc_handles) {
+  if (!h) return FTSGEMM_ERR_NO_DEVICE;
+  if (!ipc_handles || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !h->d_mailbox) return FTSGEMM_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      h->peer_box[r] = h->d_mailbox;
+      continue;
+    }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, static_cast<const char *>(ipc_handles) + static_cast<size_t>(r) * sizeof(hd), sizeof(hd));
+    void *ptr = nullptr;
+    FT_CUDA(h, cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_box[r] = static_cast<double *>(ptr);
+    h->peer_opened[r] = true;
+  }
+  h->peer_rank = rank;
+  h->peer_world = world;
+  h->peer_seq = 0;
+  return FTSGEMM_OK;
+}
+
+int ftsgemm_peer_verdict(ftsgemm_handle_t h, double *out8, double *per_rank /* world x 8, may be NULL */, int timeout_ms) {
+  if (!h) return FTSGEMM_ERR_NO_DEVICE;
+  if (!out8 || h->peer_world < 1) return FTSGEMM_ERR_INVALID_ARG;
+  DeviceGuard guard(h);
+  FT_CUDA(h, cudaStreamSynchronize(h->last_stream));
+  const int arc = check_abort_flag(h);
+  if (arc) return arc;
+  // every rank's slot must carry (at least) the sequence number of this rank's last publishing launch: the ranks of a
+  // tile-sharded product launch the same number of GEMMs
+  double box[kMaxPeers * kPeerSlotDoubles];
+  const double want = static_cast<double>(h->peer_seq);
+  for (int waited = 0;; ++waited) {
+    FT_CUDA(h, cudaMemcpy(box, h->d_mailbox, sizeof(double) * h->peer_world * kPeerSlotDoubles, cudaMemcpyDeviceToHost));
+    if (timeout_ms < 0) break;  // the caller has synchronised the ranks itself (e.g. a barrier after a stream sync)
+    bool all = true;
+    for (int r = 0; r < h->peer_world; ++r) all = all && box[r * kPeerSlotDoubles + 8] >= want;
+    if (all) break;
+    if (waited >= (timeout_ms > 0 ? timeout_ms : 10000)) return FTSGEMM_ERR_TIMEOUT;
+    struct timespec ts = {0, 1000000};
+    nanosleep(&ts, nullptr);
+  }
+  for (int i = 0; i < 8; ++i) out8[i] = 0.0;
+  for (int r = 0; r < h->peer_world; ++r) {
+    const double *v = box + r * kPeerSlotDoubles;
+    for (int i = 0; i < 6; ++i) out8[i] += v[i];
+    for (int i = 6; i < 8; ++i) out8[i] = v[i] > out8[i] ? v[i] : out8[i];
+    if (per_rank) memcpy(per_rank + r * 8, v, 8 * sizeof(double));
   }
   return FTSGEMM_OK;
 }

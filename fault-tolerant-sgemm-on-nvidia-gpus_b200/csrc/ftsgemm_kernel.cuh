@@ -47,6 +47,8 @@ constexpr int kBK = 32;           // K extent of one shared-memory stage (4 UMMA
 constexpr int kAtomMN = 32;       // floats per 128-byte swizzle row
 constexpr int kChkPerTile = 4;    // checksum columns per N-tile: e hi/lo, w hi/lo (2 x 11-bit TF32 terms = 2^-22 relative)
 constexpr int kThreads = 384;     // 12 warps: producer, MMA, TMEM alloc, idle, 4 epilogue, 4 helpers
+constexpr int kMaxPeers = 16;     // ranks of one box whose verdict mailboxes a launch can write to
+constexpr int kPeerSlotDoubles = 16;  // mailbox slot of one rank: 8 verdict doubles, [8] = sequence number
 constexpr int kMaxFaults = 8;
 constexpr int kMaxEvents = 16;
 
@@ -144,6 +146,15 @@ struct KernelParams {
   int n_faults;
   DeviceFault faults[kMaxFaults];
   DeviceStats *stats;
+  // Multi-GPU verdict exchange FUSED into this kernel (tile-sharded products, sharding.py): the last CTA of the grid to
+  // finish writes this rank's verdict vector (the handle's counters, as ftsgemm_stats_device reports them) and the launch's
+  // sequence number into slot peer_rank of EVERY rank's mailbox -- plain stores to peer memory over NVLink (the mailboxes
+  // are mapped through CUDA IPC) -- so the exchange needs no collective kernel and nothing on the step's critical path but
+  // ~2 us of one thread.  peer_world = 0: off.
+  double *peer_box[kMaxPeers];
+  int peer_world, peer_rank;
+  double peer_seq;
+  unsigned int *exit_count;  // CTAs of this launch that have finished (the last one resets it)
   // debug timeline (ftsgemm_debug_trace): per unit and item 8 x u64 = %globaltimer ns at {producer start, producer end,
   // MMA start, MMA issue end, epilogue start (accumulator complete), after check/fold, epilogue end}, tile | kind << 24
   unsigned long long *trace;
@@ -1306,6 +1317,33 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   ptx::tc_fence_before();
   if (CG == 2) ptx::cluster_sync_all();  // no CTA may exit while its peer can still signal its barriers
   else __syncthreads();
+  if (FT && p.peer_world > 0 && threadIdx.x == 0) {
+    // fused verdict push: every CTA's counter updates are ordered before its arrival; the last arrival publishes
+    __threadfence();
+    const unsigned int arrived = atomicAdd(p.exit_count, 1u);
+    if (arrived == gridDim.x - 1) {
+      __threadfence();
+      const volatile DeviceStats *st = p.stats;
+      double v[8];
+      v[0] = static_cast<double>(st->tiles);
+      v[1] = static_cast<double>(st->rows_checked);
+      v[2] = static_cast<double>(st->detected);
+      v[3] = static_cast<double>(st->corrected);
+      v[4] = static_cast<double>(st->uncorrectable);
+      v[5] = static_cast<double>(st->checksum_faults);
+      v[6] = static_cast<double>(__uint_as_float(st->max_abs_bits));
+      v[7] = static_cast<double>(__uint_as_float(st->max_rel_bits));
+      for (int r = 0; r < p.peer_world; ++r) {
+        double *slot = p.peer_box[r] + p.peer_rank * kPeerSlotDoubles;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) slot[i] = v[i];
+      }
+      __threadfence_system();  // the vectors are visible on every GPU before any sequence number is
+      for (int r = 0; r < p.peer_world; ++r)
+        *reinterpret_cast<volatile double *>(p.peer_box[r] + p.peer_rank * kPeerSlotDoubles + 8) = p.peer_seq;
+      *p.exit_count = 0u;
+    }
+  }
   if (warp == 2) {
     ptx::tc_fence_after();
     if (CG == 2) ptx::tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);

@@ -190,6 +190,20 @@ int ftsgemm_get_stats(ftsgemm_handle_t h, ftsgemm_stats *out);
  * verdict of a distributed product without a host round trip (new work: the reference is single-GPU, sgemm.cu:34). */
 int ftsgemm_stats_device(ftsgemm_handle_t h, double *d_out8, void *stream);
 
+/* ---- multi-GPU verdict exchange fused into the GEMM kernel (new work: the reference is single-GPU, sgemm.cu:34) ----------
+ * For a product that is tile-sharded over the GPUs of one box (one process per GPU).  Each rank exports the CUDA-IPC handle of
+ * its verdict mailbox (ftsgemm_peer_export, 64 bytes), the ranks exchange the handles by any means (the bench uses
+ * torch.distributed.all_gather_object), and ftsgemm_peer_connect maps all of them.  From then on the last CTA of every
+ * fault-tolerant launch on this handle stores the handle's verdict vector (the 8 doubles of ftsgemm_stats_device) and the
+ * launch's sequence number into slot `rank` of EVERY rank's mailbox -- peer stores over NVLink from inside the GEMM kernel,
+ * no collective launch.  ftsgemm_peer_verdict synchronises this handle's stream, waits (up to timeout_ms, default 10 s)
+ * until every rank's slot carries the sequence number of this rank's latest launch (the ranks launch the same number of
+ * GEMMs), and returns the reduced verdict: counters summed, residual maxima max-ed; per_rank (world x 8 doubles) optional.
+ * timeout_ms < 0: no waiting -- for callers that have synchronised the ranks themselves (stream sync + a barrier). */
+int ftsgemm_peer_export(ftsgemm_handle_t h, void *ipc_handle_64bytes);
+int ftsgemm_peer_connect(ftsgemm_handle_t h, int rank, int world, const void *ipc_handles /* world x 64 bytes */);
+int ftsgemm_peer_verdict(ftsgemm_handle_t h, double *out8, double *per_rank, int timeout_ms);
+
 /* Same contract with HOST buffers, synchronous: the call the e2e benchmark times.  The transfers are pipelined over
  * column panels of C (upload A, then per panel B_j (+ C_j when beta != 0) | GEMM_j | download C_j on three streams), so
  * the step costs about the upload time of A, B, C (PCIe is full duplex); pass page-locked host memory for that to

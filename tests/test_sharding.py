@@ -111,7 +111,7 @@ def _nccl_worker(rank, world, port, q):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     ft = pkg.FtSgemm()
-    n = 1024
+    n = 1536
     g = torch.Generator(device="cuda").manual_seed(5 + rank)
     dA = torch.randint(-9, 10, (n * n,), generator=g, device="cuda").float() * 0.1
     dB = torch.randint(-9, 10, (n * n,), generator=g, device="cuda").float() * 0.1
@@ -125,7 +125,15 @@ def _nccl_worker(rank, world, port, q):
         ex.step()
     v = ex.verdict()
     local = ft.stats()
-    q.put((rank, v, local["rows_checked"]))
+    # the same exchange FUSED into the kernel: peer stores over NVLink from the last CTA of every launch, no collective
+    pv = sh.PeerVerdict(ft, dist)
+    n0 = ft.launch_count()
+    for _ in range(7):
+        ft.run(31, n, n, n, dA, dB, dC, 1.0, 0.0, pkg.make_opts(stream=stream, faults=faults))
+    fused_launches = ft.launch_count() - n0
+    v2 = pv.verdict()
+    local2 = ft.stats()
+    q.put((rank, v, local["rows_checked"], v2, local2["rows_checked"], fused_launches))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -146,7 +154,10 @@ def test_world2_nccl_device_verdict_exchange(cuda, ft):
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    for rank, v, local_rows in res:
+    for rank, v, local_rows, v2, local_rows2, fused_launches in res:
         assert v["detected"] == 5 and v["corrected"] == 5 and v["clean"], v
-        assert v["rows_checked"] == 2 * local_rows == 2 * 5 * 1024 * 4
+        assert v["rows_checked"] == 2 * local_rows == 2 * 5 * 1536 * 6
         assert v["per_rank_rows_checked"] == [local_rows, local_rows]
+        assert v2["detected"] == 7 and v2["corrected"] == 7 and v2["clean"], v2
+        assert v2["rows_checked"] == 2 * local_rows2 == 2 * 7 * 1536 * 6
+        assert fused_launches == 7  # one kernel per GEMM, the exchange included
