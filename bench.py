@@ -289,7 +289,7 @@ def main():
     opts_reuse = pkg.make_opts(stream=stream, reuse_b_checksums=True)
     o_cmp = pkg.make_opts(stream=stream, baseline_host_sync=True)
     names = {k["id"]: k for k in pkg.kernel_table()}
-    launches = {"n": 0}
+    last_per_rank = []  # device time of every rank in the most recent timed() call
 
     def sync_all():
         torch.cuda.synchronize()
@@ -311,8 +311,10 @@ def main():
         ms = e0.elapsed_time(e1)
         if dist is not None:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            every = torch.zeros(world, device="cuda", dtype=torch.float64)
+            dist.all_gather_into_tensor(every, t)
+            last_per_rank[:] = [float(x) for x in every.tolist()]
+            ms = max(last_per_rank)  # MAX over ranks
             dist.barrier()
         return ms
 
@@ -355,16 +357,14 @@ def main():
     # fallback when CUDA IPC is unavailable: snapshot kernel + asynchronous NCCL all-gather (sharding.VerdictExchange)
     exch, peer = None, None
     if dist is not None:
-        ok = torch.zeros(1, device="cuda")
-        try:
-            if os.environ.get("FTSGEMM_BENCH_EXCHANGE", "fused") == "fused":
-                peer = sharding.PeerVerdict(ft, dist)
-                ok += 1
-        except Exception as e:  # noqa: BLE001
-            sys.stderr.write(f"[bench] rank {rank}: fused verdict exchange unavailable ({e}); using the NCCL all-gather\n")
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if peer is None or float(ok.item()) < 1:
-            peer = None
+        mode = os.environ.get("FTSGEMM_BENCH_EXCHANGE", "fused")  # fused | nccl | none (none: experiments only)
+        if mode == "fused":
+            try:
+                peer = sharding.PeerVerdict(ft, dist)  # (succeeds or raises on ALL ranks together)
+            except Exception as e:  # noqa: BLE001
+                sys.stderr.write(f"[bench] rank {rank}: {e}; using the NCCL all-gather\n")
+                peer = None
+        if peer is None and mode != "none":
             exch = sharding.VerdictExchange(lambda buf: ft.stats_device(buf, stream), dist, dev)
 
     def step_ft():
@@ -388,6 +388,7 @@ def main():
     t_wall0 = time.time()
     ms_total = timed(step_ft, steps, after=(exch.join if exch is not None else None))
     gpu_launches = ft.launch_count() - launches0
+    ms_per_rank = [round(x / steps, 4) for x in last_per_rank]
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     verdict = exch.verdict() if exch is not None else (peer.verdict() if peer is not None else None)
@@ -593,6 +594,8 @@ def main():
         "clocks": clocks,
         "parity": parity,
     }
+    if world > 1:
+        out["ms_per_step_per_rank"] = ms_per_rank  # the headline is their maximum
     if verdict is not None:
         out["verdict"] = {k: verdict[k] for k in ("tiles", "rows_checked", "detected", "corrected", "uncorrectable", "clean")}
     if id16 is not None:

@@ -1162,7 +1162,8 @@ int ftsgemm_peer_verdict(ftsgemm_handle_t h, double *out8, double *per_rank /* w
     FT_CUDA(h, cudaMemcpy(box, h->d_mailbox, sizeof(double) * h->peer_world * kPeerSlotDoubles, cudaMemcpyDeviceToHost));
     if (timeout_ms < 0) break;  // the caller has synchronised the ranks itself (e.g. a barrier after a stream sync)
     bool all = true;
-    for (int r = 0; r < h->peer_world; ++r) all = all && box[r * kPeerSlotDoubles + 8] >= want;
+    for (int r = 0; r < h->peer_world; ++r)
+      for (int i = 0; i < 8; ++i) all = all && box[r * kPeerSlotDoubles + 2 * i + 1] >= want;  // (value, sequence) pairs
     if (all) break;
     if (waited >= (timeout_ms > 0 ? timeout_ms : 10000)) return FTSGEMM_ERR_TIMEOUT;
     struct timespec ts = {0, 1000000};
@@ -1171,9 +1172,10 @@ int ftsgemm_peer_verdict(ftsgemm_handle_t h, double *out8, double *per_rank /* w
   for (int i = 0; i < 8; ++i) out8[i] = 0.0;
   for (int r = 0; r < h->peer_world; ++r) {
     const double *v = box + r * kPeerSlotDoubles;
-    for (int i = 0; i < 6; ++i) out8[i] += v[i];
-    for (int i = 6; i < 8; ++i) out8[i] = v[i] > out8[i] ? v[i] : out8[i];
-    if (per_rank) memcpy(per_rank + r * 8, v, 8 * sizeof(double));
+    for (int i = 0; i < 6; ++i) out8[i] += v[2 * i];
+    for (int i = 6; i < 8; ++i) out8[i] = v[2 * i] > out8[i] ? v[2 * i] : out8[i];
+    if (per_rank)
+      for (int i = 0; i < 8; ++i) per_rank[r * 8 + i] = v[2 * i];
   }
   return FTSGEMM_OK;
 }

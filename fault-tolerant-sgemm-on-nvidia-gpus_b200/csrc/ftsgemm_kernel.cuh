@@ -48,7 +48,7 @@ constexpr int kAtomMN = 32;       // floats per 128-byte swizzle row
 constexpr int kChkPerTile = 4;    // checksum columns per N-tile: e hi/lo, w hi/lo (2 x 11-bit TF32 terms = 2^-22 relative)
 constexpr int kThreads = 384;     // 12 warps: producer, MMA, TMEM alloc, idle, 4 epilogue, 4 helpers
 constexpr int kMaxPeers = 16;     // ranks of one box whose verdict mailboxes a launch can write to
-constexpr int kPeerSlotDoubles = 16;  // mailbox slot of one rank: 8 verdict doubles, [8] = sequence number
+constexpr int kPeerSlotDoubles = 16;  // mailbox slot of one rank: 8 x (verdict double, sequence number), 16-byte pairs
 constexpr int kMaxFaults = 8;
 constexpr int kMaxEvents = 16;
 
@@ -1333,14 +1333,14 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       v[5] = static_cast<double>(st->checksum_faults);
       v[6] = static_cast<double>(__uint_as_float(st->max_abs_bits));
       v[7] = static_cast<double>(__uint_as_float(st->max_rel_bits));
+      // every value travels with the launch's sequence number in ONE 16-byte store, so a reader can tell a complete
+      // vector (eight equal sequence numbers) without a system-scope fence between data and flag: one NVLink round trip
+      // at the end of the kernel instead of two
       for (int r = 0; r < p.peer_world; ++r) {
-        double *slot = p.peer_box[r] + p.peer_rank * kPeerSlotDoubles;
+        double2 *slot = reinterpret_cast<double2 *>(p.peer_box[r] + p.peer_rank * kPeerSlotDoubles);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) slot[i] = v[i];
+        for (int i = 0; i < 8; ++i) slot[i] = make_double2(v[i], p.peer_seq);
       }
-      __threadfence_system();  // the vectors are visible on every GPU before any sequence number is
-      for (int r = 0; r < p.peer_world; ++r)
-        *reinterpret_cast<volatile double *>(p.peer_box[r] + p.peer_rank * kPeerSlotDoubles + 8) = p.peer_seq;
       *p.exit_count = 0u;
     }
   }

@@ -120,11 +120,28 @@ class PeerVerdict:
     residual maxima max-ed."""
 
     def __init__(self, ft, dist):
+        import torch
         self.ft, self.dist = ft, dist
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        err = None
+        try:
+            mine = ft.peer_export()
+        except Exception as e:  # noqa: BLE001
+            mine, err = None, e
         handles = [None] * self.world
-        dist.all_gather_object(handles, ft.peer_export())
-        ft.peer_connect(self.rank, self.world, handles)
+        dist.all_gather_object(handles, mine)
+        if err is None and all(h is not None for h in handles):
+            try:
+                ft.peer_connect(self.rank, self.world, handles)
+            except Exception as e:  # noqa: BLE001
+                err = e
+        elif err is None:
+            err = RuntimeError("a peer could not export its mailbox")
+        # every rank takes the same decision (an exception on one rank only would leave the others in the barrier)
+        ok = torch.tensor([0.0 if err is not None else 1.0], device="cuda" if torch.cuda.is_available() else "cpu")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) < 1.0:
+            raise RuntimeError(f"fused verdict exchange unavailable on at least one rank ({err})")
         dist.barrier()  # every mailbox is mapped everywhere before the first publishing launch
 
     def verdict(self) -> dict:

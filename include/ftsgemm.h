@@ -194,8 +194,8 @@ int ftsgemm_stats_device(ftsgemm_handle_t h, double *d_out8, void *stream);
  * For a product that is tile-sharded over the GPUs of one box (one process per GPU).  Each rank exports the CUDA-IPC handle of
  * its verdict mailbox (ftsgemm_peer_export, 64 bytes), the ranks exchange the handles by any means (the bench uses
  * torch.distributed.all_gather_object), and ftsgemm_peer_connect maps all of them.  From then on the last CTA of every
- * fault-tolerant launch on this handle stores the handle's verdict vector (the 8 doubles of ftsgemm_stats_device) and the
- * launch's sequence number into slot `rank` of EVERY rank's mailbox -- peer stores over NVLink from inside the GEMM kernel,
+ * fault-tolerant launch on this handle stores the handle's verdict vector (the 8 doubles of ftsgemm_stats_device), each value
+ * paired with the launch's sequence number in one 16-byte store, into slot `rank` of EVERY rank's mailbox -- peer stores over NVLink from inside the GEMM kernel,
  * no collective launch.  ftsgemm_peer_verdict synchronises this handle's stream, waits (up to timeout_ms, default 10 s)
  * until every rank's slot carries the sequence number of this rank's latest launch (the ranks launch the same number of
  * GEMMs), and returns the reduced verdict: counters summed, residual maxima max-ed; per_rank (world x 8 doubles) optional.
