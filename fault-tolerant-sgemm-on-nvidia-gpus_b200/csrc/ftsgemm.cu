@@ -328,12 +328,18 @@ void chk_costs(const KernelParams &p, double floor_cost, std::vector<double> *ou
     out->push_back(std::max(floor_cost, static_cast<double>(chk_tile_width<BNv, CGv>(p, c)) / BNv));
 }
 
+int carrier_tile_index(const KernelParams &p, int m_blk);
+
 PlanInput make_plan_input(int max_units, int CG, int BN, int K, const KernelParams &p) {
   PlanInput in;
   long long units = dbg("grid", 0);
   in.units = (units > 0 && units <= max_units) ? static_cast<int>(units) : max_units;
   in.chk_slices = p.chk_slices > 1 ? p.chk_slices : 1;
-  in.n_chk_tiles = p.tiles_c * p.tiles_m * in.chk_slices;
+  in.n_chk_tiles = p.chk_in_carriers ? 0 : p.tiles_c * p.tiles_m * in.chk_slices;
+  if (p.chk_in_carriers) {
+    for (int m = 0; m < p.tiles_m; ++m) in.carriers.push_back(carrier_tile_index(p, m));
+    in.carrier_cost = static_cast<double>(dbg("carrier_cost_permille", 1400)) * 1e-3;
+  }
   in.n_data_tiles = p.tiles_m * p.tiles_n;
   in.num_kb = (K + kBK - 1) / kBK;
   in.tiles_m = p.tiles_m;
@@ -361,6 +367,28 @@ PlanInput make_plan_input(int max_units, int CG, int BN, int K, const KernelPara
   in.slab_bytes = static_cast<size_t>(CG) * kBM * BN * sizeof(float);
   in.full_search = dbg("plan_full_search", 0) != 0 ? 1 : 0;
   return in;
+}
+
+// Carrier tiles or checksum items?  Legal when the whole checksum-operand box fits the 4 KiB slot of a stage
+// (n_chk_cols <= 32 * CG, i.e. N <= 4096 with 256-wide pair tiles), every operand goes through 3-D tensor maps and there is
+// at most one carrier per unit (a carrier must be the FIRST item of its unit: tensor-memory stage 1 is only free then).
+// Measured (profiles/r02_carriers_on_off.jsonl, us per launch, carriers vs checksum items): a carrier's main loop takes 1.39
+// tile-times (59.8 vs 42.9 us at 4096^3) against 0.68 + epilogue for a checksum item, but it is a longer CHAIN: with fewer
+// than ~2.3 waves of tiles the carrier + its unit's next tile set the makespan -- 2304^3 58.4 vs 53.8, 2560^3 67.5 vs 60.5,
+// then 3328^3 111.9 vs 113.3, 3584^3 137.4 vs 144.8, 3840^3 172.0 vs 171.9, 4096^3 199.8 vs 202.3.
+bool use_carriers(const KernelParams &p, int units, int CG) {
+  const long long c = dbg("carriers", -2);
+  if (c == 0) return false;
+  const bool legal = p.tiles_c == 1 && p.n_chk_cols <= kAtomMN * CG && (p.tma3d & 7) == 7 && p.tiles_m <= units;
+  if (!legal) return false;
+  if (c > 0) return true;
+  return 4ll * p.tiles_m * p.tiles_n >= 9ll * units;  // from 2.25 waves of data tiles on
+}
+
+// raster index (among the data tiles) of tile (m_blk, n_blk = 0): inverse of decode_tile
+int carrier_tile_index(const KernelParams &p, int m_blk) {
+  const int gsz = p.group_n < p.tiles_n ? p.group_n : p.tiles_n;
+  return m_blk * gsz;
 }
 
 // K-slices of the checksum items (KernelParams::chk_slices): only where units would otherwise idle -- all data tiles and
@@ -586,7 +614,9 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
     if (max_units < 1) return FTSGEMM_ERR_UNSUPPORTED;  // not a single CTA (pair) of this kernel fits on the device partition
   }
   if (ft) {
-    p.chk_slices = choose_chk_slices(p, max_units, K);
+    // Carrier tiles instead of checksum items (KernelParams::chk_in_carriers, use_carriers)
+    p.chk_in_carriers = use_carriers(p, max_units, CG) ? 1 : 0;
+    p.chk_slices = p.chk_in_carriers ? 1 : choose_chk_slices(p, max_units, K);
     const size_t n_flags_s = static_cast<size_t>(p.tiles_m) * CG * (kBM / 32) * p.tiles_c * p.chk_slices;
     if (p.chk_slices > 1 && n_flags_s * sizeof(int) > kChkFlagBytes) p.chk_slices = 1;
     if (p.chk_slices > 1) {
@@ -606,7 +636,7 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
   }
   const PlanInput pin = make_plan_input(max_units, CG, BN, K, p);
   const std::array<long long, 6> key = {v.info.id, M, N, K, pin.units,
-                                        pin.force_slices * 16 + pin.max_slices + pin.lockstep * 8192 + pin.full_search * 16384 + pin.chk_slices * 65536};
+                                        pin.force_slices * 16 + pin.max_slices + pin.lockstep * 8192 + pin.full_search * 16384 + pin.chk_slices * 65536 + (p.chk_in_carriers ? 1048576 : 0)};
   ftsgemm_handle_s::CachedPlan &cp = h->plans[key];
   if (!cp.uploaded) {
     if (h->plans.size() > 64) {  // bound the cache: drop everything but this entry
@@ -875,7 +905,11 @@ int ftsgemm_debug_schedule(int kernel_id, int M, int N, int K, int num_sms, int 
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
   plan_tiles(M, N, v->bn, v->cg, v->info.fault_tolerant != 0, &p);
-  if (v->info.fault_tolerant) p.chk_slices = choose_chk_slices(p, num_sms / v->cg, K);
+  if (v->info.fault_tolerant) {
+    if (M % kAtomMN == 0 && N % kAtomMN == 0 && dbg("tma3d", 1) != 0) p.tma3d = 7;
+    p.chk_in_carriers = use_carriers(p, num_sms / v->cg, v->cg) ? 1 : 0;
+    p.chk_slices = p.chk_in_carriers ? 1 : choose_chk_slices(p, num_sms / v->cg, K);
+  }
   const PlanInput pin = make_plan_input(num_sms / v->cg, v->cg, v->bn, K, p);
   const Plan plan = build_plan(pin);
   if (hdr) {

@@ -98,6 +98,11 @@ struct KernelParams {
   int sk_epoch;
   // fault tolerance: checksum tile-columns
   int tiles_c;          // number of BN-wide checksum tile-columns (0 when FT is off)
+  int chk_in_carriers;  // 1: no checksum tiles in the work plan -- the first data tile of every tile-row (plan kind 6, always the
+                        // first item of its unit, when tensor-memory stage 1 is still free) also accumulates that row's
+                        // checksum product R = A [e, w]^T in columns [BN, BN + n_chk_cols) and publishes it before its own
+                        // check.  Costs ~0.25 tile-times per tile-row (the A slab is read from shared memory twice per
+                        // k-step) instead of a 0.68 tile-time checksum item that streams A from HBM a second time.
   int chk_slices;       // >= 1: every checksum tile is computed as chk_slices independent K-slices (one plan item each, on
                         // otherwise idle units of small problems, where the checksum item is the critical path: its K loop
                         // starts after the encode and is as long as a data tile's); slice s publishes its partial expected
@@ -177,16 +182,25 @@ struct TileCfg {
   static constexpr int kBNLocal = BN / CG;                  // B rows staged by this CTA
   static constexpr int kABytes = kBM * kBK * 4;
   static constexpr int kBBytes = kBNLocal * kBK * 4;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kOperandBytes = kABytes + kBBytes;
+  // ABFT instantiations keep one 4 KiB slot per stage for a box of the checksum operand (one 32-column atom per CTA): a
+  // CARRIER tile (plan item kind 6) loads it next to its own A / B stage and issues a second UMMA per k-step on the same A
+  // slab, so the checksum product of its tile-row rides along instead of being a work item of its own.  The ring gets one
+  // stage shorter for it (6 instead of 7 for the 256x256 pair tile: measured neutral, profiles/r02_ring_6_vs_7_stages.jsonl).
+  // The slots form a ring of their own BEHIND the A / B stages (whose 32 KiB stride stays a power of two: with the slot
+  // inside each stage -- a 36 KiB stride -- every main loop ran 21 % slower, profiles/r02_neg_stage_stride_36k.jsonl).
+  static constexpr int kESlotBytes = FT ? kAtomMN * kBK * 4 : 0;
+  static constexpr int kStageBytes = kOperandBytes;          // stride of the A / B ring
+  static constexpr int kStageFootprint = kOperandBytes + kESlotBytes;
   static constexpr int kAccStages = (2 * BN <= 512) ? 2 : 1;
   static constexpr int kTmemNeeded = kAccStages * BN;
   static constexpr int kTmemCols = kTmemNeeded <= 32 ? 32 : kTmemNeeded <= 64 ? 64 : kTmemNeeded <= 128 ? 128
                                    : kTmemNeeded <= 256 ? 256 : 512;
   static constexpr int kBarBytes = 2048;  // barriers (512) + the epilogue pairs' exchange area (4 x 32 lanes x 3 floats)
   static constexpr int kMaxSmem = 227 * 1024 - 1024 /*alignment slack*/ - kBarBytes;
-  static constexpr int kStagesFit = kMaxSmem / kStageBytes;
+  static constexpr int kStagesFit = kMaxSmem / kStageFootprint;
   static constexpr int kStages = kStagesFit > FTSGEMM_MAX_STAGES ? FTSGEMM_MAX_STAGES : kStagesFit;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kBarBytes;
+  static constexpr int kSmemBytes = kStages * kStageFootprint + 1024 + kBarBytes;
 };
 
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
@@ -205,7 +219,7 @@ __host__ __device__ __forceinline__ TileCoord decode_tile(const KernelParams &p,
   TileCoord tc;
   tc.slice = 0;
   const int per_slice = p.tiles_c * p.tiles_m;
-  const int n_chk_tiles = per_slice * (p.chk_slices > 1 ? p.chk_slices : 1);
+  const int n_chk_tiles = p.chk_in_carriers ? 0 : per_slice * (p.chk_slices > 1 ? p.chk_slices : 1);
   if (t < n_chk_tiles) {
     tc.is_chk = true;
     tc.slice = t / (per_slice > 0 ? per_slice : 1);
@@ -253,7 +267,7 @@ __host__ __device__ __forceinline__ int chk_tile_width(const KernelParams &p, in
 // ------------------------------------------------------------------------------------------------------------
 struct Segment {
   int tile, kb_begin, kb_end;
-  int kind;   // 0 whole tile, 1 first piece, 3 middle piece, 2 last piece
+  int kind;   // 0 whole tile, 1 first piece, 3 middle piece, 2 last piece, 6 carrier (whole data tile + its row's checksum product)
   int slice;
   int split_idx;
 };
@@ -822,12 +836,15 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // 128B-swizzle atoms need 1024B alignment.  (Both CTAs of a pair see the same dynamic-smem base offset, which
   // cta_group::2 requires: the pair's MMA applies one descriptor to both CTAs' shared memory.)
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+  const uint32_t eslot_base = smem_base + kStages * Cfg::kStageBytes;  // checksum-operand slots of the carrier tiles
+  const uint32_t bar_base = smem_base + kStages * Cfg::kStageFootprint;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   auto seeded_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 4 + a); };  // leader: TMEM stage a holds the seed
+  // carrier tiles: the epilogue warps (of both CTAs) have read the checksum columns out of tensor-memory stage 1
+  const uint32_t chk_drained_bar = bar_base + 8u * (2 * kStages + 6);
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 7);
   // number of (epilogue warp, item) pairs this CTA has finished: the helper warps' view of which accumulator stages
   // are drained (a counter, not an mbarrier: the helpers may be many items behind while they encode B)
@@ -862,6 +879,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ptx::mbar_init(seeded_bar(a), 4 * CG);  // one arrive per helper warp of every CTA in the group
     }
     ptx::st_shared_u32(epi_count, 0u);
+    ptx::mbar_init(chk_drained_bar, 4 * CG);
     ptx::fence_mbar_init();
   }
   if (CG == 2) ptx::cluster_sync_all();  // peer barriers must be initialised before any remote arrive / 2-CTA alloc
@@ -907,6 +925,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const TileCoord tc = decode_tile(p, sg.tile);
       const int m0 = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;        // this CTA's 128 rows of A
       const bool b_is_chk = FT && tc.is_chk;
+      const bool carrier = FT && sg.kind == 6;
       const bool wave_item = p.wave_cnt != nullptr && sg.kind == 0 && !b_is_chk && is_leader;
       if (wave_item && whole_ord > 0) {
         // all units have finished loading their previous whole tile: start this one together
@@ -924,11 +943,11 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int nb0 = (b_is_chk ? tc.n_blk * chk_cols_per_tile(BN) : tc.n_blk * BN) +
                       static_cast<int>(cta_rank) * (n_eff / CG);  // this CTA's share of B rows
       const CUtensorMap *tmb = b_is_chk ? &tmChk : &tmB;
-      if (FT && b_is_chk && p.pdl_wait == 1 && !pdl_done) {
+      if (FT && (b_is_chk || carrier) && p.pdl_wait == 1 && !pdl_done) {
         ptx::pdl_wait();  // the pre-pass kernel has completed and its writes are visible
         pdl_done = true;
       }
-      if (FT && b_is_chk && p.enc_front && !pdl_done) {
+      if (FT && (b_is_chk || carrier) && p.enc_front && !pdl_done) {
         // front-phase encode: every warp of the grid has stored its share of the checksum operand
         if (lane == 0) {
           ptx::Watchdog wd;
@@ -950,7 +969,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       //  selected descriptor pointer measurably slows the TMA issue)
       auto fast_loop = [&](const CUtensorMap *tmb_const) {
         const uint32_t stage_tx = b_is_chk ? static_cast<uint32_t>(Cfg::kABytes + p.chk_box_bytes)
-                                           : static_cast<uint32_t>(Cfg::kStageBytes);
+                                           : static_cast<uint32_t>(Cfg::kOperandBytes);
         for (int kb = sg.kb_begin; kb < sg.kb_end; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sA = smem_base + stage * Cfg::kStageBytes;
@@ -976,7 +995,42 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       };
-      if (all3d) {
+      // carrier tile: the same loop with a third load per stage (the loops are specialised OUTSIDE the k loop: a predicated-off
+      // TMA / UMMA instruction in the ordinary loops cost every tile 20 % -- the issue threads are the bottleneck)
+      auto carrier_loop = [&]() {
+        const uint32_t stage_tx = static_cast<uint32_t>(Cfg::kOperandBytes + p.chk_box_bytes);
+        const int e_atom = static_cast<int>(cta_rank) * (p.chk_box_bytes / (kAtomMN * kBK * 4));  // this CTA's share of [e, w]
+        for (int kb = sg.kb_begin; kb < sg.kb_end; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sA = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sB = sA + Cfg::kABytes;
+          const uint32_t sE = eslot_base + stage * Cfg::kESlotBytes;
+          const int k0 = kb * kBK;
+          if (ptx::elect_one()) {
+            if (CG == 2) {
+              const uint32_t bar = ptx::mapa(full_bar(stage), 0);
+              if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * stage_tx);
+              else ptx::mbar_arrive_cluster(bar);
+              ptx::tma_load_3d_cg2(sA, &tmA, bar, 0, k0, a_atom);
+              ptx::tma_load_3d_cg2(sB, &tmB, bar, 0, k0, b_atom);
+              ptx::tma_load_3d_cg2(sE, &tmChk, bar, 0, k0, e_atom);
+            } else {
+              ptx::mbar_arrive_expect_tx(full_bar(stage), stage_tx);
+              ptx::tma_load_3d(sA, &tmA, full_bar(stage), 0, k0, a_atom);
+              ptx::tma_load_3d(sB, &tmB, full_bar(stage), 0, k0, b_atom);
+              ptx::tma_load_3d(sE, &tmChk, full_bar(stage), 0, k0, e_atom);
+            }
+          }
+          __syncwarp();
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      };
+      if (FT && carrier) {
+        carrier_loop();
+      } else if (all3d) {
         if (b_is_chk) fast_loop(&tmChk);
         else fast_loop(&tmB);
       } else {
@@ -987,7 +1041,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int k0 = kb * kBK;
           const uint32_t bar = (CG == 2) ? ptx::mapa(full_bar(stage), 0) : full_bar(stage);
           const uint32_t stage_tx = (b_is_chk && (p.tma3d & 4)) ? static_cast<uint32_t>(Cfg::kABytes + p.chk_box_bytes)
-                                                                : static_cast<uint32_t>(Cfg::kStageBytes);
+                                                                : static_cast<uint32_t>(Cfg::kOperandBytes);
           if (ptx::elect_one()) {
           if (CG == 2) {
             if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * stage_tx);
@@ -1037,20 +1091,32 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint64_t desc_hi = desc0 & 0xFFFFFFFF00000000ull;
     const uint32_t desc_lo0 = static_cast<uint32_t>(desc0);
     const uint32_t kstep16 = p.kstep_bytes >> 4;
+    const uint32_t e_lo0 = desc_lo0 + ((eslot_base - smem_base) >> 4);  // checksum-operand slot of stage 0 (carrier tiles)
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t seed_phase = 0;  // bit a: parity of seeded_bar(a)
+    bool first_is_carrier = false;
     SegIter it(p, unit);
     Segment sg;
     int item_idx = -1;
     while (it.next(sg)) {
       ++item_idx;
       uint32_t idesc_t = idesc;
+      const bool carrier = FT && sg.kind == 6;
+      uint32_t idesc_c = 0u;
       if (FT) {
         const TileCoord tc = decode_tile(p, sg.tile);
         if (tc.is_chk) idesc_t = ptx::make_idesc_tf32(kBM * CG, chk_tile_width<BN, CG>(p, tc.n_blk), 1, 1);
+        if (carrier) idesc_c = ptx::make_idesc_tf32(kBM * CG, chk_tile_width<BN, CG>(p, 0), 1, 1);
+        // a carrier is the first item of its unit and also occupies accumulator stage 1: the second item may only start
+        // once the carrier's epilogue has read the checksum columns out of it
+        if (item_idx == 1 && first_is_carrier) {
+          ptx::mbar_wait(chk_drained_bar, 0u);
+          ptx::tc_fence_after();
+        }
+        if (item_idx == 0) first_is_carrier = carrier;
       }
       ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       ptx::tc_fence_after();
@@ -1066,6 +1132,47 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         ptx::tc_fence_after();
         first = 0u;
       }
+      if (FT && carrier) {
+        // carrier tile: two UMMAs per k-step on the same A slab -- the data tile, and the tile-row's checksum product into
+        // accumulator stage acc ^ 1 (a loop of its own: see the producer)
+        const uint32_t c_tmem = tmem_base + (acc ^ 1) * BN;
+        for (int kb = sg.kb_begin; kb < sg.kb_end; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t a_lo = desc_lo0 + static_cast<uint32_t>(stage) * (Cfg::kStageBytes >> 4);
+          const uint32_t b_lo = a_lo + (Cfg::kABytes >> 4);
+          const uint32_t e_lo = e_lo0 + static_cast<uint32_t>(stage) * (Cfg::kESlotBytes >> 4);
+          const bool last_kb = (kb + 1 == sg.kb_end);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int j = 0; j < kBK / 8; ++j) {
+              const uint64_t da = desc_hi | static_cast<uint64_t>(a_lo + j * kstep16);
+              const uint64_t db = desc_hi | static_cast<uint64_t>(b_lo + j * kstep16);
+              const uint64_t de = desc_hi | static_cast<uint64_t>(e_lo + j * kstep16);
+              const uint32_t accum = (j == 0) ? (first ^ 1u) : 1u;
+              if (CG == 2) {
+                ptx::mma_tf32_cg2(d_tmem, da, db, idesc_t, accum);
+                ptx::mma_tf32_cg2(c_tmem, da, de, idesc_c, accum);
+              } else {
+                ptx::mma_tf32(d_tmem, da, db, idesc_t, accum);
+                ptx::mma_tf32(c_tmem, da, de, idesc_c, accum);
+              }
+            }
+            if (CG == 2) ptx::mma_commit_cg2(empty_bar(stage), 0x3);
+            else ptx::mma_commit(empty_bar(stage));
+            if (last_kb) {
+              if (CG == 2) ptx::mma_commit_cg2(tfull_bar(acc), 0x3);
+              else ptx::mma_commit(tfull_bar(acc));
+            }
+          }
+          __syncwarp();
+          first = 0u;
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      } else
       for (int kb = sg.kb_begin; kb < sg.kb_end; ++kb) {
         ptx::mbar_wait(full_bar(stage), phase);
         ptx::tc_fence_after();
@@ -1124,7 +1231,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int m = m0_cta + row;
       ExpectedChk xp;
       xp.ready = false;
-      if (FT && !tc.is_chk && (sg.kind == 0 || sg.kind == 2) && !(p.dbg_flags & 1)) {
+      if (FT && !tc.is_chk && (sg.kind == 0 || sg.kind == 2 || sg.kind == 6) && !(p.dbg_flags & 1)) {
         // poll the slab flag (at most ~2 polls per microsecond) until it is raised or the accumulator is complete
         try_prefetch_expected(p, q, lane, m, m0_cta, tc.n_blk, xp);
         while (!xp.ready && !ptx::mbar_try_wait(tfull_bar(acc), acc_phase)) {
@@ -1140,6 +1247,21 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         trace_put(p, unit, item_idx, 7, static_cast<unsigned long long>(sg.tile) | (static_cast<unsigned long long>(sg.kind) << 24));
       }
 
+      if (FT && sg.kind == 6) {
+        // carrier: publish the tile-row's expected checksums (accumulator stage acc ^ 1), raise the slab flag, hand the
+        // stage back to the UMMA warp -- then this tile is checked like any other (its own flag is the last one to wait for)
+        const uint32_t taddr_c = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (acc ^ 1) * BN;
+        store_tile<BN>(taddr_c, p.chk_out + m, m < p.M, 0, p.n_chk_cols, p.M, 1.0f, 0.0f, 0, (p.n_chk_cols + 31) / 32);
+        __threadfence();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          atomicExch(p.chk_flags + ((m0_cta >> 5) + q) * chk_flags_per_slab(p), p.chk_epoch);
+          if (CG == 2) ptx::mbar_arrive_cluster(ptx::mapa(chk_drained_bar, 0));
+          else ptx::mbar_arrive(chk_drained_bar);
+        }
+        __syncwarp();
+      }
       const bool parks = sg.kind == 1 || sg.kind == 3;  // first / middle piece of a cut tile
       if (parks) {
         // park the raw sums of this piece for the unit that owns the next one
@@ -1269,6 +1391,7 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int acc = 0;
       uint32_t acc_phase = 0;
       int item_idx = -1;
+      int first_kind = 0;
       bool have_prev = false;
       Segment prev;
       int prev_acc = 0;
@@ -1277,13 +1400,16 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       Segment sg;
       while (it.next(sg)) {
         ++item_idx;
+        if (item_idx == 0) first_kind = sg.kind;
         if (sg.kind == 2 || sg.kind == 3) {
           // Seed first (it has to be in tensor memory before this item's first UMMA, i.e. during the previous item's main
           // loop), assist the previous item's epilogue afterwards.  The accumulator stage must have been drained by this
           // CTA's four epilogue warps (item_idx - 2 and before).  A parked accumulator never depends on a helper warp
           // (parking epilogues are not assisted), so waiting here for another unit's flag cannot close a cycle.
-          if (item_idx >= 2) {
-            const uint32_t need = 4u * static_cast<uint32_t>(item_idx - 1);
+          // (after a carrier -- always item 0 -- stage 1 also holds the tile-row's checksum product until the carrier's
+          //  epilogue has stored it: wait for that whole epilogue)
+          if (item_idx >= 2 || (item_idx == 1 && first_kind == 6)) {
+            const uint32_t need = item_idx >= 2 ? 4u * static_cast<uint32_t>(item_idx - 1) : 4u;
             ptx::Watchdog wd;
             while (ptx::ld_acquire_shared_u32(epi_count) < need) {
               __nanosleep(64);

@@ -31,7 +31,8 @@ namespace ftsgemm {
 struct PlanItem {
   int tile;        // decode order: checksum tiles first, then data tiles
   int kb_begin, kb_end;
-  int kind;        // 0 whole tile, 1 first piece (park), 3 middle piece (seed + park), 2 last piece (seed + finish)
+  int kind;        // 0 whole tile, 1 first piece (park), 3 middle piece (seed + park), 2 last piece (seed + finish),
+                   // 6 carrier (a whole data tile that also computes its tile-row's checksum product; first in its unit's list)
   int slice;       // piece index within its tile
   int split_idx;   // index among the cut tiles (workspace slot), -1 otherwise
 };
@@ -54,6 +55,9 @@ struct PlanInput {
   int tiles_m;          // checksum tile t belongs to checksum tile-column t / tiles_m
   std::vector<double> chk_col_cost;  // tile-times of one tile of each checksum tile-column
   double chk_release = 0.0;          // tile-times before checksum items can start (their operand comes from the pre-pass)
+  std::vector<int> carriers;         // raster indices of the data tiles that carry their tile-row's checksum product
+                                     // (then n_chk_tiles == 0); given first, one per unit
+  double carrier_cost = 1.4;         // tile-times of a carrier (second UMMA per k-step on the same A slab; measured 59.8 vs 42.9 us)
   double item_overhead = 0.0;        // tile-times per item (pipeline fill + drain)
   double park_latency = 0.0;         // tile-times between the end of a piece's main loop and its successor's start
   double seed_overhead = 0.0;        // extra tile-times of a seeded piece (its accumulator stage is loaded before the first UMMA)
@@ -131,6 +135,11 @@ inline double schedule(const PlanInput &in, const Cut &c, Plan *out) {
                             len + (p > 0 ? in.seed_overhead : 0.0), ready[i], false);
     ready[i] = end + in.park_latency;
   };
+  std::vector<char> is_carrier(static_cast<size_t>(in.n_data_tiles), 0);
+  for (int d : in.carriers) {
+    is_carrier[static_cast<size_t>(d)] = 1;
+    give(PlanItem{in.n_chk_tiles + d, 0, in.num_kb, 6, 0, -1}, in.carrier_cost, 0.0, true);
+  }
   for (int i = 0; i < c.He; ++i) piece(i, 0);
   {
     const int S = in.chk_slices > 1 ? in.chk_slices : 1, per_slice = in.n_chk_tiles / S;
@@ -141,7 +150,8 @@ inline double schedule(const PlanInput &in, const Cut &c, Plan *out) {
       give(PlanItem{t, kb0, kb1, 0, sl, -1}, in.chk_col_cost[static_cast<size_t>(r / in.tiles_m)] / S, in.chk_release, false);
     }
   }
-  for (int d = 0; d < whole; ++d) give(PlanItem{in.n_chk_tiles + d, 0, in.num_kb, 0, 0, -1}, 1.0, 0.0, true);
+  for (int d = 0; d < whole; ++d)
+    if (!is_carrier[static_cast<size_t>(d)]) give(PlanItem{in.n_chk_tiles + d, 0, in.num_kb, 0, 0, -1}, 1.0, 0.0, true);
   for (int i = c.He; i < H; ++i) piece(i, 0);
   for (int p = 1; p < max_pieces; ++p) {
     std::vector<int> order;
@@ -200,8 +210,11 @@ inline Plan build_plan(const PlanInput &in) {
     const size_t slab_cap = std::min<size_t>((static_cast<size_t>(256) << 20) / std::max<size_t>(1, in.slab_bytes * (pieces - 1)),
                                              65536 / (8 * sizeof(int) * (pieces - 1)));
     const int hcap = static_cast<int>(std::min<size_t>(slab_cap, static_cast<size_t>(T)));
+    int max_carrier = -1;
+    for (int d : in.carriers) max_carrier = std::max(max_carrier, d);
     auto consider = [&](const Cut &c) {
       if (c.He + c.Hl <= 0 || c.He + c.Hl > hcap) return;
+      if (T - (c.He + c.Hl) <= max_carrier) return;  // the cut tiles are the last ones of the raster: no carrier among them
       const double t = schedule(in, c, nullptr);
       if (best < 0.0 || t < best) {
         best = t;

@@ -64,7 +64,7 @@ def trace_case(pkg, kid, n, dbg=None, tag="", reuse=False, m=None, k=None):
     for u in tr:
         prev_end = None
         for it in u:
-            cls = "chk" if it["tile"] < n_chk else {0: "whole", 1: "contrib", 2: "finish", 3: "contrib", 5: "enc_tile"}[it["kind"]]
+            cls = "chk" if it["tile"] < n_chk else {0: "whole", 1: "contrib", 2: "finish", 3: "contrib", 5: "enc_tile", 6: "enc_tile"}[it["kind"]]
             main[cls].append(it["mma_end"] - it["mma_start"])
             epi[cls].append(it["epi_end"] - it["acc_done"])
             if cls in ("whole", "finish", "enc_tile") and it["check_done"]:

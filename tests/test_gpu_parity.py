@@ -154,7 +154,8 @@ def test_random_shapes_and_knobs(cuda, ft, dev, oracle, seed):
     alpha = float(rng.choice([1.0, 0.75, -2.0]))
     beta = float(rng.choice([0.0, -1.5, 1.0]))
     knobs = {"splitk": int(rng.choice([-1, 0, 2, 3])), 
-             "wave_sync": int(rng.choice([0, 1])), "pdl": int(rng.choice([0, 1])), "epi_assist": int(rng.choice([0, 1]))}
+             "wave_sync": int(rng.choice([0, 1])), "pdl": int(rng.choice([0, 1])), "epi_assist": int(rng.choice([0, 1])),
+             "carriers": int(rng.choice([0, 1])), "chk_slices": int(rng.choice([1, 2, 3])), "enc_front": int(rng.choice([0, 1]))}
     A, B = rng.standard_normal(M * K).astype(np.float32), rng.standard_normal(N * K).astype(np.float32)
     C0 = rng.standard_normal(M * N).astype(np.float32)
     model = oracle.sgemm_nt_tf32_model(M, N, K, alpha, A, B, beta, C0, "trunc")
@@ -179,6 +180,43 @@ def test_random_shapes_and_knobs(cuda, ft, dev, oracle, seed):
     finally:
         for k in knobs:
             ft.debug_set(k, -1)
+
+
+def test_carrier_tiles_equal_checksum_items(cuda, ft, dev, oracle):
+    """Carrier tiles (the first data tile of every tile-row also accumulates the row's checksum product in tensor-memory
+    stage 1, plan kind 6) against checksum items: the same UMMA sequence produces the same expected checksums, so results
+    and verdicts are bit-identical -- fault-free, with faults inside and outside carrier tiles, with every cut plan (a seeded
+    piece right behind a carrier must wait for the carrier's epilogue before its seed goes into stage 1)."""
+    rng = np.random.default_rng(31)
+    for (kid, M, N, K) in ((31, 1536, 1024, 640), (31, 768, 2048, 352), (15, 512, 512, 256), (12, 1024, 512, 300)):
+        A, B = _rand(rng, M * K), _rand(rng, N * K)
+        C0 = rng.standard_normal(M * N).astype(np.float32)
+        faults = [{"row": 5, "col": 3, "xor": 1 << 29}, {"row": M - 1, "col": N - 1, "add": 77.0},
+                  {"row": M // 2, "col": 200, "xor": 1 << 30}, {"row": 300, "col": N // 2 + 7, "add": -9.0}]
+        for splitk in (-1, 0, 2, 3):
+            outs, sts = [], []
+            for carriers in (1, 0):
+                try:
+                    ft.debug_set("carriers", carriers)
+                    ft.debug_set("splitk", splitk)
+                    ft.debug_set("chk_slices", 1)  # (K-slices of checksum items add their partial sums in another order)
+                    if carriers:  # (the plan really contains carriers: one per tile-row)
+                        hdr, segs = ft.debug_schedule(kid, M, N, K, cuda.cuda.get_device_properties(0).multi_processor_count)
+                        assert sum(1 for s_ in segs if s_["kind"] == 6) > 0 and hdr["n_chk_tiles"] == 0
+                    dev.stats()
+                    clean = _run(cuda, dev, kid, M, N, K, A, B, C0, 0.75, -1.5)
+                    assert dev.stats()["detected"] == 0
+                    outs.append((clean, _run(cuda, dev, kid, M, N, K, A, B, C0, 0.75, -1.5, opts=ft.make_opts(faults=faults))))
+                    st = dev.stats()
+                    sts.append((st["detected"], st["corrected"], st["recomputed"], st["uncorrectable"]))
+                finally:
+                    ft.debug_set("carriers", -1)
+                    ft.debug_set("splitk", -1)
+                    ft.debug_set("chk_slices", -1)
+            assert sts[0] == sts[1] and sts[0][0] == 4 and sts[0][3] == 0, (kid, splitk, sts)
+            assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]), (kid, splitk)
+    model = oracle.sgemm_nt_tf32_model(M, N, K, 0.75, A, B, -1.5, C0, "trunc")
+    assert oracle.error_metrics(model, outs[0][0])["rel_fro"] < TOL_MODEL
 
 
 def test_epilogue_assist_is_neutral(cuda, ft, dev):

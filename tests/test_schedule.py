@@ -29,6 +29,8 @@ def _simulate(hdr, segs, acc_stages):
                 tiles_c = max(tiles_c, s["n_blk"] + 1)
             if s["kind"] in (1, 2, 3):
                 piece_at[(s["tile"], s["slice"])] = (u, i)
+    carrier_rows = {s["m_blk"] for s in segs if s["kind"] == 6}  # rows whose checksum product rides on their first data tile
+    row_done = {m: False for m in carrier_rows}
     mma_done = [0] * units   # number of items whose main loop finished
     epi_done = [0] * units
     done_epi = set()         # (unit, idx)
@@ -50,12 +52,16 @@ def _simulate(hdr, segs, acc_stages):
                 ok = True
                 if hdr["n_chk_tiles"] and not s["is_chk"] and s["kind"] in (0, 2):  # parking pieces are not checked
                     ok = all(chk_done[(s["m_blk"], c, sl)] for c in range(tiles_c) for sl in range(max(1, hdr.get("chk_slices", 1))))
+                if carrier_rows and s["kind"] in (0, 2):  # waits for the carrier of its tile-row (a carrier publishes, then checks itself)
+                    ok = row_done[s["m_blk"]]
                 if not ok:
                     break
                 epi_done[u] += 1
                 done_epi.add((u, i))
                 if s["is_chk"]:
                     chk_done[(s["m_blk"], s["n_blk"], s["slice"])] = True
+                if s["kind"] == 6:
+                    row_done[s["m_blk"]] = True
                 progress = True
     return all(epi_done[u] == len(per_unit[u]) for u in range(units))
 
@@ -74,7 +80,7 @@ def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms):
     cover = {}
     for s in segs:
         assert 0 <= s["kb_begin"] < s["kb_end"] <= num_kb
-        assert s["kind"] in (0, 1, 2, 3)
+        assert s["kind"] in (0, 1, 2, 3, 6)
         cover.setdefault(s["tile"], []).append((s["kb_begin"], s["kb_end"], s["kind"], s["slice"]))
         if s["kind"] in (1, 2, 3):
             assert not s["is_chk"]
@@ -90,7 +96,7 @@ def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms):
         for a, b in zip(pieces, pieces[1:]):
             assert a[1] == b[0]  # contiguous, no overlap
         if len(pieces) == 1:
-            assert pieces[0][2] == 0
+            assert pieces[0][2] in (0, 6)
         else:
             assert 2 <= len(pieces) <= S
             assert [p[2] for p in pieces] == [1] + [3] * (len(pieces) - 2) + [2]
@@ -104,8 +110,8 @@ def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms):
     for s_ in segs:
         per_unit.setdefault(s_["unit"], []).append(s_)
     for lst in per_unit.values():
-        word = "".join("C" if s_["is_chk"] else "WPFM"[s_["kind"]] for s_ in lst)
-        assert re.fullmatch(r"P*C*W*P*[FM]*", word), word
+        word = "".join("C" if s_["is_chk"] else "WPFM__K"[s_["kind"]] for s_ in lst)
+        assert re.fullmatch(r"K?P*C*W*P*[FM]*", word), word  # (a carrier is always the first item of its unit)
         later = [s_["slice"] for s_ in lst if s_["kind"] in (2, 3)]
         assert later == sorted(later)
         for cls in ("C", "W"):
@@ -117,7 +123,11 @@ def test_decomposition_covers_and_cannot_deadlock(ft, kid, shape, num_sms):
     # checksum tiles: n_chk_tiles of them, 8 columns per N-tile
     chk = {(s["m_blk"], s["n_blk"], s["slice"]) for s in segs if s["is_chk"]}
     assert len(chk) == hdr["n_chk_tiles"]
-    if kid in (11, 12, 13, 14, 16, 15, 31, 32):
+    carriers = [s_ for s_ in segs if s_["kind"] == 6]
+    if carriers:  # one per tile-row, the row's first tile, and no checksum tiles at all
+        assert hdr["n_chk_tiles"] == 0 and sorted(s_["m_blk"] for s_ in carriers) == list(range(-(-M // (128 * hdr["cta_group"]))))
+        assert all(s_["n_blk"] == 0 for s_ in carriers) and 4 * -(-N // TILE_N[kid]) <= 32 * hdr["cta_group"]
+    elif kid in (11, 12, 13, 14, 16, 15, 31, 32):
         tiles_n = -(-N // TILE_N[kid])
         assert hdr["n_chk_tiles"] == -(-M // (128 * hdr["cta_group"])) * -(-(tiles_n * 4) // TILE_N[kid]) * S_chk
         if S_chk > 1:  # slices only where every data tile and every slice get a unit of their own
@@ -132,13 +142,13 @@ def test_planner_levels_the_units(ft):
         hdr, segs = ft.debug_schedule(kid, n, n, n, 148)
         work = [0.0] * hdr["units"]
         for s in segs:
-            work[s["unit"]] += (0.58 if s["is_chk"] else 1.0) * (s["kb_end"] - s["kb_begin"]) / hdr["num_kb"]
+            work[s["unit"]] += (0.58 if s["is_chk"] else 1.25 if s["kind"] == 6 else 1.0) * (s["kb_end"] - s["kb_begin"]) / hdr["num_kb"]
         return hdr, max(work), sum(work) / hdr["units"]
     hdr, t, ideal = makespan(21, 4096)   # 256 tiles on 74 pairs: 3.46 waves -> 4 waves uncut
     assert hdr["sk_tiles"] > 0 and hdr["sk_slices"] == 2 and t <= 3.7
     hdr, t, ideal = makespan(21, 1024)   # 16 tiles on 74 pairs: nothing to level
     assert hdr["sk_tiles"] == 0 and t == 1.0
-    hdr, t, ideal = makespan(31, 4096)   # ABFT tiles are cut as well (seeded chains keep the checksum algebra exact)
-    assert hdr["sk_tiles"] > 0 and hdr["n_chk_tiles"] == 16 and t <= ideal * 1.05
+    hdr, t, ideal = makespan(31, 4096)   # ABFT tiles are cut as well (seeded chains keep the checksum algebra exact); the
+    assert hdr["sk_tiles"] > 0 and hdr["n_chk_tiles"] == 0 and t <= ideal * 1.05  # checksum product rides on 16 carrier tiles
     hdr, t, ideal = makespan(31, 8192)
     assert hdr["n_chk_tiles"] == 32 and t <= ideal * 1.03
