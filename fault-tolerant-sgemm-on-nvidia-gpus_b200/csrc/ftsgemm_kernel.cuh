@@ -304,6 +304,35 @@ template <int BN>
 __device__ __forceinline__ void store_tile(uint32_t taddr, float *crow, bool row_ok, int n0, int n_limit, int ldc,
                                            float alpha, float beta, int c_begin = 0, int c_end = BN / 32) {
   const bool full_n = (n0 + BN <= n_limit);
+  if (full_n && beta != 0.0f) {
+    // Software pipeline: the old values of chunk c + 1 are fetched while chunk c is stored (a chunk's 32 loads would
+    // otherwise expose one L2 / HBM round trip per chunk, 4-8 in a row: the store pass is latency-, not bandwidth-bound).
+    // (no per-lane control flow around the warp-collective tcgen05.ld: row_ok only predicates the global accesses)
+    float old[32];
+    if (row_ok) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) old[i] = crow[static_cast<size_t>(n0 + c_begin * 32 + i) * ldc];
+    }
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; ++c) {
+      uint32_t v[32];
+      __syncwarp();
+      ptx::tmem_ld_x32(taddr + c * 32, v);
+      ptx::tmem_wait_ld();
+      const int nb = n0 + c * 32;
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = f2u(alpha * u2f(v[i]) + beta * old[i]);
+        if (c + 1 < c_end) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) old[i] = crow[static_cast<size_t>(nb + 32 + i) * ldc];
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) crow[static_cast<size_t>(nb + i) * ldc] = u2f(v[i]);
+      }
+    }
+    return;
+  }
 #pragma unroll 1
   for (int c = c_begin; c < c_end; ++c) {
     uint32_t v[32];
@@ -312,16 +341,8 @@ __device__ __forceinline__ void store_tile(uint32_t taddr, float *crow, bool row
     const int nb = n0 + c * 32;
     if (!row_ok) continue;
     if (full_n) {
-      if (beta == 0.0f) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) crow[static_cast<size_t>(nb + i) * ldc] = alpha * u2f(v[i]);
-      } else {
-        float old[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) old[i] = crow[static_cast<size_t>(nb + i) * ldc];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) crow[static_cast<size_t>(nb + i) * ldc] = alpha * u2f(v[i]) + beta * old[i];
-      }
+      for (int i = 0; i < 32; ++i) crow[static_cast<size_t>(nb + i) * ldc] = alpha * u2f(v[i]);
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -340,21 +361,47 @@ __device__ __forceinline__ void store_tile(uint32_t taddr, float *crow, bool row
 // (or -1) and its corrected value.  q = TMEM lane quadrant of this warp, m = global row of this lane.
 // ------------------------------------------------------------------------------------------------------------
 // The per-row sums of one chunk range of the accumulator (pass 1 of the check; also run by the assisting helper warp).
+// Tensor-memory reads are the bound of this pass (64 B/clk per SM: 128 KiB of accumulator = ~1 us), so the next chunk's
+// tcgen05.ld is in flight while this one is summed, and the sums run as two independent chains per quantity.
+//   s2 = sum_j (j + 1) acc[j]  is formed per chunk as  (32 c + 1) * sum_i f_i + sum_i i * f_i   (i: compile-time weights)
+__device__ __forceinline__ void abft_chunk_sums(const uint32_t (&v)[32], int c, float &s1, float &s2, float &sabs) {
+  float a0 = 0.0f, a1 = 0.0f, t0 = 0.0f, t1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    const float f0 = u2f(v[i]), f1 = u2f(v[i + 1]);
+    a0 += f0;
+    a1 += f1;
+    t0 = fmaf(f0, static_cast<float>(i), t0);
+    t1 = fmaf(f1, static_cast<float>(i + 1), t1);
+    b0 += fabsf(f0);
+    b1 += fabsf(f1);
+  }
+  const float sc = a0 + a1;
+  s1 += sc;
+  s2 += fmaf(static_cast<float>(c * 32 + 1), sc, t0 + t1);
+  sabs += b0 + b1;
+}
 template <int BN>
 __device__ __forceinline__ void abft_row_sums(uint32_t taddr, int c_begin, int c_end, float &s1, float &s2, float &sabs) {
+  if (c_begin >= c_end) return;
+  uint32_t va[32], vb[32];
+  ptx::tmem_ld_x32(taddr + c_begin * 32, va);
+  int c = c_begin;
 #pragma unroll 1
-  for (int c = c_begin; c < c_end; ++c) {
-    uint32_t v[32];
-    ptx::tmem_ld_x32(taddr + c * 32, v);
+  while (true) {
     ptx::tmem_wait_ld();
-    const float wbase = static_cast<float>(c * 32 + 1);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float f = u2f(v[i]);
-      s1 += f;
-      s2 = fmaf(f, wbase + static_cast<float>(i), s2);
-      sabs += fabsf(f);
-    }
+    ptx::tmem_ld_landed(va);
+    const bool more_b = c + 1 < c_end;  // (warp-uniform)
+    if (more_b) ptx::tmem_ld_x32(taddr + (c + 1) * 32, vb);
+    abft_chunk_sums(va, c, s1, s2, sabs);
+    if (!more_b) break;
+    ptx::tmem_wait_ld();
+    ptx::tmem_ld_landed(vb);
+    const bool more_a = c + 2 < c_end;
+    if (more_a) ptx::tmem_ld_x32(taddr + (c + 2) * 32, va);
+    abft_chunk_sums(vb, c + 1, s1, s2, sabs);
+    if (!more_a) break;
+    c += 2;
   }
 }
 
@@ -901,8 +948,8 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (FT && p.enc_front) {
     // front-phase ENCODE of B (see KernelParams::enc_front): the same routine as the pre-pass kernel
-    encode_b_warp<BN, 8>(p.B, p.N, p.K, p.ldb, p.enc_out, p.enc_ld, 0, p.tiles_n, static_cast<int>(blockIdx.x) * (kThreads / 32) + warp,
-                         static_cast<int>(gridDim.x) * (kThreads / 32), lane);
+    const int gw = static_cast<int>(blockIdx.x) * (kThreads / 32) + warp, nw = static_cast<int>(gridDim.x) * (kThreads / 32);
+    encode_b_warp<BN, 8>(p.B, p.N, p.K, p.ldb, p.enc_out, p.enc_ld, 0, p.tiles_n, gw, nw, lane);
     __syncwarp();  // the warp's stores are ordered before lane 0's release (cumulativity)
     if (lane == 0) {
       ptx::fence_acq_rel_gpu();
