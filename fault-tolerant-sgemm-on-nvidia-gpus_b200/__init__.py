@@ -54,7 +54,7 @@ class Opts(C.Structure):
                 ("n_faults", C.c_int), ("faults", Fault * MAX_FAULTS), ("tau_abs", C.c_float),
                 ("tau_rel", C.c_float), ("detect_only", C.c_int), ("reuse_b_checksums", C.c_int),
                 ("baseline_host_sync", C.c_int), ("precision", C.c_int), ("check_segments", C.c_int),
-                ("no_recompute", C.c_int)]
+                ("no_recompute", C.c_int), ("protect_epilogue", C.c_int)]
 
 
 class Event(C.Structure):
@@ -66,11 +66,12 @@ class Stats(C.Structure):
     _fields_ = [("tiles", C.c_ulonglong), ("rows_checked", C.c_ulonglong), ("detected", C.c_ulonglong),
                 ("corrected", C.c_ulonglong), ("uncorrectable", C.c_ulonglong), ("checksum_faults", C.c_ulonglong),
                 ("max_abs_residual", C.c_float), ("max_rel_residual", C.c_float), ("n_events", C.c_int),
-                ("events", Event * MAX_EVENTS), ("recomputed", C.c_ulonglong)]
+                ("events", Event * MAX_EVENTS), ("recomputed", C.c_ulonglong),
+                ("epilogue_faults", C.c_ulonglong)]
 
     def as_dict(self):
         return {"tiles": self.tiles, "rows_checked": self.rows_checked, "detected": self.detected,
-                "corrected": self.corrected, "uncorrectable": self.uncorrectable, "recomputed": self.recomputed,
+                "corrected": self.corrected, "uncorrectable": self.uncorrectable, "recomputed": self.recomputed, "epilogue_faults": self.epilogue_faults,
                 "checksum_faults": self.checksum_faults, "max_abs_residual": self.max_abs_residual,
                 "max_rel_residual": self.max_rel_residual,
                 "events": [{"row": e.row, "col": e.col, "residual": e.residual,
@@ -167,9 +168,11 @@ def default_opts() -> Opts:
 
 
 def make_opts(stream=None, selftest=None, faults=None, tau_abs=0.0, tau_rel=0.0, detect_only=False,
-              reuse_b_checksums=False, baseline_host_sync=True, no_recompute=False, precision=0, check_segments=0) -> Opts:
+              reuse_b_checksums=False, baseline_host_sync=True, no_recompute=False, precision=0, check_segments=0,
+              protect_epilogue=False) -> Opts:
     """selftest: None | (value, tile_row, tile_col)  -> the reference's always-on injector (ft_sgemm_huge.cuh:324-327)
-    faults: list of dicts {row, col, add=float} or {row, col, xor=int}"""
+    faults: list of dicts {row, col, add=float} or {row, col, xor=int}; with xor, where="epilogue_tmem" | "epilogue_value"
+    places the upset after the accumulator check (ftsgemm_fault.mode 2 / 3)"""
     o = default_opts()
     o.stream = stream
     if selftest is not None:
@@ -182,7 +185,7 @@ def make_opts(stream=None, selftest=None, faults=None, tau_abs=0.0, tau_rel=0.0,
         for i, f in enumerate(faults):
             o.faults[i].row, o.faults[i].col = int(f["row"]), int(f["col"])
             if "xor" in f:
-                o.faults[i].mode, o.faults[i].xor_mask = 1, int(f["xor"]) & 0xFFFFFFFF
+                o.faults[i].mode, o.faults[i].xor_mask = {"acc": 1, "epilogue_tmem": 2, "epilogue_value": 3}[f.get("where", "acc")], int(f["xor"]) & 0xFFFFFFFF
             else:
                 o.faults[i].mode, o.faults[i].add_value = 0, float(f["add"])
     o.tau_abs, o.tau_rel = float(tau_abs), float(tau_rel)
@@ -192,6 +195,7 @@ def make_opts(stream=None, selftest=None, faults=None, tau_abs=0.0, tau_rel=0.0,
     o.no_recompute = int(no_recompute)
     o.precision = int(precision)  # 0 = single-pass TF32, 1 = 3xTF32 (FP32-grade)
     o.check_segments = int(check_segments)  # > 1: intra-K checking (K-segments verified one after the other)
+    o.protect_epilogue = int(protect_epilogue)
     return o
 
 

@@ -244,16 +244,16 @@ int make_tmap_3d(ftsgemm_handle_t h, CUtensorMap *tm, const float *base, uint64_
 // persistent kernel's inter-CTA waits (checksum flags, parked accumulators, wave counters) are only deadlock-free for
 // such a grid, so the planner never gets more units than this -- on a device partition (MPS active-thread percentage,
 // green context) that is fewer than multiProcessorCount / CG.  Cached per handle (= per device).
-template <int BN, bool FT, int CG>
+template <int BN, bool FT, int CG, bool PROT = false>
 int query_max_units(ftsgemm_handle_t h, int *out) {
   using Cfg = TileCfg<BN, FT, CG>;
-  const int key = BN * 8 + (FT ? 4 : 0) + CG;
+  const int key = BN * 16 + (PROT ? 8 : 0) + (FT ? 4 : 0) + CG;
   auto it = h->max_units.find(key);
   if (it != h->max_units.end()) {
     *out = it->second;
     return FTSGEMM_OK;
   }
-  auto kern = ftsgemm_tc_kernel<BN, FT, CG>;
+  auto kern = ftsgemm_tc_kernel<BN, FT, CG, PROT>;
   FT_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   int units = 0;
   if (CG > 1) {
@@ -281,14 +281,14 @@ int query_max_units(ftsgemm_handle_t h, int *out) {
   return FTSGEMM_OK;
 }
 
-template <int BN, bool FT, int CG>
+template <int BN, bool FT, int CG, bool PROT = false>
 int launch_tc(ftsgemm_handle_t h, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC,
               const KernelParams &p, int units, cudaStream_t stream) {
   // p.pdl_wait: the launch may overlap the tail of its predecessor in the stream (KernelParams::pdl_wait)
   using Cfg = TileCfg<BN, FT, CG>;
-  auto kern = ftsgemm_tc_kernel<BN, FT, CG>;
+  auto kern = ftsgemm_tc_kernel<BN, FT, CG, PROT>;
   int resident = 0;
-  const int qrc = query_max_units<BN, FT, CG>(h, &resident);  // (also sets the shared-memory attribute, once per handle)
+  const int qrc = query_max_units<BN, FT, CG, PROT>(h, &resident);  // (also sets the shared-memory attribute, once per handle)
   if (qrc) return qrc;
   if (units > resident) return FTSGEMM_ERR_UNSUPPORTED;  // the plan was built for more units than can be co-resident
   cudaLaunchConfig_t cfg;
@@ -757,8 +757,9 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
   int lrc = FTSGEMM_ERR_UNSUPPORTED;
 #define FT_DISPATCH(bn, cg)                                                          \
   if (BN == bn && CG == cg)                                                          \
-    lrc = ft ? launch_tc<bn, true, cg>(h, tmA, tmB, tmC, p, units, stream)           \
-             : launch_tc<bn, false, cg>(h, tmA, tmB, tmC, p, units, stream);
+    lrc = !ft ? launch_tc<bn, false, cg>(h, tmA, tmB, tmC, p, units, stream)         \
+              : (o.protect_epilogue ? launch_tc<bn, true, cg, true>(h, tmA, tmB, tmC, p, units, stream) \
+                                    : launch_tc<bn, true, cg>(h, tmA, tmB, tmC, p, units, stream));
   FT_DISPATCH(32, 1)
   FT_DISPATCH(64, 1)
   FT_DISPATCH(128, 1)
@@ -1033,7 +1034,7 @@ static int load_opts(const ftsgemm_opts *opts, ftsgemm_opts *o) {
   if (opts->struct_size < FTSGEMM_OPTS_V1_SIZE) return FTSGEMM_ERR_INVALID_ARG;
   memcpy(o, opts, opts->struct_size < sizeof(*o) ? opts->struct_size : sizeof(*o));
   o->struct_size = sizeof(*o);
-  if (o->check_segments < 0 || o->check_segments > 4096 || o->precision < 0 || o->precision > 1 || o->inject_mode < 0 || o->inject_mode > 2 || o->selftest_row < 0 || o->selftest_col < 0 || o->n_faults < 0 ||
+  if (o->check_segments < 0 || o->check_segments > 4096 || o->precision < 0 || o->precision > 1 || o->inject_mode < 0 || o->inject_mode > 2 || o->protect_epilogue < 0 || o->protect_epilogue > 1 || o->selftest_row < 0 || o->selftest_col < 0 || o->n_faults < 0 ||
       o->n_faults > FTSGEMM_MAX_FAULTS)
     return FTSGEMM_ERR_INVALID_ARG;
   return FTSGEMM_OK;
@@ -1128,6 +1129,7 @@ int ftsgemm_get_stats(ftsgemm_handle_t h, ftsgemm_stats *out) {
   out->uncorrectable = ds.uncorrectable;
   out->checksum_faults = ds.checksum_faults;
   out->recomputed = ds.recomputed;
+  out->epilogue_faults = ds.epilogue_faults;
   memcpy(&out->max_abs_residual, &ds.max_abs_bits, 4);
   memcpy(&out->max_rel_residual, &ds.max_rel_bits, 4);
   out->n_events = ds.n_events < FTSGEMM_MAX_EVENTS ? ds.n_events : FTSGEMM_MAX_EVENTS;

@@ -68,6 +68,7 @@ struct DeviceStats {
   int n_events;
   DeviceEvent events[kMaxEvents];
   unsigned long long recomputed;  // rows that were detected but not cleanly correctable and were recomputed on CUDA cores
+  unsigned long long epilogue_faults;  // row segments whose store pass failed its check (protect_epilogue)
 };
 
 struct KernelParams {
@@ -451,7 +452,7 @@ __device__ __forceinline__ void try_prefetch_expected(const KernelParams &p, int
 template <int BN>
 __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr, int q, int lane, int m, int m0_cta,
                                            int n0, int n_blk, int &fix_col, float &fix_val, bool &redo, ExpectedChk &xp,
-                                           int c_mid = BN / 32, uint32_t xchg = 0u, int pair_bar = 0) {
+                                           float &own_s1, int c_mid = BN / 32, uint32_t xchg = 0u, int pair_bar = 0) {
   // ---- fault injection into the TMEM accumulator (reference: ft_sgemm_huge.cuh:324-327) ----
   if (p.inject_mode == 1) {
     if ((p.selftest_row >> 5) == q && p.selftest_col < BN) {
@@ -464,7 +465,7 @@ __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr
   } else if (p.inject_mode == 2) {
     for (int f = 0; f < p.n_faults; ++f) {
       const int tr = p.faults[f].row - m0_cta, tc = p.faults[f].col - n0;
-      if (tr >= 0 && tr < kBM && tc >= 0 && tc < BN && (tr >> 5) == q) {  // warp-uniform
+      if (p.faults[f].mode <= 1 && tr >= 0 && tr < kBM && tc >= 0 && tc < BN && (tr >> 5) == q) {  // warp-uniform
         uint32_t x = ptx::tmem_ld_x1(taddr + tc);
         ptx::tmem_wait_ld();
         if (lane == (tr & 31))
@@ -482,6 +483,7 @@ __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr
   // ---- pass 1: actual row checksums (thread-local: lane == row) ----
   float s1 = 0.0f, s2 = 0.0f, sabs = 0.0f;
   abft_row_sums<BN>(taddr, 0, c_mid, s1, s2, sabs);
+  own_s1 = s1;  // (this warp's columns only: what a protected store pass re-derives)
   if (assisted) {
     ptx::named_bar_sync(pair_bar, 64);  // the helper's partial sums are in shared memory
     s1 += ptx::ld_shared_f1(xchg + lane * 12);
@@ -624,6 +626,80 @@ __device__ __forceinline__ void abft_check(const KernelParams &p, uint32_t taddr
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Protected store pass (opts.protect_epilogue; the reference's epilogue, ft_sgemm_huge.cuh:573-690, is unprotected, and so
+// is the window between its last accumulator check and the store).  The warp re-derives, from the accumulator values it
+// re-reads, the row sum the ABFT check verified -- same association, so any difference in the bits is an upset of tensor
+// memory or of the read path after the check -- and sums what it stores: sum(out) must equal alpha * sum(acc) + beta *
+// sum(old) within the rounding of n_cols fused multiply-adds (2 * 128 * 2^-24 of the magnitudes).  Returns true in the
+// lanes (= rows) whose segment failed.  bad_col / bad_mask: test injector (ftsgemm_fault.mode 3), -1 = none.
+// ------------------------------------------------------------------------------------------------------------
+struct StoreVerdict {
+  float resid;
+  bool bad;
+};
+template <int BN>
+__device__ __forceinline__ StoreVerdict store_tile_protected(uint32_t taddr, float *crow, bool row_ok, int n0, int ldc, float alpha,
+                                                          float beta, int c_begin, int c_end, float chk_s1, bool chk_s1_valid,
+                                                          int bad_col, uint32_t bad_mask) {
+  float s1 = 0.0f, s2 = 0.0f, sabs = 0.0f, so0 = 0.0f, so1 = 0.0f, sold0 = 0.0f, sold1 = 0.0f, aold0 = 0.0f, aold1 = 0.0f;
+  const bool rmw = beta != 0.0f;
+  float old[32];
+  if (row_ok && rmw) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) old[i] = crow[static_cast<size_t>(n0 + c_begin * 32 + i) * ldc];
+  }
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; ++c) {
+    uint32_t v[32];
+    __syncwarp();
+    ptx::tmem_ld_x32(taddr + c * 32, v);
+    ptx::tmem_wait_ld();
+    abft_chunk_sums(v, c, s1, s2, sabs);
+    const int nb = n0 + c * 32;
+    if (row_ok) {
+      if (rmw) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          sold0 += old[i];
+          sold1 += old[i + 1];
+          aold0 += fabsf(old[i]);
+          aold1 += fabsf(old[i + 1]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = f2u(alpha * u2f(v[i]) + beta * old[i]);
+        if (c + 1 < c_end) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) old[i] = crow[static_cast<size_t>(nb + 32 + i) * ldc];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = f2u(alpha * u2f(v[i]));
+      }
+      if (bad_col >= c * 32 && bad_col < c * 32 + 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i == bad_col) v[i] ^= bad_mask;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        so0 += u2f(v[i]);
+        so1 += u2f(v[i + 1]);
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) crow[static_cast<size_t>(nb + i) * ldc] = u2f(v[i]);
+    }
+  }
+  const float ref = alpha * s1 + beta * (sold0 + sold1);
+  const float tol = 1.6e-5f * (fabsf(alpha) * sabs + fabsf(beta) * (aold0 + aold1)) + 1e-30f;
+  StoreVerdict out;
+  out.resid = (so0 + so1) - ref;
+  const bool reread_differs = chk_s1_valid && f2u(s1) != f2u(chk_s1);
+  // (a non-finite reference -- Inf / NaN already in the old C -- cannot be verified and is not an upset)
+  out.bad = row_ok && (reread_differs || (isfinite(ref) && !(fabsf(out.resid) <= tol)));
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Recompute fallback (rare): one warp recomputes row m of the tile's BN columns from global memory -- the values the
 // tensor core would have produced up to FP32 accumulation order (TF32-truncated operands: every product is exact in
 // FP32) -- and writes C = alpha * acc + beta * C directly.  K iterations of 1 broadcast + BN/32 coalesced loads.
@@ -657,6 +733,76 @@ __device__ __noinline__ void recompute_row(const float *A, const float *B, float
       *dst = alpha * acc[j] + o;
     }
   }
+}
+
+// The whole protected store pass of one warp, out of line and with scalars by value: an opt-in path must not cost the
+// common epilogue registers (inlined it pushed the kernel into spills), and a reference to the __grid_constant__ parameter
+// block would force a local copy of all of it.  Row segments that fail are counted and, with beta == 0, recomputed from A
+// and B (with beta != 0 the old values of C are already overwritten: reported as uncorrectable).
+template <int BN>
+__device__ __noinline__ void protected_store_pass(uint32_t taddr, const float *A, const float *B, float *C, int lda, int ldb, int ldc,
+                                                  int N, int K, float alpha, float beta, DeviceStats *stats, bool can_recompute,
+                                                  int m, int row0, bool row_ok, int n0, int c_begin, int c_end, float chk_s1,
+                                                  bool chk_s1_valid, int bad_col, uint32_t bad_mask, int lane) {
+  const StoreVerdict sv = store_tile_protected<BN>(taddr, C + m, row_ok, n0, ldc, alpha, beta, c_begin, c_end, chk_s1, chk_s1_valid,
+                                                   bad_col, bad_mask);
+  unsigned mask = __ballot_sync(0xffffffffu, sv.bad);
+  if (mask == 0u) return;
+  const bool can_fix = beta == 0.0f && can_recompute;
+  if (sv.bad && stats) {
+    atomicAdd(&stats->epilogue_faults, 1ull);
+    atomicAdd(can_fix ? &stats->recomputed : &stats->uncorrectable, 1ull);
+    const int slot = atomicAdd(&stats->n_events, 1);
+    if (slot < kMaxEvents) {
+      DeviceEvent ev;
+      ev.row = m;
+      ev.col = -1;
+      ev.residual = sv.resid;
+      ev.corrected_value = 0.0f;
+      ev.status = can_fix ? 6 : 7;
+      stats->events[slot] = ev;
+    }
+  }
+  if (!can_fix) return;
+  while (mask != 0u) {
+    const int r = __ffs(mask) - 1;
+    mask &= mask - 1u;
+    if (c_end - c_begin == BN / 32) {
+      recompute_row<BN>(A, B, C, lda, ldb, ldc, N, K, alpha, beta, row0 + r, n0, lane);
+    } else {
+      if constexpr (BN >= 64) recompute_row<BN / 2>(A, B, C, lda, ldb, ldc, N, K, alpha, beta, row0 + r, n0 + c_begin * 32, lane);
+    }
+  }
+}
+
+// Test injectors for upsets AFTER the accumulator check (ftsgemm_fault.mode 2: into tensor memory before the store pass
+// re-reads it; mode 3: into the value about to be stored -- returns the tile column for this lane, -1 if none).
+template <int BN>
+__device__ __forceinline__ void inject_after_check(const KernelParams &p, uint32_t taddr, int q, int lane, int m0_cta, int n0) {
+  for (int f = 0; f < p.n_faults; ++f) {
+    const int tr = p.faults[f].row - m0_cta, tc = p.faults[f].col - n0;
+    if (p.faults[f].mode == 2 && tr >= 0 && tr < kBM && tc >= 0 && tc < BN && (tr >> 5) == q) {  // warp-uniform
+      uint32_t x = ptx::tmem_ld_x1(taddr + tc);
+      ptx::tmem_wait_ld();
+      if (lane == (tr & 31)) x ^= p.faults[f].xor_mask;
+      ptx::tmem_st_x1(taddr + tc, x);
+      ptx::tmem_wait_st();
+    }
+  }
+}
+template <int BN>
+__device__ __forceinline__ int stored_value_fault(const KernelParams &p, int q, int lane, int m0_cta, int n0, int c_begin, int c_end,
+                                                  uint32_t &mask) {
+  int col = -1;
+  if (p.inject_mode == 2)
+    for (int f = 0; f < p.n_faults; ++f) {
+      const int tr = p.faults[f].row - m0_cta, tc = p.faults[f].col - n0;
+      if (p.faults[f].mode == 3 && tr >= 0 && tr < kBM && (tr >> 5) == q && lane == (tr & 31) && tc >= c_begin * 32 && tc < c_end * 32) {
+        col = tc;
+        mask = p.faults[f].xor_mask;
+      }
+    }
+  return col;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -871,7 +1017,9 @@ __device__ __forceinline__ void encode_b_warp(const float *__restrict__ B, int N
 // ------------------------------------------------------------------------------------------------------------
 // The kernel.
 // ------------------------------------------------------------------------------------------------------------
-template <int BN, bool FT, int CG>
+// PROT: the instantiation with the protected store pass (opts.protect_epilogue) -- a separate binary, because the common
+// kernel sits exactly at the 168-register limit of a 384-thread CTA and every extra live value of an opt-in path spilled.
+template <int BN, bool FT, int CG, bool PROT = false>
 __global__ void __launch_bounds__(kThreads, 1)
 ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmChk, const KernelParams p) {
@@ -1333,17 +1481,23 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int fix_col = -1;
         float fix_val = 0.0f;
         bool redo = false;
+        float own_s1 = 0.0f;
         if (FT && !(p.dbg_flags & 1))
-          abft_check<BN>(p, taddr, q, lane, m, m0_cta, n0, tc.n_blk, fix_col, fix_val, redo, xp, c_mid, xchg_base(q), 4 + q);
+          abft_check<BN>(p, taddr, q, lane, m, m0_cta, n0, tc.n_blk, fix_col, fix_val, redo, xp, own_s1, c_mid, xchg_base(q), 4 + q);
         // rows to recompute are skipped by both store passes (the helper reads the mask after the pair barrier below)
         const unsigned redo_mask = FT ? __ballot_sync(0xffffffffu, redo) : 0u;
-        if (FT && assist && !(p.dbg_flags & 1) && lane == 0) ptx::st_shared_u32(xchg_base(q), redo_mask);
+        // rows repaired in tensor memory: the sums of pass 1 no longer describe what a protected store pass re-reads
+        const unsigned stale_mask = FT ? __ballot_sync(0xffffffffu, fix_col >= 0) : 0u;
+        if (FT && assist && !(p.dbg_flags & 1) && lane == 0) {
+          ptx::st_shared_u32(xchg_base(q), redo_mask);
+          if constexpr (PROT) ptx::st_shared_u32(xchg_base(q) + 4, stale_mask);
+        }
         if (tracer) trace_put(p, unit, item_idx, 5, globaltimer_ns());
         if (FT) {
           // rare: write the recomputed elements back into the accumulator (one lane = one row at a time, like the
           // injection path), so that the store pass stays free of per-element patching (a dynamically indexed patch of the
           // register tile had pushed it into local memory: 6.6 us instead of 3.6 us per tile)
-          unsigned fix_mask = __ballot_sync(0xffffffffu, fix_col >= 0);
+          unsigned fix_mask = stale_mask;
           while (fix_mask != 0u) {
             const int src = __ffs(fix_mask) - 1;
             fix_mask &= fix_mask - 1u;
@@ -1355,12 +1509,21 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ptx::tmem_st_x1(taddr + col, x);
             ptx::tmem_wait_st();
           }
+          if (p.inject_mode == 2) inject_after_check<BN>(p, taddr, q, lane, m0_cta, n0);
         }
         if (assist && FT && !(p.dbg_flags & 1)) {  // corrections are in tensor memory: the helper may store its half
           ptx::tc_fence_before();
           ptx::named_bar_sync(4 + q, 64);
         }
-        store_tile<BN>(taddr, p.C + m, m < p.M && !redo, n0, p.N, p.ldc, p.alpha, p.beta, 0, c_mid);
+        if (PROT && FT && !(p.dbg_flags & 1) && n0 + BN <= p.N) {
+          uint32_t bad_bits = 0u;
+          const int bad_col = stored_value_fault<BN>(p, q, lane, m0_cta, n0, 0, c_mid, bad_bits);
+          protected_store_pass<BN>(taddr, p.A, p.B, p.C, p.lda, p.ldb, p.ldc, p.N, p.K, p.alpha, p.beta, p.stats,
+                                   p.recompute != 0 && p.detect_only == 0, m, m0_cta + q * 32, m < p.M && !redo, n0, 0, c_mid, own_s1,
+                                   ((stale_mask >> lane) & 1u) == 0u, bad_col, bad_bits, lane);
+        } else {
+          store_tile<BN>(taddr, p.C + m, m < p.M && !redo, n0, p.N, p.ldc, p.alpha, p.beta, 0, c_mid);
+        }
         if (FT && redo_mask != 0u) {  // rare, warp-uniform: recompute the flagged rows from global memory
           unsigned rm = redo_mask;
           while (rm != 0u) {
@@ -1415,13 +1578,13 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a_acc * BN;
         const int m0_cta = (tc.m_blk * CG + static_cast<int>(cta_rank)) * kBM;
         const int m = m0_cta + row;
-        uint32_t skip = 0u;
+        uint32_t skip = 0u, stale = 0u;
+        float s1 = 0.0f, s2 = 0.0f, sabs = 0.0f;
         if (FT && !(p.dbg_flags & 1)) {
           if (p.inject_mode != 0) {
             ptx::named_bar_sync(4 + q, 64);  // injected
             ptx::tc_fence_after();
           }
-          float s1 = 0.0f, s2 = 0.0f, sabs = 0.0f;
           abft_row_sums<BN>(taddr, kMid, BN / 32, s1, s2, sabs);
           ptx::st_shared_u32(xchg_base(q) + lane * 12, f2u(s1));
           ptx::st_shared_u32(xchg_base(q) + lane * 12 + 4, f2u(s2));
@@ -1430,8 +1593,18 @@ ftsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           ptx::named_bar_sync(4 + q, 64);  // verdict reached, corrections written to tensor memory
           ptx::tc_fence_after();
           skip = (ptx::ld_acquire_shared_u32(xchg_base(q)) >> lane) & 1u;  // rows the epilogue warp recomputes
+          if constexpr (PROT) stale = (ptx::ld_acquire_shared_u32(xchg_base(q) + 4) >> lane) & 1u;  // rows it repaired in tensor memory
         }
-        store_tile<BN>(taddr, p.C + m, m < p.M && !skip, tc.n_blk * BN, p.N, p.ldc, p.alpha, p.beta, kMid, BN / 32);
+        const int n0 = tc.n_blk * BN;
+        if (PROT && FT && !(p.dbg_flags & 1) && n0 + BN <= p.N) {
+          uint32_t bad_bits = 0u;
+          const int bad_col = stored_value_fault<BN>(p, q, lane, m0_cta, n0, kMid, BN / 32, bad_bits);
+          protected_store_pass<BN>(taddr, p.A, p.B, p.C, p.lda, p.ldb, p.ldc, p.N, p.K, p.alpha, p.beta, p.stats,
+                                   p.recompute != 0 && p.detect_only == 0, m, m0_cta + q * 32, m < p.M && !skip, n0, kMid, BN / 32, s1,
+                                   stale == 0u, bad_col, bad_bits, lane);
+        } else {
+          store_tile<BN>(taddr, p.C + m, m < p.M && !skip, n0, p.N, p.ldc, p.alpha, p.beta, kMid, BN / 32);
+        }
         ptx::tc_fence_before();
         ptx::named_bar_sync(4 + q, 64);  // both halves are out of tensor memory
       };

@@ -80,7 +80,10 @@ typedef struct ftsgemm_kernel_info {
  * (generalises the reference's always-on injector, ft_sgemm_huge.cuh:49-51,324-327). */
 typedef struct ftsgemm_fault {
   int row, col;          /* global element (m, n) of C */
-  int mode;              /* 0: acc += add_value      1: acc bits ^= xor_mask (single/multi bit flip) */
+  int mode;              /* 0: acc += add_value      1: acc bits ^= xor_mask (single/multi bit flip)
+                          * epilogue upsets (what opts.protect_epilogue detects; the accumulator check has already passed):
+                          * 2: acc bits ^= xor_mask in tensor memory AFTER the check, before the store pass re-reads it
+                          * 3: the value alpha*acc + beta*c about to be stored has its bits ^= xor_mask */
   float add_value;
   uint32_t xor_mask;
 } ftsgemm_fault;
@@ -122,6 +125,16 @@ typedef struct ftsgemm_opts {
                             small to locate, two upsets in one row) is RECOMPUTED from A and B on CUDA cores and counted
                             in stats.recomputed -- nothing detected is stored as computed; 1: leave such rows as computed
                             and count them in stats.uncorrectable (round-1 behaviour) */
+  int protect_epilogue;  /* 1: the store pass is checked as well (the reference's epilogue c = alpha*res + beta*c,
+                            ft_sgemm_huge.cuh:573-690, is unprotected -- and so is the window between the accumulator check
+                            and the store): every warp re-sums the accumulator values it re-reads (must equal, bit for bit,
+                            the sums the check verified) and sums what it stores (must equal alpha * that + beta * sum of the
+                            old values within rounding).  A row segment that fails is counted in stats.epilogue_faults
+                            and, when beta == 0, recomputed from A and B; with beta != 0 the old values are gone: it is
+                            counted in stats.uncorrectable.  Tiles that are ragged in N are not covered; Inf / NaN already in the old C are
+                            not verifiable and not flagged.  A separate kernel instantiation (the default one has no register to
+                            spare); measured cost, id 31: +6 % at 8192^3, +18 % at 4096^3, +52 % at 2048^3
+                            (profiles/r02_protect_epilogue_cost.jsonl). */
 } ftsgemm_opts;
 /* sizeof(ftsgemm_opts) of ABI version 1: the smallest struct_size the library accepts (a zero-initialised struct is
  * rejected with FTSGEMM_ERR_INVALID_ARG instead of silently meaning "all defaults on the default stream"). */
@@ -132,7 +145,7 @@ typedef struct ftsgemm_event {
   float residual;        /* expected - actual row checksum */
   float corrected_value; /* accumulator value after correction */
   int status;            /* 1 corrected, 2 detected only (detect_only), 3 uncorrectable, 4 checksum-column fault,
-                            5 row recomputed */
+                            5 row recomputed, 6 epilogue fault (row segment recomputed), 7 epilogue fault left in C (beta != 0) */
 } ftsgemm_event;
 
 typedef struct ftsgemm_stats {
@@ -149,6 +162,7 @@ typedef struct ftsgemm_stats {
   ftsgemm_event events[FTSGEMM_MAX_EVENTS];
   /* ---- ABI version 2 ---- */
   unsigned long long recomputed;   /* rows detected but not correctable from the checksums, recomputed on CUDA cores */
+  unsigned long long epilogue_faults; /* row segments whose store pass failed its check (opts.protect_epilogue) */
 } ftsgemm_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------- */

@@ -31,9 +31,9 @@ IDS = {1: "128x64 plain cg1 (small)", 2: "256x64 plain cg2 (medium)", 3: "256x12
 
 
 def demangle(name):
-    m = re.search(r"ftsgemm_tc_kernelILi(\d+)ELb(\d)ELi(\d)", name)
+    m = re.search(r"ftsgemm_tc_kernelILi(\d+)ELb(\d)ELi(\d)ELb(\d)", name)
     if m:
-        return f"ftsgemm_tc_kernel_{m.group(1)}_{'ft' if m.group(2) == '1' else 'plain'}_cg{m.group(3)}"
+        return f"ftsgemm_tc_kernel_{m.group(1)}_{'ft' if m.group(2) == '1' else 'plain'}_cg{m.group(3)}{'_prot' if m.group(4) == '1' else ''}"
     m = re.search(r"encode_b_kernelILi(\d+)ELi(\d+)ELb(\d)", name)
     if m:
         return f"encode_b_kernel_{m.group(1)}_kr{m.group(2)}{'_stream' if m.group(3) == '1' else ''}"

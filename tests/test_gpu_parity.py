@@ -484,6 +484,56 @@ def test_two_faults_in_one_row_are_recomputed(cuda, ft, dev):
         assert np.abs(got2 - clean).max() > 10.0  # (left as computed)
 
 
+def test_protected_epilogue(cuda, ft, dev):
+    """opts.protect_epilogue (the reference's epilogue, ft_sgemm_huge.cuh:573-690, and the window between its last check and
+    the store are unprotected): the store pass re-derives the verified row sums from what it re-reads out of tensor memory
+    and checks the sum of what it stores.  Fault-free: bit-identical to the unprotected kernel, nothing flagged.  An upset of
+    tensor memory AFTER the accumulator check (fault mode 2) or of the value being stored (mode 3) goes unnoticed without
+    the option, is detected with it, and with beta == 0 the row segment is recomputed."""
+    rng = np.random.default_rng(17)
+    M, N, K = 640, 1024, 352
+    A, B = _rand(rng, M * K), _rand(rng, N * K)
+    C0 = rng.standard_normal(M * N).astype(np.float32)
+    for kid in (31, 16, 15, 12, 14):
+        for (alpha, beta) in ((0.75, 0.0), (1.0, -1.5)):
+            clean = _run(cuda, dev, kid, M, N, K, A, B, C0, alpha, beta)
+            dev.stats()
+            prot = _run(cuda, dev, kid, M, N, K, A, B, C0, alpha, beta, opts=ft.make_opts(protect_epilogue=True))
+            st = dev.stats()
+            assert np.array_equal(clean, prot) and st["epilogue_faults"] == 0 and st["detected"] == 0, (kid, beta, st)
+            if beta != 0.0:  # Inf / NaN already in the old C (the reference's timing phase lets C diverge): not an upset
+                Cx = C0.copy()
+                Cx[[5, 77777, M * N - 1]] = [np.inf, np.nan, -np.inf]
+                a_ = _run(cuda, dev, kid, M, N, K, A, B, Cx, alpha, beta)
+                dev.stats()
+                b_ = _run(cuda, dev, kid, M, N, K, A, B, Cx, alpha, beta, opts=ft.make_opts(protect_epilogue=True))
+                assert np.array_equal(a_, b_, equal_nan=True) and dev.stats()["epilogue_faults"] == 0
+            # pre-check upsets are still corrected as usual in the protected kernel (a repaired row skips the bit-compare)
+            pre = [{"row": 7, "col": 33, "xor": 1 << 29}, {"row": 600, "col": 1000, "add": 50.0}]
+            got = _run(cuda, dev, kid, M, N, K, A, B, C0, alpha, beta, opts=ft.make_opts(faults=pre, protect_epilogue=True))
+            st = dev.stats()
+            assert st["detected"] == 2 and st["corrected"] == 2 and st["epilogue_faults"] == 0, (kid, beta, st)
+            assert np.abs(got - clean).max() <= 1e-4 * float(np.abs(clean).max())
+            for where, (r, c) in (("epilogue_tmem", (37, 5)), ("epilogue_tmem", (300, 900)), ("epilogue_value", (511, 130)),
+                                  ("epilogue_value", (2, 1023))):
+                f = [{"row": r, "col": c, "xor": 1 << 27, "where": where}]
+                if where == "epilogue_tmem":  # unprotected: lands in C unnoticed
+                    bad = _run(cuda, dev, kid, M, N, K, A, B, C0, alpha, beta, opts=ft.make_opts(faults=f))
+                    st = dev.stats()
+                    assert st["detected"] == 0 and st["epilogue_faults"] == 0
+                    assert bad[r + c * M] != clean[r + c * M] and np.count_nonzero(bad != clean) == 1
+                got = _run(cuda, dev, kid, M, N, K, A, B, C0, alpha, beta, opts=ft.make_opts(faults=f, protect_epilogue=True))
+                st = dev.stats()
+                assert st["epilogue_faults"] == 1 and st["detected"] == 0, (kid, beta, where, st)
+                if beta == 0.0:
+                    assert st["recomputed"] == 1 and st["uncorrectable"] == 0 and [e["status"] for e in st["events"]] == [6]
+                    assert np.abs(got - clean).max() <= 1e-4 * float(np.abs(clean).max()), (kid, where)
+                    assert set((np.flatnonzero(got != clean) % M).tolist()) <= {r}
+                else:  # the old values of C are gone: reported, not repaired
+                    assert st["recomputed"] == 0 and st["uncorrectable"] == 1 and [e["status"] for e in st["events"]] == [7]
+                    assert st["events"][0]["row"] == r
+
+
 def test_fault_campaign_floors(cuda, ft, dev):
     """BASELINE.json configs[3] in miniature at the real size (M=N=K=8192, the bench kernel id 31): single-bit flips of
     tensor-memory accumulators.  Floors: bits >= 22 (exponent, sign, top mantissa bit) detected 100 % and repaired
