@@ -129,6 +129,7 @@ int main(int argc, char **argv) {
   // optional modes of the tcgen05 engines (not in the reference's argv: environment only)
   if (getenv("FTSGEMM_PRECISION") && !strcmp(getenv("FTSGEMM_PRECISION"), "x3")) opts.precision = 1;  // 3xTF32, FP32-grade
   opts.check_segments = env_int("FTSGEMM_CHECK_SEGMENTS", 0);  // S > 1: intra-K checking, S verified K-segments
+  opts.protect_epilogue = env_int("FTSGEMM_PROTECT_EPILOGUE", 0) ? 1 : 0;  // checked store pass (stats.epilogue_faults)
 
   if (cpu_verify) {
     Chost.resize(count);
@@ -191,8 +192,8 @@ int main(int argc, char **argv) {
     if (ftsgemm_kernel_lookup(run_id, &info) == FTSGEMM_OK && info.fault_tolerant && info.engine == 1) {
       ftsgemm_stats st;
       if (ftsgemm_get_stats(h, &st) == FTSGEMM_OK)
-        fprintf(stderr, "[abft] kernel %d: tiles %llu detected %llu corrected %llu uncorrectable %llu recomputed %llu max_resid %.3e rel_fro_vs_cublas %.3e\n",
-                id, st.tiles, st.detected, st.corrected, st.uncorrectable, st.recomputed, st.max_abs_residual, rel);
+        fprintf(stderr, "[abft] kernel %d: tiles %llu detected %llu corrected %llu uncorrectable %llu recomputed %llu epilogue_faults %llu max_resid %.3e rel_fro_vs_cublas %.3e\n",
+                id, st.tiles, st.detected, st.corrected, st.uncorrectable, st.recomputed, st.epilogue_faults, st.max_abs_residual, rel);
     }
     if (cpu_verify) {
       CUDA_OR_DIE(cudaMemcpy(Cm.data(), dC, count * sizeof(float), cudaMemcpyDeviceToHost));
