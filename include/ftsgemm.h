@@ -83,7 +83,8 @@ typedef struct ftsgemm_fault {
   int mode;              /* 0: acc += add_value      1: acc bits ^= xor_mask (single/multi bit flip)
                           * epilogue upsets (what opts.protect_epilogue detects; the accumulator check has already passed):
                           * 2: acc bits ^= xor_mask in tensor memory AFTER the check, before the store pass re-reads it
-                          * 3: the value alpha*acc + beta*c about to be stored has its bits ^= xor_mask */
+                          * 3: the value alpha*acc + beta*c about to be stored has its bits ^= xor_mask (injected by the
+                          *    protected store pass only: ignored without opts.protect_epilogue) */
   float add_value;
   uint32_t xor_mask;
 } ftsgemm_fault;
