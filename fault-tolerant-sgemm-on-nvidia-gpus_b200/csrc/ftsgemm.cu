@@ -257,8 +257,7 @@ int query_max_units(ftsgemm_handle_t h, int *out) {
   FT_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   int units = 0;
   if (CG > 1) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(h->num_sms / CG * CG);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
@@ -291,8 +290,7 @@ int launch_tc(ftsgemm_handle_t h, const CUtensorMap &tmA, const CUtensorMap &tmB
   const int qrc = query_max_units<BN, FT, CG, PROT>(h, &resident);  // (also sets the shared-memory attribute, once per handle)
   if (qrc) return qrc;
   if (units > resident) return FTSGEMM_ERR_UNSUPPORTED;  // the plan was built for more units than can be co-resident
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(units * CG);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
@@ -557,8 +555,7 @@ int run_tc(ftsgemm_handle_t h, const Variant &v, int M, int N, int K, const floa
                                      // worth more to the GEMM's first wave than the residue it evicts: off by default
 #define FT_ENC(bn)                                                                                                          \
   if (BN == bn) {                                                                                                           \
-    cudaLaunchConfig_t ec;                                                                                                  \
-    memset(&ec, 0, sizeof(ec));                                                                                             \
+    cudaLaunchConfig_t ec = {};                                                                                             \
     ec.gridDim = dim3(grid);                                                                                                \
     ec.blockDim = dim3(kEncWarps * 32);                                                                                     \
     ec.stream = stream;                                                                                                     \
@@ -1223,8 +1220,7 @@ int ftsgemm_stats_device(ftsgemm_handle_t h, double *d_out8, void *stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   // a programmatic dependent of the GEMM it reports on, and a programmatic primary of the next launch: the launch chain
   // of back-to-back steps is not broken by the snapshot
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(1);
   cfg.blockDim = dim3(32);
   cfg.stream = stream;
